@@ -1,0 +1,347 @@
+// tcgen05 implementation of the tap-offset convolution (conv_common.cuh), bf16
+// operands, fp32 accumulation in TMEM.
+//
+// GEMM view per work item:  D[128*msub rows (time), nt cols (out channels)]
+//     += sum over taps j, input channels ci of  A_j[row, ci] * W_j[col, ci]
+// where A_j is the SAME channels-last activation tile shifted by tap_off[j] rows.
+//
+//   * A: ONE halo slab per (item, 64-channel K chunk) is brought in by TMA
+//     (rows [q0+min_off, q0+min_off+slab_rows), zero filled outside [0, lin) by the
+//     TMA unit, which is exactly the per-layer zero padding of the reference).
+//     Every tap is then a row-shifted shared-memory matrix descriptor over that
+//     slab: k taps cost one global->shared transfer, not k.
+//   * W: [ntaps][ntot][cin] bf16, K-major; a pipeline stage holds `tb` taps of one
+//     K chunk for one nt-wide column tile.
+//   * D: msub accumulators of 128 x nt fp32 in TMEM, double buffered so the
+//     epilogue of item i overlaps the MMAs of item i+1.
+//
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA
+// issuer (one elected lane), warps 2..9 = epilogue (TMEM -> registers -> fused
+// bias / residual / branch-sum / mean / leaky-ReLU -> global).
+// Persistent: grid = min(items, SMs), static round-robin over items.
+#pragma once
+#include <cuda.h>
+
+#include "conv_common.cuh"
+#include "ptx.cuh"
+
+namespace l2s {
+
+constexpr int kTcThreads = 320;
+constexpr int kTcEpiWarps = 8;
+constexpr int kTcMaxStagesA = 8;
+constexpr int kTcMaxStagesB = 8;
+
+struct TcGeom {
+  int rb;            // bytes per shared-memory operand row: 32 / 64 / 128 (= swizzle span)
+  int kc;            // K chunks per tap (cin_pad * 2 / rb)
+  int k16;           // MMAs (K = 16) per chunk (rb / 32)
+  int nt;            // column tile (MMA N), multiple of 16, <= 256
+  int n_ntiles;      // ntot / nt
+  int msub;          // 128-row accumulators per item
+  int m_items;       // ceil(mrows / (128 * msub))
+  int min_off;       // min(tap_off)
+  int box_rows;      // rows per TMA box of the slab (multiple of 8, <= 256)
+  int n_loads;       // TMA boxes per slab
+  int slab_bytes;    // n_loads * box_rows * rb
+  int sa;            // slab ring depth
+  int tb;            // taps per W stage
+  int n_tstages;     // ceil(ntaps / tb)
+  int bstage_bytes;  // tb * nt * rb
+  int sb;            // W ring depth
+  int tmem_cols;     // power of two >= 2 * msub * nt
+  int total_items;
+  int base_offset_mode;  // 0: descriptor base_offset field left 0; 1: (addr >> 7) & 7
+  uint32_t idesc;
+  int smem_bytes;
+};
+
+struct TcParams {
+  ConvParams c;
+  TcGeom g;
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const ConvParams& p = P.c;
+  const TcGeom& g = P.g;
+
+  // carve dynamic shared memory (1024-byte aligned base for the swizzle pattern)
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* slabA = smem;
+  uint8_t* stageB = slabA + (size_t)g.sa * g.slab_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stageB + (size_t)g.sb * g.bstage_bytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + kTcMaxStagesA;
+  uint64_t* b_full = a_empty + kTcMaxStagesA;
+  uint64_t* b_empty = b_full + kTcMaxStagesB;
+  uint64_t* acc_full = b_empty + kTcMaxStagesB;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+    for (int i = 0; i < g.sa; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < g.sb; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kTcEpiWarps); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_dyn(tmem_slot, (uint32_t)g.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int items_per_b = g.m_items * g.n_ntiles;
+  const int acc_cols = g.msub * g.nt;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int ia = 0, ib = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int item = blockIdx.x; item < g.total_items; item += gridDim.x) {
+        const int b = item / items_per_b;
+        const int rem = item - b * items_per_b;
+        const int mi = rem / g.n_ntiles;
+        const int ni = rem - mi * g.n_ntiles;
+        const int row0 = mi * 128 * g.msub + g.min_off;
+        for (int kc = 0; kc < g.kc; ++kc) {
+          mbar_wait(&a_empty[ia], pa ^ 1u);
+          mbar_expect_tx(&a_full[ia], (uint32_t)g.slab_bytes);
+          uint8_t* dst = slabA + (size_t)ia * g.slab_bytes;
+          for (int l = 0; l < g.n_loads; ++l)
+            tma_load_3d(dst + (size_t)l * g.box_rows * g.rb, &tmA, &a_full[ia], kc * (g.rb >> 1),
+                        row0 + l * g.box_rows, b);
+          if (++ia == g.sa) { ia = 0; pa ^= 1u; }
+          for (int ts = 0; ts < g.n_tstages; ++ts) {
+            mbar_wait(&b_empty[ib], pb ^ 1u);
+            mbar_expect_tx(&b_full[ib], (uint32_t)g.bstage_bytes);
+            tma_load_3d(stageB + (size_t)ib * g.bstage_bytes, &tmW, &b_full[ib], kc * (g.rb >> 1), ni * g.nt,
+                        ts * g.tb);
+            if (++ib == g.sb) { ib = 0; pb ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      const uint64_t tmpl = umma_desc_template((uint32_t)g.rb);
+      int ia = 0, ib = 0;
+      uint32_t pa = 0, pb = 0;
+      uint32_t pacc[2] = {0u, 0u};
+      int buf = 0;
+      for (int item = blockIdx.x; item < g.total_items; item += gridDim.x) {
+        mbar_wait(&acc_empty[buf], pacc[buf] ^ 1u);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + (uint32_t)(buf * acc_cols);
+        for (int kc = 0; kc < g.kc; ++kc) {
+          mbar_wait(&a_full[ia], pa);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(slabA + (size_t)ia * g.slab_bytes);
+          for (int ts = 0; ts < g.n_tstages; ++ts) {
+            mbar_wait(&b_full[ib], pb);
+            tc_fence_after();
+            const uint32_t b_base = smem_u32(stageB + (size_t)ib * g.bstage_bytes);
+            const int t_end = min(g.tb, p.ntaps - ts * g.tb);
+            for (int t = 0; t < t_end; ++t) {
+              const int tap = ts * g.tb + t;
+              const uint32_t a_tap = a_base + (uint32_t)((p.tap_off[tap] - g.min_off) * g.rb);
+              const uint32_t b_tap = b_base + (uint32_t)(t * g.nt * g.rb);
+              for (int s = 0; s < g.msub; ++s) {
+                const uint32_t a_sub = a_tap + (uint32_t)(s * 128 * g.rb);
+                for (int k = 0; k < g.k16; ++k) {
+                  const uint32_t a_addr = a_sub + (uint32_t)(k * 32);
+                  uint64_t da = umma_desc(tmpl, a_addr);
+                  if (g.base_offset_mode == 1) da |= (uint64_t)((a_addr >> 7) & 7u) << 49;
+                  const uint64_t db = umma_desc(tmpl, b_tap + (uint32_t)(k * 32));
+                  const uint32_t accumulate = (kc | tap | k) != 0 ? 1u : 0u;
+                  umma_bf16(d_base + (uint32_t)(s * g.nt), da, db, g.idesc, accumulate);
+                }
+              }
+            }
+            umma_commit(&b_empty[ib]);  // W stage free once these MMAs retire
+            if (++ib == g.sb) { ib = 0; pb ^= 1u; }
+          }
+          umma_commit(&a_empty[ia]);    // slab free
+          if (++ia == g.sa) { ia = 0; pa ^= 1u; }
+        }
+        umma_commit(&acc_full[buf]);    // accumulators complete -> epilogue
+        pacc[buf] ^= 1u;
+        buf ^= 1;
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue
+    const int quad = warp & 3;            // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;     // two warps share a quadrant, alternate column groups
+    const int groups_per_sub = g.nt >> 4;
+    const int n_groups = g.msub * groups_per_sub;
+    uint32_t pacc[2] = {0u, 0u};
+    int buf = 0;
+    for (int item = blockIdx.x; item < g.total_items; item += gridDim.x) {
+      const int b = item / items_per_b;
+      const int rem = item - b * items_per_b;
+      const int mi = rem / g.n_ntiles;
+      const int ni = rem - mi * g.n_ntiles;
+      mbar_wait(&acc_full[buf], pacc[buf]);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * acc_cols);
+      for (int grp = half; grp < n_groups; grp += 2) {
+        const int s = grp / groups_per_sub;
+        const int cg = grp - s * groups_per_sub;
+        uint32_t r[16];
+        tmem_ld16(t_base + (uint32_t)(s * g.nt + cg * 16), r);
+        tmem_ld_wait();
+        const int q = (mi * g.msub + s) * 128 + quad * 32 + lane;
+        if (q < p.mrows) {
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+          conv_epilogue<__nv_bfloat16, 16>(p, b, q, ni * g.nt + cg * 16, v);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      pacc[buf] ^= 1u;
+      buf ^= 1;
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc_dyn(tmem_base, (uint32_t)g.tmem_cols);
+}
+
+// ------------------------------------------------------------------ host side
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_tmapEncodeTiled tmap_encoder() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_tmapEncodeTiled>(ptr);
+  }
+  return fn;
+}
+
+// bf16 tensor [d2][d1][d0] (d0 contiguous), box [b2=1 or tb][b1][b0], swizzle span = b0 * 2 bytes.
+inline bool make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0,
+                              uint32_t b1, uint32_t b2) {
+  PFN_tmapEncodeTiled enc = tmap_encoder();
+  if (!enc) return false;
+  const cuuint64_t dims[3] = {d0, d1, d2};
+  const cuuint64_t strides[2] = {d0 * 2ull, d0 * d1 * 2ull};
+  const cuuint32_t box[3] = {b0, b1, b2};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const uint32_t rb = b0 * 2;
+  const CUtensorMapSwizzle sw = rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                           : CU_TENSOR_MAP_SWIZZLE_32B;
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+struct TcTune {
+  int max_msub = 8;
+  int slab_cap = 40960;        // bytes per slab
+  int smem_budget = 220 * 1024;
+  int base_offset_mode = 0;
+  int max_ctas = 0;            // 0: number of SMs
+};
+
+// Shape-only planning (no device pointers): valid for any batch with the same (lin, mrows).
+inline bool tc_plan(const ConvParams& c, int batch, const TcTune& tune, TcGeom* out) {
+  TcGeom g{};
+  if (c.cin_pad % 16 != 0 || c.ntot % 16 != 0 || c.ntaps < 1 || c.ntaps > kMaxTaps) return false;
+  g.rb = (c.cin_pad >= 64 ? 64 : c.cin_pad) * 2;
+  if (g.rb != 32 && g.rb != 64 && g.rb != 128) return false;
+  if ((c.cin_pad * 2) % g.rb != 0) return false;
+  g.kc = c.cin_pad * 2 / g.rb;
+  g.k16 = g.rb / 32;
+  g.nt = c.ntot <= 256 ? c.ntot : 256;
+  while (c.ntot % g.nt != 0) g.nt -= 16;
+  g.n_ntiles = c.ntot / g.nt;
+  int mn = c.tap_off[0], mx = c.tap_off[0];
+  for (int j = 1; j < c.ntaps; ++j) { mn = c.tap_off[j] < mn ? c.tap_off[j] : mn; mx = c.tap_off[j] > mx ? c.tap_off[j] : mx; }
+  g.min_off = mn;
+  const int span = mx - mn;
+  int msub = 256 / g.nt;
+  if (msub < 1) msub = 1;
+  if (msub > tune.max_msub) msub = tune.max_msub;
+  const int need = (c.mrows + 127) / 128;
+  if (msub > need) msub = need;
+  while (msub > 1 && (msub * 128 + span) * g.rb > tune.slab_cap) --msub;
+  g.msub = msub;
+  g.m_items = (c.mrows + 128 * msub - 1) / (128 * msub);
+  const int slab_rows = msub * 128 + span;
+  g.n_loads = (slab_rows + 255) / 256;
+  g.box_rows = (((slab_rows + g.n_loads - 1) / g.n_loads) + 7) & ~7;
+  g.slab_bytes = g.n_loads * g.box_rows * g.rb;
+  // W stage: a few taps per stage when a single tap is tiny
+  int tb = 1;
+  while (tb < c.ntaps && tb < 16 && (tb * 2) * g.nt * g.rb <= 16384) tb *= 2;
+  if (tb > c.ntaps) tb = c.ntaps;
+  g.tb = tb;
+  g.n_tstages = (c.ntaps + tb - 1) / tb;
+  g.bstage_bytes = tb * g.nt * g.rb;
+  // ring depths within the shared-memory budget
+  const int bar_bytes = 1024 + 256;  // alignment slack + barriers
+  int sa = g.kc + 1 < kTcMaxStagesA ? g.kc + 1 : kTcMaxStagesA;
+  if (sa < 2) sa = 2;
+  int sb = 4;
+  while (sa > 2 && sa * g.slab_bytes + sb * g.bstage_bytes + bar_bytes > tune.smem_budget) --sa;
+  while (sb > 2 && sa * g.slab_bytes + sb * g.bstage_bytes + bar_bytes > tune.smem_budget) --sb;
+  if (sa * g.slab_bytes + sb * g.bstage_bytes + bar_bytes > tune.smem_budget) return false;
+  while (sb < kTcMaxStagesB && sb < g.n_tstages * g.kc &&
+         sa * g.slab_bytes + (sb + 1) * g.bstage_bytes + bar_bytes <= tune.smem_budget && (sb + 1) * g.bstage_bytes <= 96 * 1024)
+    ++sb;
+  g.sa = sa;
+  g.sb = sb;
+  g.smem_bytes = sa * g.slab_bytes + sb * g.bstage_bytes + bar_bytes;
+  int cols = 32;
+  while (cols < 2 * msub * g.nt) cols <<= 1;
+  if (cols > 512) return false;
+  g.tmem_cols = cols;
+  g.total_items = batch * g.m_items * g.n_ntiles;
+  g.base_offset_mode = tune.base_offset_mode;
+  g.idesc = umma_idesc_bf16(128u, (uint32_t)g.nt);
+  *out = g;
+  return true;
+}
+
+inline cudaError_t launch_conv_tc(const ConvParams& c, const TcGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmW,
+                                  int num_ctas, cudaStream_t stream) {
+  static int configured_smem = 0;
+  if (g.smem_bytes > configured_smem) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    configured_smem = 227 * 1024;
+  }
+  TcParams P;
+  P.c = c;
+  P.g = g;
+  int grid = g.total_items < num_ctas ? g.total_items : num_ctas;
+  if (grid < 1) grid = 1;
+  conv_tc_kernel<<<grid, kTcThreads, g.smem_bytes, stream>>>(tmA, tmW, P);
+  return cudaGetLastError();
+}
+
+}  // namespace l2s

@@ -1,0 +1,246 @@
+// Conditioning front end and waveform head: the HBM / latency bound ends of the
+// path, written as plain coalesced CUDA-core kernels.
+//
+//   spk_project_kernel   spkr Linear(256,128)                 models_multi_input.py:37,80
+//   cond_multi_kernel    dict gather -> ConvTranspose1d(E,E,4,2,1) -> exact GELU -> fc
+//                        -> concat [mel | code feats | speaker] channels-last
+//                                                             models_multi_input.py:67-82
+//   cond_unit_kernel     unit-only parent: [dict[code] | spkr_table[id]]
+//                                                             speech-resynthesis/models.py:188,214-217
+//   post_kernel          leaky_relu(0.01) -> conv_post(k=7) -> tanh (+ int16)
+//                                                             speech-resynthesis/models.py:110-112
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace l2s {
+
+template <typename Ta>
+__device__ __forceinline__ Ta to_act(float v);
+template <>
+__device__ __forceinline__ float to_act<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 to_act<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float load_mel(const void* mel, int dtype, long long i) {
+  if (dtype == 0) return reinterpret_cast<const float*>(mel)[i];
+  if (dtype == 1) return __half2float(reinterpret_cast<const __half*>(mel)[i]);
+  return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(mel)[i]);
+}
+
+// out[b][c] = bias[c] + sum_k spkr[b][k] * W[c][k].  One block per utterance.
+__global__ void spk_project_kernel(const float* __restrict__ spkr, const float* __restrict__ w,
+                                   const float* __restrict__ bias, float* __restrict__ out, int spk_dim, int e) {
+  extern __shared__ float s_in[];
+  const int b = blockIdx.x;
+  for (int k = threadIdx.x; k < spk_dim; k += blockDim.x) s_in[k] = spkr[(long long)b * spk_dim + k];
+  __syncthreads();
+  for (int c = threadIdx.x; c < e; c += blockDim.x) {
+    float acc = bias[c];
+    const float* wr = w + (long long)c * spk_dim;
+    for (int k = 0; k < spk_dim; ++k) acc = fmaf(s_in[k], wr[k], acc);
+    out[(long long)b * e + c] = acc;
+  }
+}
+
+struct CondParams {
+  const long long* code;   // (B,U)
+  const void* mel;         // (B,num_mels,T)
+  int mel_dtype;
+  const float* spk_vec;    // (B,E) projected speaker vectors (multi) or null
+  const float* dict;       // (num_embeddings,E)
+  const float* wt;         // unit ConvT weights repacked [4][E_in][E_out]
+  const float* wt_bias;    // [E]
+  const float* fc_t;       // fc weight transposed [E_in][E_out]
+  const float* fc_bias;    // [E]
+  void* cond;              // (B,T,cin_pad) channels-last, activation dtype
+  float* embed_tap;        // optional (B,U,E): the raw gathered rows (bit-exactness test hook)
+  int* err_flag;           // sticky out-of-range flag (host mapped)
+  int batch, units, frames, e, num_mels, num_embeddings, cin_pad, has_spk;
+};
+
+constexpr int kCondFrames = 8;   // frames per block (even start)
+constexpr int kCondE = 128;      // embedding_dim this kernel is specialised for
+
+template <typename Ta>
+__global__ void __launch_bounds__(kCondE) cond_multi_kernel(const CondParams p) {
+  __shared__ float s_emb[kCondFrames / 2 + 2][kCondE];   // units i0-1 .. i0+4
+  __shared__ float s_act[kCondFrames][kCondE];
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * kCondFrames;
+  const int i0 = t0 >> 1;
+  const int c = threadIdx.x;
+  Ta* cond = reinterpret_cast<Ta*>(p.cond) + ((long long)b * p.frames) * p.cin_pad;
+
+  // (1) gather: an exact row copy of the unit table
+#pragma unroll
+  for (int r = 0; r < kCondFrames / 2 + 2; ++r) {
+    const int i = i0 - 1 + r;
+    float v = 0.f;
+    if (i >= 0 && i < p.units) {
+      long long id = p.code[(long long)b * p.units + i];
+      if (id < 0 || id >= p.num_embeddings) {
+        if (c == 0) atomicOr(p.err_flag, 1);
+        id = id < 0 ? 0 : p.num_embeddings - 1;
+      }
+      v = p.dict[id * kCondE + c];
+      if (p.embed_tap && r >= 1 && r <= kCondFrames / 2) p.embed_tap[((long long)b * p.units + i) * kCondE + c] = v;
+    }
+    s_emb[r][c] = v;
+  }
+  __syncthreads();
+
+  // (2) ConvTranspose1d(E,E,4,stride 2,pad 1): out[2i] = W1 x[i] + W3 x[i-1], out[2i+1] = W2 x[i] + W0 x[i+1]
+  float acc[kCondFrames];
+  const float bias = p.wt_bias[c];
+#pragma unroll
+  for (int f = 0; f < kCondFrames; ++f) acc[f] = bias;
+  for (int ci = 0; ci < kCondE; ++ci) {
+    const float w0 = p.wt[(0 * kCondE + ci) * kCondE + c];
+    const float w1 = p.wt[(1 * kCondE + ci) * kCondE + c];
+    const float w2 = p.wt[(2 * kCondE + ci) * kCondE + c];
+    const float w3 = p.wt[(3 * kCondE + ci) * kCondE + c];
+#pragma unroll
+    for (int h = 0; h < kCondFrames / 2; ++h) {
+      const float xm = s_emb[h][ci], x0 = s_emb[h + 1][ci], xp = s_emb[h + 2][ci];
+      acc[2 * h] = fmaf(x0, w1, fmaf(xm, w3, acc[2 * h]));
+      acc[2 * h + 1] = fmaf(x0, w2, fmaf(xp, w0, acc[2 * h + 1]));
+    }
+  }
+  // (3) exact (erf) GELU
+#pragma unroll
+  for (int f = 0; f < kCondFrames; ++f) {
+    const float y = acc[f];
+    s_act[f][c] = 0.5f * y * (1.0f + erff(y * 0.70710678118654752440f));
+  }
+  __syncthreads();
+  // (4) fc
+  const float fb = p.fc_bias[c];
+#pragma unroll
+  for (int f = 0; f < kCondFrames; ++f) acc[f] = fb;
+  for (int k = 0; k < kCondE; ++k) {
+    const float w = p.fc_t[k * kCondE + c];
+#pragma unroll
+    for (int f = 0; f < kCondFrames; ++f) acc[f] = fmaf(s_act[f][k], w, acc[f]);
+  }
+  // (5) concat: [mel | code feats | speaker | zero pad]
+  const float sv = p.has_spk ? p.spk_vec[(long long)b * kCondE + c] : 0.f;
+  const int spk_base = p.num_mels + kCondE;
+#pragma unroll
+  for (int f = 0; f < kCondFrames; ++f) {
+    const int t = t0 + f;
+    if (t >= p.frames) break;
+    Ta* row = cond + (long long)t * p.cin_pad;
+    row[p.num_mels + c] = to_act<Ta>(acc[f]);
+    if (p.has_spk) row[spk_base + c] = to_act<Ta>(sv);
+  }
+  const int tail0 = spk_base + (p.has_spk ? kCondE : 0);
+  for (int idx = c; idx < kCondFrames * (p.cin_pad - tail0); idx += kCondE) {
+    const int f = idx / (p.cin_pad - tail0), ch = tail0 + idx % (p.cin_pad - tail0);
+    if (t0 + f < p.frames) cond[(long long)(t0 + f) * p.cin_pad + ch] = to_act<Ta>(0.f);
+  }
+  for (int idx = c; idx < kCondFrames * p.num_mels; idx += kCondE) {
+    const int m = idx / kCondFrames, f = idx % kCondFrames;
+    const int t = t0 + f;
+    if (t < p.frames)
+      cond[(long long)t * p.cin_pad + m] =
+          to_act<Ta>(load_mel(p.mel, p.mel_dtype, ((long long)b * p.num_mels + m) * p.frames + t));
+  }
+}
+
+// Unit-only variant: cond[b][u] = [dict[code[b][u]] | spk_table[id[b]] | 0 pad].
+struct CondUnitParams {
+  const long long* code;
+  const long long* spk_id;     // (B) or null
+  const float* dict;
+  const float* spk_table;
+  void* cond;
+  float* embed_tap;
+  int* err_flag;
+  int batch, units, e, num_embeddings, num_speakers, cin_pad, has_spk;
+};
+
+template <typename Ta>
+__global__ void cond_unit_kernel(const CondUnitParams p) {
+  const int b = blockIdx.y;
+  const int u = blockIdx.x;
+  Ta* row = reinterpret_cast<Ta*>(p.cond) + ((long long)b * p.units + u) * p.cin_pad;
+  long long id = p.code[(long long)b * p.units + u];
+  if (id < 0 || id >= p.num_embeddings) {
+    if (threadIdx.x == 0) atomicOr(p.err_flag, 1);
+    id = id < 0 ? 0 : p.num_embeddings - 1;
+  }
+  long long sid = 0;
+  if (p.has_spk) {
+    sid = p.spk_id[b];
+    if (sid < 0 || sid >= p.num_speakers) {
+      if (threadIdx.x == 0) atomicOr(p.err_flag, 2);
+      sid = sid < 0 ? 0 : p.num_speakers - 1;
+    }
+  }
+  for (int c = threadIdx.x; c < p.cin_pad; c += blockDim.x) {
+    float v = 0.f;
+    if (c < p.e) {
+      v = p.dict[id * p.e + c];
+      if (p.embed_tap) p.embed_tap[((long long)b * p.units + u) * p.e + c] = v;
+    } else if (p.has_spk && c < 2 * p.e) {
+      v = p.spk_table[sid * p.e + (c - p.e)];
+    }
+    row[c] = to_act<Ta>(v);
+  }
+}
+
+// Waveform head.  in: fp32 channels-last (B,L,C) MRF mean of the last stage.
+struct PostParams {
+  const float* in;
+  const float* w;      // [7][C]
+  float bias;
+  float* out;          // (B,L) or null
+  int16_t* out_i16;    // (B,L) or null
+  int batch, len, c;
+};
+
+constexpr int kPostTile = 256;
+
+__global__ void __launch_bounds__(kPostTile) post_kernel(const PostParams p) {
+  extern __shared__ float s_x[];                 // [(kPostTile + 6)][C + 1]
+  __shared__ float s_w[7 * 64];
+  const int b = blockIdx.y;
+  const int l0 = blockIdx.x * kPostTile;
+  const int c = p.c, pitch = c + 1;
+  for (int i = threadIdx.x; i < 7 * c; i += kPostTile) s_w[i] = p.w[i];
+  const float* in = p.in + (long long)b * p.len * c;
+  const int n = (kPostTile + 6) * c;
+  for (int i = threadIdx.x; i < n; i += kPostTile) {
+    const int r = i / c, ch = i - r * c;
+    const int l = l0 - 3 + r;
+    float v = 0.f;
+    if (l >= 0 && l < p.len) {
+      v = in[(long long)l * c + ch];
+      v = v > 0.f ? v : v * 0.01f;               // F.leaky_relu default slope, models.py:110
+    }
+    s_x[r * pitch + ch] = v;
+  }
+  __syncthreads();
+  const int l = l0 + threadIdx.x;
+  if (l >= p.len) return;
+  float acc = p.bias;
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    const float* xr = s_x + (threadIdx.x + j) * pitch;
+    const float* wr = s_w + j * c;
+    for (int ch = 0; ch < c; ++ch) acc = fmaf(xr[ch], wr[ch], acc);
+  }
+  const float y = tanhf(acc);
+  const long long o = (long long)b * p.len + l;
+  if (p.out) p.out[o] = y;
+  if (p.out_i16) {
+    // inference.py:79-81: audio * 32768 -> int16 (astype truncates toward zero); saturate instead of wrapping
+    float s = y * 32768.0f;
+    s = fminf(fmaxf(s, -32768.0f), 32767.0f);
+    p.out_i16[o] = (int16_t)s;
+  }
+}
+
+}  // namespace l2s

@@ -1,0 +1,804 @@
+// C ABI (include/l2s_vocoder.h) of the B200-native multi_input_vocoder generator
+// forward: layer table, weight repacking, workspace carving and the launch
+// sequence that replaces MelCodeGenerator.forward (models_multi_input.py:60-97) /
+// Generator.forward (speech-resynthesis/models.py:98-114).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/l2s_vocoder.h"
+#include "conv_common.cuh"
+#include "conv_simt.cuh"
+#include "conv_tc.cuh"
+#include "frontend.cuh"
+
+using namespace l2s;
+
+namespace {
+
+// ------------------------------------------------------------------ knobs
+struct Knobs {
+  long long force_simt = 0;        // bf16 mode: run the CUDA-core kernel on the bf16 operands
+  long long stop_after_stage = -1; // >= 0: stop after that MRF stage (taps stay valid)
+  long long stop_after_pre = 0;    // stop after conv_pre
+  long long base_offset_mode = 0;
+  long long max_msub = 8;
+  long long slab_cap = 40960;
+  long long max_ctas = 0;
+  long long embed_tap = 0;
+  long long layer_events = 0;      // record a cudaEvent pair around every launch of the next forwards
+};
+Knobs g_knobs;
+
+inline uint16_t f2bf(float f) {  // round to nearest even
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct ConvLayer {
+  std::string name;
+  bool transposed = false;
+  int cin = 0, cout = 0, k = 0, dil = 1, up = 1, pad = 0;
+  int cin_pad = 0, ntaps = 0, ntot = 0;
+  int tap_off[kMaxTaps] = {0};
+  long long out_shift = 0;
+  void* w_dev = nullptr;       // [ntaps][ntot][cin_pad] fp32 or bf16
+  float* bias_dev = nullptr;   // [ntot]
+  CUtensorMap tmW;
+  bool has_tmW = false;
+  int tm_nt = 0, tm_tb = 0;
+};
+
+}  // namespace
+
+struct l2s_vocoder {
+  l2s_config cfg;
+  std::map<std::string, std::vector<float>> weights;
+  std::map<std::string, long long> expected;   // name -> numel
+  std::vector<ConvLayer> convs;                // conv_pre, then per stage: ups, 3 x 3 x (c1, c2)
+  int conv_pre = -1;
+  std::vector<int> ups;                        // index into convs
+  std::vector<std::vector<std::vector<int>>> rb_c1, rb_c2;  // [stage][branch][dil]
+  std::vector<int> stage_ch;
+  bool finalized = false;
+  int device = -1, num_sms = 0;
+  // device-side small weights
+  float *d_dict = nullptr, *d_spk_w = nullptr, *d_spk_b = nullptr, *d_wt = nullptr, *d_wt_b = nullptr, *d_fc_t = nullptr,
+        *d_fc_b = nullptr, *d_post_w = nullptr;
+  float post_bias = 0.f;
+  int* err_host = nullptr;   // mapped pinned
+  int* err_dev = nullptr;
+  std::vector<void*> dev_allocs;
+  std::string err;
+  std::mutex mu;
+  // last-forward bookkeeping for taps
+  struct Tap { const void* ptr; long long numel; bool act; };
+  std::map<std::string, Tap> taps;
+  // optional per-launch timing (l2s_debug_set("layer_events", 1))
+  struct Timed { std::string name; cudaEvent_t a, b; double flops; };
+  std::vector<Timed> timed;
+  size_t timed_used = 0;
+};
+
+namespace {
+
+int fail(l2s_vocoder* v, int code, const std::string& msg) {
+  if (v) v->err = msg;
+  return code;
+}
+
+bool is_bf16(const l2s_vocoder* v) { return v->cfg.precision == L2S_PREC_BF16; }
+size_t act_size(const l2s_vocoder* v) { return is_bf16(v) ? 2 : 4; }
+
+int hop_of(const l2s_config& c) {
+  int h = 1;
+  for (int i = 0; i < c.n_ups; ++i) h *= c.up_rates[i];
+  return h;
+}
+
+ConvLayer make_conv(const std::string& name, int cin, int cout, int k, int dil) {
+  ConvLayer L;
+  L.name = name;
+  L.cin = cin; L.cout = cout; L.k = k; L.dil = dil;
+  L.cin_pad = cin <= 64 ? (int)align_up(cin, 16) : (int)align_up(cin, 64);
+  L.ntaps = k;
+  L.ntot = cout;
+  for (int j = 0; j < k; ++j) L.tap_off[j] = (j - (k - 1) / 2) * dil;
+  L.out_shift = 0;
+  return L;
+}
+
+ConvLayer make_convT(const std::string& name, int cin, int cout, int k, int u, int p) {
+  ConvLayer L;
+  L.name = name;
+  L.transposed = true;
+  L.cin = cin; L.cout = cout; L.k = k; L.up = u; L.pad = p;
+  L.cin_pad = cin <= 64 ? (int)align_up(cin, 16) : (int)align_up(cin, 64);
+  L.ntaps = (k + u - 1) / u;
+  L.ntot = u * cout;
+  for (int m = 0; m < L.ntaps; ++m) L.tap_off[m] = -m;
+  L.out_shift = -(long long)p * cout;
+  return L;
+}
+
+int build_layers(l2s_vocoder* v) {
+  const l2s_config& c = v->cfg;
+  if (c.n_ups < 1 || c.n_ups > L2S_MAX_UPS || c.n_rk < 1 || c.n_rk > L2S_MAX_RK || c.n_dil < 1 || c.n_dil > L2S_MAX_DIL)
+    return fail(v, L2S_ERR_INVALID, "bad layer counts");
+  if (c.precision != L2S_PREC_FP32 && c.precision != L2S_PREC_BF16) return fail(v, L2S_ERR_INVALID, "bad precision");
+  if (c.embedding_dim != kCondE) return fail(v, L2S_ERR_UNSUPPORTED, "embedding_dim must be 128");
+  if (c.num_embeddings < 1) return fail(v, L2S_ERR_INVALID, "num_embeddings");
+  const int E = c.embedding_dim;
+  int in_dim;
+  if (c.variant == L2S_VARIANT_MULTI_INPUT) {
+    if (c.num_mels < 1) return fail(v, L2S_ERR_INVALID, "num_mels");
+    if (c.multispkr && c.spk_dim <= 0) return fail(v, L2S_ERR_UNSUPPORTED, "multi-input needs embedder_dim (speaker Linear)");
+    in_dim = c.num_mels + E + (c.multispkr ? E : 0);
+  } else if (c.variant == L2S_VARIANT_UNIT_ONLY) {
+    if (c.multispkr && c.num_speakers < 1) return fail(v, L2S_ERR_INVALID, "num_speakers");
+    in_dim = E + (c.multispkr ? E : 0);
+  } else {
+    return fail(v, L2S_ERR_INVALID, "bad variant");
+  }
+  if (c.model_in_dim != in_dim) {
+    char b[128];
+    snprintf(b, sizeof b, "model_in_dim %d does not match the conditioning channels %d", c.model_in_dim, in_dim);
+    return fail(v, L2S_ERR_SHAPE, b);
+  }
+  int ch = c.up_init_ch;
+  if (ch % 16 != 0) return fail(v, L2S_ERR_UNSUPPORTED, "upsample_initial_channel must be a multiple of 16");
+  v->convs.clear();
+  v->convs.push_back(make_conv("conv_pre", in_dim, ch, 7, 1));
+  v->conv_pre = 0;
+  v->expected["conv_pre.weight"] = (long long)ch * in_dim * 7;
+  v->expected["conv_pre.bias"] = ch;
+  for (int i = 0; i < c.n_ups; ++i) {
+    const int u = c.up_rates[i], k = c.up_ksizes[i];
+    if (u < 1 || k < u || (k - u) % 2 != 0) return fail(v, L2S_ERR_UNSUPPORTED, "upsample kernel/rate: need k >= u and k-u even");
+    if ((k + u - 1) / u > kMaxTaps) return fail(v, L2S_ERR_UNSUPPORTED, "too many polyphase taps");
+    if (ch % 2 != 0 || (ch / 2) % 16 != 0) return fail(v, L2S_ERR_UNSUPPORTED, "stage channels must stay multiples of 16");
+    char nm[64];
+    snprintf(nm, sizeof nm, "ups.%d", i);
+    v->convs.push_back(make_convT(nm, ch, ch / 2, k, u, (k - u) / 2));
+    v->ups.push_back((int)v->convs.size() - 1);
+    v->expected[std::string(nm) + ".weight"] = (long long)ch * (ch / 2) * k;
+    v->expected[std::string(nm) + ".bias"] = ch / 2;
+    ch /= 2;
+    v->stage_ch.push_back(ch);
+    std::vector<std::vector<int>> s1, s2;
+    for (int j = 0; j < c.n_rk; ++j) {
+      const int rk = c.rk_sizes[j];
+      if (rk < 1 || rk > kMaxTaps || rk % 2 == 0) return fail(v, L2S_ERR_UNSUPPORTED, "resblock kernel sizes must be odd and <= 16");
+      std::vector<int> b1, b2;
+      for (int m = 0; m < c.n_dil; ++m) {
+        const int n = i * c.n_rk + j;
+        snprintf(nm, sizeof nm, "resblocks.%d.convs1.%d", n, m);
+        v->convs.push_back(make_conv(nm, ch, ch, rk, c.rk_dils[j][m]));
+        b1.push_back((int)v->convs.size() - 1);
+        v->expected[std::string(nm) + ".weight"] = (long long)ch * ch * rk;
+        v->expected[std::string(nm) + ".bias"] = ch;
+        snprintf(nm, sizeof nm, "resblocks.%d.convs2.%d", n, m);
+        v->convs.push_back(make_conv(nm, ch, ch, rk, 1));
+        b2.push_back((int)v->convs.size() - 1);
+        v->expected[std::string(nm) + ".weight"] = (long long)ch * ch * rk;
+        v->expected[std::string(nm) + ".bias"] = ch;
+      }
+      s1.push_back(b1);
+      s2.push_back(b2);
+    }
+    v->rb_c1.push_back(s1);
+    v->rb_c2.push_back(s2);
+  }
+  if (ch > 64) return fail(v, L2S_ERR_UNSUPPORTED, "final channel count must be <= 64");
+  v->expected["conv_post.weight"] = (long long)ch * 7;
+  v->expected["conv_post.bias"] = 1;
+  v->expected["dict.weight"] = (long long)c.num_embeddings * E;
+  if (c.variant == L2S_VARIANT_MULTI_INPUT) {
+    v->expected["layer.0.weight"] = (long long)E * E * 4;
+    v->expected["layer.0.bias"] = E;
+    v->expected["fc.weight"] = (long long)E * E;
+    v->expected["fc.bias"] = E;
+    if (c.multispkr) {
+      v->expected["spkr.weight"] = (long long)E * c.spk_dim;
+      v->expected["spkr.bias"] = E;
+    }
+  } else if (c.multispkr) {
+    v->expected["spkr.weight"] = (long long)c.num_speakers * E;
+  }
+  return L2S_OK;
+}
+
+template <typename T>
+T* dev_upload(l2s_vocoder* v, const T* host, size_t n, cudaError_t* e) {
+  void* d = nullptr;
+  *e = cudaMalloc(&d, n * sizeof(T) > 0 ? n * sizeof(T) : 16);
+  if (*e != cudaSuccess) return nullptr;
+  v->dev_allocs.push_back(d);
+  *e = cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice);
+  return reinterpret_cast<T*>(d);
+}
+
+// [ntaps][ntot][cin_pad] from the PyTorch layouts.
+void pack_conv(const ConvLayer& L, const std::vector<float>& w, const std::vector<float>& b, std::vector<float>* pw,
+               std::vector<float>* pb) {
+  pw->assign((size_t)L.ntaps * L.ntot * L.cin_pad, 0.f);
+  pb->assign((size_t)L.ntot, 0.f);
+  if (!L.transposed) {
+    // Conv1d weight (Cout, Cin, k)
+    for (int co = 0; co < L.cout; ++co)
+      for (int ci = 0; ci < L.cin; ++ci)
+        for (int j = 0; j < L.k; ++j)
+          (*pw)[((size_t)j * L.ntot + co) * L.cin_pad + ci] = w[((size_t)co * L.cin + ci) * L.k + j];
+    for (int co = 0; co < L.cout; ++co) (*pb)[co] = b[co];
+  } else {
+    // ConvTranspose1d weight (Cin, Cout, k); column r*Cout+co of tap m holds W[ci][co][r + m*u]
+    for (int m = 0; m < L.ntaps; ++m)
+      for (int r = 0; r < L.up; ++r) {
+        const int j = r + m * L.up;
+        if (j >= L.k) continue;
+        for (int co = 0; co < L.cout; ++co)
+          for (int ci = 0; ci < L.cin; ++ci)
+            (*pw)[((size_t)m * L.ntot + r * L.cout + co) * L.cin_pad + ci] = w[((size_t)ci * L.cout + co) * L.k + j];
+      }
+    for (int r = 0; r < L.up; ++r)
+      for (int co = 0; co < L.cout; ++co) (*pb)[(size_t)r * L.cout + co] = b[co];
+  }
+}
+
+TcTune current_tune(const l2s_vocoder* v) {
+  TcTune t;
+  t.max_msub = (int)g_knobs.max_msub;
+  t.slab_cap = (int)g_knobs.slab_cap;
+  t.base_offset_mode = (int)g_knobs.base_offset_mode;
+  t.max_ctas = g_knobs.max_ctas > 0 ? (int)g_knobs.max_ctas : (v ? v->num_sms : 148);
+  return t;
+}
+
+void timed_begin(l2s_vocoder* v, cudaStream_t st, const std::string& name, double flops) {
+  if (!g_knobs.layer_events) return;
+  if (v->timed_used == v->timed.size()) {
+    l2s_vocoder::Timed t;
+    cudaEventCreate(&t.a);
+    cudaEventCreate(&t.b);
+    v->timed.push_back(t);
+  }
+  l2s_vocoder::Timed& t = v->timed[v->timed_used];
+  t.name = name;
+  t.flops = flops;
+  cudaEventRecord(t.a, st);
+}
+void timed_end(l2s_vocoder* v, cudaStream_t st) {
+  if (!g_knobs.layer_events) return;
+  cudaEventRecord(v->timed[v->timed_used].b, st);
+  ++v->timed_used;
+}
+
+// One conv launch in the handle's precision mode.
+int run_conv(l2s_vocoder* v, ConvLayer& L, cudaStream_t st, int batch, int lin, const void* in, float* out_raw,
+             void* out_act, const float* res, const float* acc_in, float div, float slope) {
+  ConvParams p{};
+  p.in = in;
+  p.w = L.w_dev;
+  p.bias = L.bias_dev;
+  p.out_raw = out_raw;
+  p.out_act = out_act;
+  p.res = res;
+  p.acc_in = acc_in;
+  p.batch = batch;
+  p.lin = lin;
+  p.cin_pad = L.cin_pad;
+  p.ntaps = L.ntaps;
+  p.ntot = L.ntot;
+  p.mrows = L.transposed ? lin + 1 : lin;
+  for (int j = 0; j < L.ntaps; ++j) p.tap_off[j] = L.tap_off[j];
+  p.out_shift = L.out_shift;
+  p.out_valid = (long long)lin * L.up * L.cout;
+  p.div = div;
+  p.slope = slope;
+  cudaError_t e;
+  timed_begin(v, st, L.name, 2.0 * L.cin * L.cout * L.k * (double)batch * lin);
+  if (!is_bf16(v)) {
+    e = launch_conv_simt<float>(p, st);
+  } else if (g_knobs.force_simt) {
+    e = launch_conv_simt<__nv_bfloat16>(p, st);
+  } else {
+    TcTune tune = current_tune(v);
+    TcGeom g;
+    if (!tc_plan(p, batch, tune, &g)) return fail(v, L2S_ERR_UNSUPPORTED, "no tcgen05 plan for " + L.name);
+    if (!L.has_tmW || L.tm_nt != g.nt || L.tm_tb != g.tb) {
+      if (!make_tmap_bf16_3d(&L.tmW, L.w_dev, (uint64_t)L.cin_pad, (uint64_t)L.ntot, (uint64_t)L.ntaps, (uint32_t)(g.rb / 2),
+                             (uint32_t)g.nt, (uint32_t)g.tb))
+        return fail(v, L2S_ERR_CUDA, "cuTensorMapEncodeTiled failed for the weights of " + L.name);
+      L.has_tmW = true;
+      L.tm_nt = g.nt;
+      L.tm_tb = g.tb;
+    }
+    CUtensorMap tmA;
+    if (!make_tmap_bf16_3d(&tmA, in, (uint64_t)L.cin_pad, (uint64_t)lin, (uint64_t)batch, (uint32_t)(g.rb / 2),
+                           (uint32_t)g.box_rows, 1u))
+      return fail(v, L2S_ERR_CUDA, "cuTensorMapEncodeTiled failed for the input of " + L.name);
+    e = launch_conv_tc(p, g, tmA, L.tmW, tune.max_ctas, st);
+  }
+  timed_end(v, st);
+  if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, std::string("launch ") + L.name + ": " + cudaGetErrorString(e));
+  return L2S_OK;
+}
+
+struct Workspace {
+  void* cond;
+  void* ma[2];
+  float *x, *y, *acc;
+  void *xa, *ya, *ta;
+  float* spk_vec;
+  float* embed;
+  size_t bytes;
+};
+
+Workspace carve(const l2s_vocoder* v, int batch, int frames, uint8_t* base) {
+  const l2s_config& c = v->cfg;
+  const size_t as = act_size(v);
+  size_t max_stage = 0;
+  long long len = frames;
+  for (int i = 0; i < c.n_ups; ++i) {
+    len *= c.up_rates[i];
+    const size_t e = (size_t)len * v->stage_ch[i];
+    if (e > max_stage) max_stage = e;
+  }
+  const size_t pre_elems = (size_t)frames * c.up_init_ch;
+  const size_t ma_elems = max_stage > pre_elems ? max_stage : pre_elems;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    uint8_t* p = base ? base + off : nullptr;
+    off += align_up(bytes, 1024);
+    return (void*)p;
+  };
+  Workspace w;
+  w.cond = take((size_t)batch * frames * v->convs[v->conv_pre].cin_pad * as);
+  w.ma[0] = take((size_t)batch * ma_elems * as);
+  w.ma[1] = take((size_t)batch * ma_elems * as);
+  w.x = (float*)take((size_t)batch * max_stage * 4);
+  w.y = (float*)take((size_t)batch * max_stage * 4);
+  w.acc = (float*)take((size_t)batch * max_stage * 4);
+  w.xa = take((size_t)batch * max_stage * as);
+  w.ya = take((size_t)batch * max_stage * as);
+  w.ta = take((size_t)batch * max_stage * as);
+  w.spk_vec = (float*)take((size_t)batch * c.embedding_dim * 4);
+  const int units = c.variant == L2S_VARIANT_MULTI_INPUT ? frames / 2 : frames;
+  w.embed = (float*)take((size_t)batch * units * c.embedding_dim * 4);
+  w.bytes = off;
+  return w;
+}
+
+int forward_impl(l2s_vocoder* v, void* stream, const int64_t* code, const void* mel, int32_t mel_dtype, const void* spkr,
+                 int32_t batch, int32_t units, int32_t frames, float* out, int16_t* out_i16, void* workspace,
+                 int64_t workspace_bytes) {
+  if (!v) return L2S_ERR_INVALID;
+  std::lock_guard<std::mutex> lock(v->mu);
+  if (!v->finalized) return fail(v, L2S_ERR_STATE, "l2s_finalize has not been called");
+  const l2s_config& c = v->cfg;
+  const bool multi = c.variant == L2S_VARIANT_MULTI_INPUT;
+  if (batch < 1 || units < 1 || frames < 1) return fail(v, L2S_ERR_SHAPE, "empty batch / sequence");
+  if (!code || (!out && !out_i16) || !workspace) return fail(v, L2S_ERR_INVALID, "null pointer");
+  if (multi) {
+    if (!mel) return fail(v, L2S_ERR_INVALID, "mel is required (models_multi_input.py:65)");
+    if (frames != 2 * units) {
+      char b[160];
+      snprintf(b, sizeof b, "Sizes of tensors must match except in dimension 1. Expected size %d but got size %d (mel frames vs 2*units)",
+               frames, 2 * units);
+      return fail(v, L2S_ERR_SHAPE, b);
+    }
+    if (mel_dtype < 0 || mel_dtype > 2) return fail(v, L2S_ERR_INVALID, "mel dtype");
+  } else if (frames != units) {
+    return fail(v, L2S_ERR_SHAPE, "unit-only variant: frames must equal units");
+  }
+  if (c.multispkr && !spkr) return fail(v, L2S_ERR_INVALID, "spkr is required");
+  if ((uintptr_t)workspace % 256 != 0) return fail(v, L2S_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+  Workspace ws = carve(v, batch, frames, (uint8_t*)workspace);
+  if ((int64_t)ws.bytes > workspace_bytes) return fail(v, L2S_ERR_WORKSPACE, "workspace too small");
+  int dev_now = -1;
+  cudaGetDevice(&dev_now);
+  if (dev_now != v->device) cudaSetDevice(v->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool bf = is_bf16(v);
+  const int E = c.embedding_dim;
+  v->taps.clear();
+  v->timed_used = 0;
+  cudaError_t e;
+  ConvLayer& pre = v->convs[v->conv_pre];
+
+  // ---- conditioning front end
+  timed_begin(v, st, "front_end", 0.0);
+  float* embed_tap = g_knobs.embed_tap ? ws.embed : nullptr;
+  if (multi) {
+    if (c.multispkr) {
+      spk_project_kernel<<<batch, 128, c.spk_dim * sizeof(float), st>>>((const float*)spkr, v->d_spk_w, v->d_spk_b, ws.spk_vec,
+                                                                        c.spk_dim, E);
+    }
+    CondParams cp{};
+    cp.code = (const long long*)code;
+    cp.mel = mel;
+    cp.mel_dtype = mel_dtype;
+    cp.spk_vec = ws.spk_vec;
+    cp.dict = v->d_dict;
+    cp.wt = v->d_wt;
+    cp.wt_bias = v->d_wt_b;
+    cp.fc_t = v->d_fc_t;
+    cp.fc_bias = v->d_fc_b;
+    cp.cond = ws.cond;
+    cp.embed_tap = embed_tap;
+    cp.err_flag = v->err_dev;
+    cp.batch = batch; cp.units = units; cp.frames = frames; cp.e = E; cp.num_mels = c.num_mels;
+    cp.num_embeddings = c.num_embeddings; cp.cin_pad = pre.cin_pad; cp.has_spk = c.multispkr ? 1 : 0;
+    dim3 grid((frames + kCondFrames - 1) / kCondFrames, batch);
+    if (bf) cond_multi_kernel<__nv_bfloat16><<<grid, kCondE, 0, st>>>(cp);
+    else cond_multi_kernel<float><<<grid, kCondE, 0, st>>>(cp);
+  } else {
+    CondUnitParams cp{};
+    cp.code = (const long long*)code;
+    cp.spk_id = (const long long*)spkr;
+    cp.dict = v->d_dict;
+    cp.spk_table = v->d_spk_w;
+    cp.cond = ws.cond;
+    cp.embed_tap = embed_tap;
+    cp.err_flag = v->err_dev;
+    cp.batch = batch; cp.units = units; cp.e = E; cp.num_embeddings = c.num_embeddings;
+    cp.num_speakers = c.num_speakers; cp.cin_pad = pre.cin_pad; cp.has_spk = c.multispkr ? 1 : 0;
+    dim3 grid(units, batch);
+    if (bf) cond_unit_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(cp);
+    else cond_unit_kernel<float><<<grid, 128, 0, st>>>(cp);
+  }
+  timed_end(v, st);
+  if ((e = cudaGetLastError()) != cudaSuccess) return fail(v, L2S_ERR_CUDA, std::string("front end: ") + cudaGetErrorString(e));
+  v->taps["cond"] = {ws.cond, (long long)batch * frames * pre.cin_pad, true};
+  if (embed_tap) v->taps["embed"] = {ws.embed, (long long)batch * units * E, false};
+
+  // ---- conv_pre (its consumer applies leaky_relu(0.1): emit the activated copy only)
+  int rc = run_conv(v, pre, st, batch, frames, ws.cond, nullptr, ws.ma[0], nullptr, nullptr, 1.f, 0.1f);
+  if (rc) return rc;
+  v->taps["conv_pre_act"] = {ws.ma[0], (long long)batch * frames * c.up_init_ch, true};
+  if (g_knobs.stop_after_pre) return L2S_OK;
+
+  // ---- upsample stages + MRF
+  int cur = 0;
+  long long len = frames;
+  for (int i = 0; i < c.n_ups; ++i) {
+    ConvLayer& up = v->convs[v->ups[i]];
+    rc = run_conv(v, up, st, batch, (int)len, ws.ma[cur], ws.x, ws.xa, nullptr, nullptr, 1.f, 0.1f);
+    if (rc) return rc;
+    len *= c.up_rates[i];
+    const int ch = v->stage_ch[i];
+    const long long numel = (long long)batch * len * ch;
+    const bool last_stage = i == c.n_ups - 1;
+    const bool want_raw = last_stage || g_knobs.stop_after_stage == i;
+    for (int j = 0; j < c.n_rk; ++j) {
+      for (int m = 0; m < c.n_dil; ++m) {
+        ConvLayer& c1 = v->convs[v->rb_c1[i][j][m]];
+        ConvLayer& c2 = v->convs[v->rb_c2[i][j][m]];
+        const void* in1 = m == 0 ? ws.xa : ws.ya;
+        const float* res = m == 0 ? ws.x : ws.y;
+        rc = run_conv(v, c1, st, batch, (int)len, in1, nullptr, ws.ta, nullptr, nullptr, 1.f, 0.1f);
+        if (rc) return rc;
+        if (m < c.n_dil - 1) {
+          rc = run_conv(v, c2, st, batch, (int)len, ws.ta, ws.y, ws.ya, res, nullptr, 1.f, 0.1f);
+        } else if (j < c.n_rk - 1) {
+          rc = run_conv(v, c2, st, batch, (int)len, ws.ta, ws.acc, nullptr, res, j == 0 ? nullptr : ws.acc, 1.f, 0.1f);
+        } else {
+          // last branch: mean over branches (true division by num_kernels, models.py:109)
+          rc = run_conv(v, c2, st, batch, (int)len, ws.ta, want_raw ? ws.acc : nullptr, last_stage ? nullptr : ws.ma[cur ^ 1],
+                        res, c.n_rk == 1 ? nullptr : ws.acc, (float)c.n_rk, 0.1f);
+        }
+        if (rc) return rc;
+      }
+    }
+    cur ^= 1;
+    if (g_knobs.stop_after_stage == i) {
+      v->taps["ups"] = {ws.x, numel, false};
+      v->taps["mrf"] = {ws.acc, numel, false};
+      return L2S_OK;
+    }
+  }
+
+  // ---- waveform head
+  PostParams pp{};
+  pp.in = ws.acc;
+  pp.w = v->d_post_w;
+  pp.bias = v->post_bias;
+  pp.out = out;
+  pp.out_i16 = out_i16;
+  pp.batch = batch;
+  pp.len = (int)len;
+  pp.c = v->stage_ch.back();
+  dim3 grid((unsigned)((len + kPostTile - 1) / kPostTile), batch);
+  timed_begin(v, st, "conv_post", 2.0 * pp.c * 7 * (double)batch * len);
+  post_kernel<<<grid, kPostTile, (kPostTile + 6) * (pp.c + 1) * sizeof(float), st>>>(pp);
+  timed_end(v, st);
+  if ((e = cudaGetLastError()) != cudaSuccess) return fail(v, L2S_ERR_CUDA, std::string("post: ") + cudaGetErrorString(e));
+  return L2S_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ C ABI
+
+extern "C" {
+
+int l2s_create(const l2s_config* cfg, l2s_vocoder** out) {
+  if (!cfg || !out) return L2S_ERR_INVALID;
+  l2s_vocoder* v = new (std::nothrow) l2s_vocoder();
+  if (!v) return L2S_ERR_INVALID;
+  v->cfg = *cfg;
+  const int rc = build_layers(v);
+  *out = v;   // returned even on failure so the caller can read l2s_last_error, then destroy
+  return rc;
+}
+
+void l2s_destroy(l2s_vocoder* v) {
+  if (!v) return;
+  if (v->finalized) {
+    int dev = -1;
+    cudaGetDevice(&dev);
+    if (dev != v->device) cudaSetDevice(v->device);
+    for (void* p : v->dev_allocs) cudaFree(p);
+    if (v->err_host) cudaFreeHost(v->err_host);
+    if (dev >= 0 && dev != v->device) cudaSetDevice(dev);
+  }
+  delete v;
+}
+
+int l2s_set_weight(l2s_vocoder* v, const char* name, const float* host_data, int64_t numel) {
+  if (!v || !name || !host_data) return L2S_ERR_INVALID;
+  std::lock_guard<std::mutex> lock(v->mu);
+  if (v->finalized) return fail(v, L2S_ERR_STATE, "weights are frozen after l2s_finalize");
+  auto it = v->expected.find(name);
+  if (it == v->expected.end()) return fail(v, L2S_ERR_INVALID, std::string("unexpected weight name: ") + name);
+  if (it->second != numel) {
+    char b[160];
+    snprintf(b, sizeof b, "size mismatch for %s: expected %lld elements, got %lld", name, it->second, (long long)numel);
+    return fail(v, L2S_ERR_SHAPE, b);
+  }
+  v->weights[name].assign(host_data, host_data + numel);
+  return L2S_OK;
+}
+
+int l2s_finalize(l2s_vocoder* v, int device) {
+  if (!v) return L2S_ERR_INVALID;
+  std::lock_guard<std::mutex> lock(v->mu);
+  if (v->finalized) return fail(v, L2S_ERR_STATE, "already finalized");
+  for (auto& kv : v->expected)
+    if (!v->weights.count(kv.first)) return fail(v, L2S_ERR_STATE, "missing weight: " + kv.first);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev < 1) return fail(v, L2S_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(v, L2S_ERR_INVALID, "bad device index");
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(v, L2S_ERR_CUDA, cudaGetErrorString(e));
+  if (prop.major != 10) {
+    char b[128];
+    snprintf(b, sizeof b, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    return fail(v, L2S_ERR_UNSUPPORTED, b);
+  }
+  int prev = -1;
+  cudaGetDevice(&prev);
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(v, L2S_ERR_CUDA, cudaGetErrorString(e));
+  v->device = device;
+  v->num_sms = prop.multiProcessorCount;
+  const l2s_config& c = v->cfg;
+  const bool bf = is_bf16(v);
+  const int E = c.embedding_dim;
+
+  for (ConvLayer& L : v->convs) {
+    std::vector<float> pw, pb;
+    pack_conv(L, v->weights[L.name + ".weight"], v->weights[L.name + ".bias"], &pw, &pb);
+    if (bf) {
+      std::vector<uint16_t> hw(pw.size());
+      for (size_t i = 0; i < pw.size(); ++i) hw[i] = f2bf(pw[i]);
+      L.w_dev = dev_upload<uint16_t>(v, hw.data(), hw.size(), &e);
+    } else {
+      L.w_dev = dev_upload<float>(v, pw.data(), pw.size(), &e);
+    }
+    if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, std::string("upload ") + L.name + ": " + cudaGetErrorString(e));
+    L.bias_dev = dev_upload<float>(v, pb.data(), pb.size(), &e);
+    if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, cudaGetErrorString(e));
+  }
+  {
+    const std::vector<float>& d = v->weights["dict.weight"];
+    v->d_dict = dev_upload<float>(v, d.data(), d.size(), &e);
+    if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, cudaGetErrorString(e));
+  }
+  if (c.variant == L2S_VARIANT_MULTI_INPUT) {
+    // unit ConvTranspose1d weight (E_in, E_out, 4) -> [4][E_in][E_out]
+    const std::vector<float>& w = v->weights["layer.0.weight"];
+    std::vector<float> wt((size_t)4 * E * E);
+    for (int ci = 0; ci < E; ++ci)
+      for (int co = 0; co < E; ++co)
+        for (int j = 0; j < 4; ++j) wt[((size_t)j * E + ci) * E + co] = w[((size_t)ci * E + co) * 4 + j];
+    v->d_wt = dev_upload<float>(v, wt.data(), wt.size(), &e);
+    if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, cudaGetErrorString(e));
+    v->d_wt_b = dev_upload<float>(v, v->weights["layer.0.bias"].data(), E, &e);
+    const std::vector<float>& fw = v->weights["fc.weight"];   // (out, in)
+    std::vector<float> ft((size_t)E * E);
+    for (int o = 0; o < E; ++o)
+      for (int k = 0; k < E; ++k) ft[(size_t)k * E + o] = fw[(size_t)o * E + k];
+    v->d_fc_t = dev_upload<float>(v, ft.data(), ft.size(), &e);
+    v->d_fc_b = dev_upload<float>(v, v->weights["fc.bias"].data(), E, &e);
+    if (c.multispkr) {
+      v->d_spk_w = dev_upload<float>(v, v->weights["spkr.weight"].data(), v->weights["spkr.weight"].size(), &e);
+      v->d_spk_b = dev_upload<float>(v, v->weights["spkr.bias"].data(), E, &e);
+    }
+    if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, cudaGetErrorString(e));
+  } else if (c.multispkr) {
+    v->d_spk_w = dev_upload<float>(v, v->weights["spkr.weight"].data(), v->weights["spkr.weight"].size(), &e);
+    if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, cudaGetErrorString(e));
+  }
+  {
+    // conv_post weight (1, C, 7) -> [7][C]
+    const int C = v->stage_ch.back();
+    const std::vector<float>& w = v->weights["conv_post.weight"];
+    std::vector<float> pw((size_t)7 * C);
+    for (int ch = 0; ch < C; ++ch)
+      for (int j = 0; j < 7; ++j) pw[(size_t)j * C + ch] = w[(size_t)ch * 7 + j];
+    v->d_post_w = dev_upload<float>(v, pw.data(), pw.size(), &e);
+    if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, cudaGetErrorString(e));
+    v->post_bias = v->weights["conv_post.bias"][0];
+  }
+  if ((e = cudaHostAlloc((void**)&v->err_host, sizeof(int), cudaHostAllocMapped)) != cudaSuccess)
+    return fail(v, L2S_ERR_CUDA, cudaGetErrorString(e));
+  *v->err_host = 0;
+  if ((e = cudaHostGetDevicePointer((void**)&v->err_dev, v->err_host, 0)) != cudaSuccess)
+    return fail(v, L2S_ERR_CUDA, cudaGetErrorString(e));
+  if ((e = cudaDeviceSynchronize()) != cudaSuccess) return fail(v, L2S_ERR_CUDA, cudaGetErrorString(e));
+  v->weights.clear();
+  v->finalized = true;
+  if (prev >= 0 && prev != device) cudaSetDevice(prev);
+  return L2S_OK;
+}
+
+int64_t l2s_workspace_bytes(l2s_vocoder* v, int32_t batch, int32_t frames) {
+  if (!v || batch < 1 || frames < 1 || v->convs.empty()) return -1;
+  return (int64_t)carve(v, batch, frames, nullptr).bytes;
+}
+
+int32_t l2s_hop(l2s_vocoder* v) { return v ? hop_of(v->cfg) : -1; }
+
+int l2s_forward(l2s_vocoder* v, void* stream, const int64_t* code, const void* mel, int32_t mel_dtype, const void* spkr,
+                int32_t batch, int32_t units, int32_t frames, float* out, void* workspace, int64_t workspace_bytes) {
+  return forward_impl(v, stream, code, mel, mel_dtype, spkr, batch, units, frames, out, nullptr, workspace, workspace_bytes);
+}
+
+int l2s_forward_i16(l2s_vocoder* v, void* stream, const int64_t* code, const void* mel, int32_t mel_dtype, const void* spkr,
+                    int32_t batch, int32_t units, int32_t frames, float* out, int16_t* out_i16, void* workspace,
+                    int64_t workspace_bytes) {
+  if (!out_i16) return fail(v, L2S_ERR_INVALID, "out_i16 is null");
+  return forward_impl(v, stream, code, mel, mel_dtype, spkr, batch, units, frames, out, out_i16, workspace, workspace_bytes);
+}
+
+int l2s_poll_index_error(l2s_vocoder* v) {
+  if (!v || !v->err_host) return L2S_ERR_STATE;
+  const int f = *(volatile int*)v->err_host;
+  *(volatile int*)v->err_host = 0;
+  if (f) return fail(v, L2S_ERR_INDEX, (f & 1) ? "index out of range in self (unit id outside the dict table)"
+                                                : "index out of range in self (speaker id outside the table)");
+  return L2S_OK;
+}
+
+int32_t l2s_launch_count(l2s_vocoder* v, int32_t batch, int32_t frames) {
+  if (!v) return -1;
+  (void)batch; (void)frames;
+  const l2s_config& c = v->cfg;
+  int n = (int)v->convs.size() + 1 /* post */ + 1 /* cond */;
+  if (c.variant == L2S_VARIANT_MULTI_INPUT && c.multispkr) n += 1;
+  return n;
+}
+
+const char* l2s_last_error(l2s_vocoder* v) { return v ? v->err.c_str() : "null handle"; }
+const char* l2s_version(void) { return "l2s_vocoder 0.1 (sm_100a)"; }
+
+int l2s_debug_tap(l2s_vocoder* v, const char* name, float* host_dst, int64_t numel) {
+  if (!v || !name || !host_dst) return L2S_ERR_INVALID;
+  std::lock_guard<std::mutex> lock(v->mu);
+  auto it = v->taps.find(name);
+  if (it == v->taps.end()) return fail(v, L2S_ERR_INVALID, std::string("no such tap: ") + name);
+  if (it->second.numel != numel) {
+    char b[128];
+    snprintf(b, sizeof b, "tap %s has %lld elements, caller asked for %lld", name, it->second.numel, (long long)numel);
+    return fail(v, L2S_ERR_SHAPE, b);
+  }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, cudaGetErrorString(e));
+  if (it->second.act && is_bf16(v)) {
+    std::vector<uint16_t> tmp((size_t)numel);
+    e = cudaMemcpy(tmp.data(), it->second.ptr, (size_t)numel * 2, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, cudaGetErrorString(e));
+    for (int64_t i = 0; i < numel; ++i) {
+      const uint32_t u = (uint32_t)tmp[(size_t)i] << 16;
+      memcpy(&host_dst[i], &u, 4);
+    }
+  } else {
+    e = cudaMemcpy(host_dst, it->second.ptr, (size_t)numel * 4, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, cudaGetErrorString(e));
+  }
+  return L2S_OK;
+}
+
+int l2s_debug_conv(const l2s_conv_desc* d, int32_t impl, int32_t device, void* stream, char* err, int32_t err_len) {
+  auto say = [&](const char* m) {
+    if (err && err_len > 0) snprintf(err, (size_t)err_len, "%s", m);
+  };
+  if (!d) { say("null desc"); return L2S_ERR_INVALID; }
+  if (d->ntaps < 1 || d->ntaps > kMaxTaps) { say("ntaps"); return L2S_ERR_INVALID; }
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) { say(cudaGetErrorString(e)); return L2S_ERR_CUDA; }
+  ConvParams p{};
+  p.in = d->in; p.w = d->w; p.bias = d->bias; p.out_raw = d->out_raw; p.out_act = d->out_act; p.res = d->res;
+  p.acc_in = d->acc_in;
+  p.batch = d->batch; p.lin = d->lin; p.cin_pad = d->cin_pad; p.ntaps = d->ntaps; p.ntot = d->ntot; p.mrows = d->mrows;
+  for (int j = 0; j < d->ntaps; ++j) p.tap_off[j] = d->tap_off[j];
+  p.out_shift = d->out_shift; p.out_valid = d->out_valid;
+  p.div = d->scale; p.slope = d->slope;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (impl == 0) {
+    e = d->act_bf16 ? launch_conv_simt<__nv_bfloat16>(p, st) : launch_conv_simt<float>(p, st);
+  } else {
+    if (!d->act_bf16) { say("the tcgen05 kernel takes bf16 operands"); return L2S_ERR_UNSUPPORTED; }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    TcTune tune = current_tune(nullptr);
+    if (g_knobs.max_ctas <= 0) tune.max_ctas = sms;
+    tune.base_offset_mode = impl == 2 ? 1 : 0;
+    TcGeom g;
+    if (!tc_plan(p, d->batch, tune, &g)) { say("no tcgen05 plan"); return L2S_ERR_UNSUPPORTED; }
+    CUtensorMap tmA, tmW;
+    if (!make_tmap_bf16_3d(&tmW, d->w, (uint64_t)d->cin_pad, (uint64_t)d->ntot, (uint64_t)d->ntaps, (uint32_t)(g.rb / 2),
+                           (uint32_t)g.nt, (uint32_t)g.tb) ||
+        !make_tmap_bf16_3d(&tmA, d->in, (uint64_t)d->cin_pad, (uint64_t)d->lin, (uint64_t)d->batch, (uint32_t)(g.rb / 2),
+                           (uint32_t)g.box_rows, 1u)) {
+      say("cuTensorMapEncodeTiled failed");
+      return L2S_ERR_CUDA;
+    }
+    e = launch_conv_tc(p, g, tmA, tmW, tune.max_ctas, st);
+  }
+  if (e != cudaSuccess) { say(cudaGetErrorString(e)); return L2S_ERR_CUDA; }
+  return L2S_OK;
+}
+
+int l2s_debug_layer_time(l2s_vocoder* v, int32_t idx, float* ms, double* flops, char* name, int32_t name_len) {
+  if (!v || !ms) return L2S_ERR_INVALID;
+  std::lock_guard<std::mutex> lock(v->mu);
+  if (idx < 0 || (size_t)idx >= v->timed_used) return L2S_ERR_INVALID;
+  l2s_vocoder::Timed& t = v->timed[(size_t)idx];
+  cudaError_t e = cudaEventSynchronize(t.b);
+  if (e == cudaSuccess) e = cudaEventElapsedTime(ms, t.a, t.b);
+  if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, cudaGetErrorString(e));
+  if (flops) *flops = t.flops;
+  if (name && name_len > 0) snprintf(name, (size_t)name_len, "%s", t.name.c_str());
+  return L2S_OK;
+}
+
+int l2s_debug_set(const char* key, int64_t value) {
+  if (!key) return L2S_ERR_INVALID;
+  const std::string k(key);
+  if (k == "force_simt") g_knobs.force_simt = value;
+  else if (k == "stop_after_stage") g_knobs.stop_after_stage = value;
+  else if (k == "stop_after_pre") g_knobs.stop_after_pre = value;
+  else if (k == "base_offset_mode") g_knobs.base_offset_mode = value;
+  else if (k == "max_msub") g_knobs.max_msub = value;
+  else if (k == "slab_cap") g_knobs.slab_cap = value;
+  else if (k == "max_ctas") g_knobs.max_ctas = value;
+  else if (k == "embed_tap") g_knobs.embed_tap = value;
+  else if (k == "layer_events") g_knobs.layer_events = value;
+  else return L2S_ERR_INVALID;
+  return L2S_OK;
+}
+
+}  // extern "C"

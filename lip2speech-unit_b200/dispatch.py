@@ -1,0 +1,60 @@
+"""Host-side work partitioning around the generator forward: utterance sharding
+across GPUs (no collective: utterances are independent) and the
+halo-exact chunk plan for long streams."""
+from typing import List, Sequence, Tuple
+
+import torch
+
+# An output sample depends on conditioning within +-21.6 mel frames;
+# 24 is the next even count, so chunk boundaries stay on unit (2-frame) boundaries.
+HALO_FRAMES = 24
+
+
+def shard_utterances(lengths: Sequence[int], world_size: int, rank: int) -> List[int]:
+    """Indices of the utterances rank `rank` vocodes.  Longest-first round-robin
+    dealing keeps per-rank work within one utterance of balanced; equal lengths
+    degenerate to a strided split.  Every index is owned by exactly one rank."""
+    if world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError("bad world_size / rank")
+    order = sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i))
+    return sorted(order[rank::world_size])
+
+
+def chunk_plan(frames: int, core: int, halo: int = HALO_FRAMES) -> List[Tuple[int, int, int, int]]:
+    """Split `frames` conditioning frames into chunks of `core` frames plus `halo`
+    frames of context per side.  Returns (lo, hi, keep_lo, keep_hi): vocode
+    frames [lo,hi) and keep the samples of frames [keep_lo,keep_hi).  All bounds
+    are even so unit boundaries (2 frames) are respected."""
+    if frames < 1 or core < 2 or core % 2 or halo % 2 or halo < 0:
+        raise ValueError("frames >= 1, core even >= 2, halo even >= 0 required")
+    out = []
+    k = 0
+    while k < frames:
+        k2 = min(k + core, frames)
+        out.append((max(0, k - halo), min(frames, k2 + halo), k, k2))
+        k = k2
+    return out
+
+
+@torch.no_grad()
+def vocode_long(generator, code: torch.Tensor, mel: torch.Tensor, spkr: torch.Tensor, core: int = 1000,
+                halo: int = HALO_FRAMES, hop: int = 160) -> torch.Tensor:
+    """Vocode one long stream (B=1) in overlapping chunks; chunks of equal length are
+    batched into one forward.  With halo >= 22 frames the result equals the
+    unchunked forward (every layer's zero padding only matters within the halo)."""
+    if code.shape[0] != 1:
+        raise ValueError("vocode_long takes a single stream (B=1)")
+    frames = mel.shape[2]
+    plan = chunk_plan(frames, core, halo)
+    out = torch.empty((1, 1, frames * hop), dtype=torch.float32, device=mel.device)
+    by_len = {}
+    for c in plan:
+        by_len.setdefault(c[1] - c[0], []).append(c)
+    for n, chunks in by_len.items():
+        mel_b = torch.stack([mel[0, :, lo:hi] for lo, hi, _, _ in chunks])
+        code_b = torch.stack([code[0, lo // 2:hi // 2] for lo, hi, _, _ in chunks])
+        spk_b = spkr.expand(len(chunks), -1).contiguous()
+        y = generator(code=code_b, mel=mel_b, spkr=spk_b)
+        for i, (lo, hi, klo, khi) in enumerate(chunks):
+            out[0, 0, klo * hop:khi * hop] = y[i, 0, (klo - lo) * hop:(khi - lo) * hop]
+    return out

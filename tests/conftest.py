@@ -17,3 +17,11 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(scope="session")
+def pkg():
+    """The product package (hyphen-named directory) with its CUDA library built."""
+    import __graft_entry__ as ge
+    ge.build()
+    return ge.load_package()

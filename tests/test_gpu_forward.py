@@ -1,0 +1,230 @@
+"""Parity of the CUDA path (through the C ABI, via the drop-in classes) against
+the CPU oracle and the golden vectors made from the unmodified reference.
+
+Tolerances (stated per mode, vs the fp64 reference run):
+  fp32 mode  CUDA-core FFMA, fp32 storage      : SNR >= 100 dB, max-abs <= 2e-5
+  bf16 mode  tcgen05 bf16 operands, fp32 accum,
+             fp32 residual stream              : SNR >= 35 dB on trained-like weights
+Unit-table indexing is bit-exact in both modes.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vocoder_oracle as vo
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+DEV = "cuda:0"
+
+TOL = {"fp32": dict(snr=100.0, max_abs=2e-5), "bf16": dict(snr=35.0, max_abs=5e-2)}
+
+
+def make_gen(pkg, h, sd, precision, cls="MelCodeGenerator", fold=True):
+    g = getattr(pkg, cls)(pkg.AttrDict(h))
+    g.load_state_dict(sd, strict=True)
+    g.eval()
+    if fold:
+        g.remove_weight_norm()
+    g.set_precision(precision)
+    return g.to(DEV)
+
+
+@pytest.fixture(scope="module")
+def weights():
+    h = vo.shipped_config()
+    return h, {st: vo.init_state_dict(h, seed=1234, style=st) for st in ("ref", "trained")}
+
+
+def check(ref, y, precision, what):
+    y = y.detach().cpu()
+    assert y.shape == ref.shape, what
+    assert torch.isfinite(y).all(), what
+    snr, ma = vo.snr_db(ref, y), vo.max_abs(ref, y)
+    print(f"[parity] {what} {precision}: snr {snr:.2f} dB max-abs {ma:.3e}")
+    assert snr >= TOL[precision]["snr"], f"{what}: SNR {snr:.1f} dB"
+    assert ma <= TOL[precision]["max_abs"], f"{what}: max-abs {ma:.3e}"
+    return snr, ma
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("style", ["trained", "ref"])
+def test_cfg1_golden(pkg, weights, precision, style):
+    """configs[0]: the shipped datasets/lrs3 sample utterance (T=428) against the
+    fp64 output of the reference classes."""
+    h, sds = weights
+    z = np.load(os.path.join(GOLDEN, "cfg1.npz"))
+    g = make_gen(pkg, h, sds[style], precision)
+    y = g(code=torch.from_numpy(z["code"]).unsqueeze(0).to(DEV), mel=torch.from_numpy(z["mel"]).unsqueeze(0).to(DEV),
+          spkr=torch.from_numpy(z["spkr"]).unsqueeze(0).to(DEV))
+    ref = torch.from_numpy(z["wave_" + style]).view(1, 1, -1)
+    if style == "ref" and precision == "bf16":
+        # bias-dominated output (rms 0.1, nearly constant): SNR is not informative, bound the error
+        assert vo.max_abs(ref, y.cpu()) <= 2e-3
+    else:
+        check(ref, y, precision, f"cfg1/{style}")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_small_batch_taps(pkg, weights, precision):
+    """B=2, T=16 golden with per-layer taps: conv_pre, ups.0, first MRF stage, final wave."""
+    h, sds = weights
+    z = np.load(os.path.join(GOLDEN, "small_b2_t16.npz"))
+    g = make_gen(pkg, h, sds["trained"], precision)
+    lib = pkg._cabi.load()
+    code, mel, spkr = (torch.from_numpy(z[k]).to(DEV) for k in ("code", "mel", "spkr"))
+    tol = 1e-4 if precision == "fp32" else 6e-2
+    try:
+        lib.l2s_debug_set(b"stop_after_stage", 0)
+        g(code=code, mel=mel, spkr=spkr)
+        pre = g.debug_tap("conv_pre_act", (2, 16, 512), DEV)
+        ref_pre = torch.nn.functional.leaky_relu(torch.from_numpy(z["tap_conv_pre"]), 0.1).transpose(1, 2)
+        assert float((pre - ref_pre).abs().max()) <= tol * max(1.0, float(ref_pre.abs().max()))
+        ups0 = g.debug_tap("ups", (2, 80, 256), DEV)
+        ref_u = torch.from_numpy(z["tap_ups.0"]).transpose(1, 2)
+        assert float((ups0 - ref_u).abs().max()) <= tol * max(1.0, float(ref_u.abs().max()))
+    finally:
+        lib.l2s_debug_set(b"stop_after_stage", -1)
+    y = g(code=code, mel=mel, spkr=spkr)
+    check(torch.from_numpy(z["wave_trained"]), y, precision, "small_b2_t16")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_edge_shortest_utterance(pkg, weights, precision):
+    """U=1, T=2: every layer is shorter than its receptive field (all padding)."""
+    h, sds = weights
+    z = np.load(os.path.join(GOLDEN, "edge_t2.npz"))
+    g = make_gen(pkg, h, sds["trained"], precision)
+    y = g(code=torch.from_numpy(z["code"]).to(DEV), mel=torch.from_numpy(z["mel"]).to(DEV),
+          spkr=torch.from_numpy(z["spkr"]).to(DEV))
+    check(torch.from_numpy(z["wave_trained"]), y, precision, "edge_t2")
+    z6 = np.load(os.path.join(GOLDEN, "edge_t6.npz"))
+    y = g(code=torch.from_numpy(z6["code"]).to(DEV), mel=torch.from_numpy(z6["mel"]).to(DEV),
+          spkr=torch.from_numpy(z6["spkr"]).to(DEV))
+    check(torch.from_numpy(z6["wave_trained"]), y, precision, "edge_t6")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_unit_only_variant(pkg, precision):
+    """Parent CodeGenerator.forward (rates [5,4,4,2,2], speaker id table)."""
+    h = vo.unit_only_config()
+    sd = vo.init_state_dict(h, seed=1234, style="trained", unit_only=True)
+    z = np.load(os.path.join(GOLDEN, "unit_only_b2_u12.npz"))
+    g = make_gen(pkg, h, sd, precision, cls="CodeGenerator")
+    y = g(code=torch.from_numpy(z["code"]).to(DEV), spkr=torch.from_numpy(z["spkr"]).to(DEV))
+    check(torch.from_numpy(z["wave_trained"]), y, precision, "unit_only")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_oracle_seeded_batch(pkg, weights, precision):
+    """Seeded synthetic batch (BASELINE.md section 4 distribution) vs the CPU oracle in fp64."""
+    h, sds = weights
+    code, mel, spkr = vo.synthetic_inputs(3, 100, seed=52)
+    ref = vo.mel_code_generator_forward(vo.fold_weight_norm(sds["trained"]), h, code, mel, spkr, dtype=torch.float64)
+    g = make_gen(pkg, h, sds["trained"], precision)
+    y = g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV))
+    check(ref, y, precision, "synthetic_b3_t100")
+
+
+def test_lazy_fold_matches_removed_weight_norm(pkg, weights):
+    """forward before remove_weight_norm() folds g*v/||v|| on the fly (train.py-style use)."""
+    h, sds = weights
+    code, mel, spkr = vo.synthetic_inputs(1, 20, seed=3)
+    a = make_gen(pkg, h, sds["trained"], "fp32", fold=True)(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV))
+    b = make_gen(pkg, h, sds["trained"], "fp32", fold=False)(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV))
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_unit_gather_bit_exact(pkg, weights, precision):
+    h, sds = weights
+    code, mel, spkr = vo.synthetic_inputs(2, 64, seed=11)
+    code[0, 0], code[1, -1] = 0, 199
+    g = make_gen(pkg, h, sds["trained"], precision)
+    lib = pkg._cabi.load()
+    try:
+        lib.l2s_debug_set(b"embed_tap", 1)
+        g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV))
+        emb = g.debug_tap("embed", (2, 32, 128), DEV)
+    finally:
+        lib.l2s_debug_set(b"embed_tap", 0)
+    assert torch.equal(emb, sds["trained"]["dict.weight"][code])
+
+
+def test_mel_fp16_input_promotes(pkg, weights):
+    """pred_mel may arrive as float16: same result as the fp32 copy of those values."""
+    h, sds = weights
+    code, mel, spkr = vo.synthetic_inputs(1, 40, seed=5)
+    mel16 = mel.half()
+    g = make_gen(pkg, h, sds["trained"], "fp32")
+    a = g(code=code.to(DEV), mel=mel16.to(DEV), spkr=spkr.to(DEV))
+    b = g(code=code.to(DEV), mel=mel16.float().to(DEV), spkr=spkr.to(DEV))
+    assert torch.equal(a, b)
+
+
+def test_int16_output(pkg, weights):
+    h, sds = weights
+    code, mel, spkr = vo.synthetic_inputs(2, 40, seed=7)
+    g = make_gen(pkg, h, sds["trained"], "fp32")
+    y, y16 = g.forward_int16(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV))
+    expect = (y.squeeze(1) * 32768.0).clamp(-32768, 32767).cpu().numpy().astype("int16")   # inference.py:79-81
+    assert np.array_equal(y16.cpu().numpy(), expect)
+
+
+def test_error_conventions(pkg, weights):
+    h, sds = weights
+    g = make_gen(pkg, h, sds["trained"], "fp32")
+    code, mel, spkr = vo.synthetic_inputs(1, 20, seed=1)
+    with pytest.raises(RuntimeError):           # torch.cat size mismatch, models_multi_input.py:73
+        g(code=code.to(DEV), mel=mel[:, :, :18].contiguous().to(DEV), spkr=spkr.to(DEV))
+    with pytest.raises(KeyError):
+        g(code=code.to(DEV), spkr=spkr.to(DEV))
+    with pytest.raises(RuntimeError):           # no CPU fallback
+        g(code=code, mel=mel, spkr=spkr)
+    g.strict_index_check = True
+    bad = code.clone()
+    bad[0, 3] = 200
+    with pytest.raises(IndexError):
+        g(code=bad.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV))
+    g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV))   # flag was cleared
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_batch_invariance(pkg, weights, precision):
+    """Utterances are independent: a batched forward equals the per-utterance forwards bit for bit."""
+    h, sds = weights
+    code, mel, spkr = vo.synthetic_inputs(4, 60, seed=9)
+    g = make_gen(pkg, h, sds["trained"], precision)
+    y = g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV))
+    for i in range(4):
+        yi = g(code=code[i:i + 1].to(DEV), mel=mel[i:i + 1].to(DEV), spkr=spkr[i:i + 1].to(DEV))
+        assert torch.equal(yi[0], y[i])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_chunked_long_form_equals_full(pkg, weights, precision):
+    """Config 4 property: chunks with a 24-frame halo reproduce the unchunked forward
+    (interior exactly; allow last-bit differences from tile-boundary summation order)."""
+    h, sds = weights
+    code, mel, spkr = vo.synthetic_inputs(1, 700, seed=13)
+    g = make_gen(pkg, h, sds["trained"], precision)
+    full = g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV))
+    chunked = pkg.vocode_long(g, code.to(DEV), mel.to(DEV), spkr.to(DEV), core=200)
+    assert chunked.shape == full.shape
+    assert float((chunked - full).abs().max()) <= (1e-6 if precision == "fp32" else 1e-6)
+
+
+def test_cfg2_shape_bf16_vs_fp32_device_reference(pkg, weights):
+    """configs[1] at full size (16 x 4 s): bf16 tensor-core path against the fp32
+    CUDA-core mode of the same library, plus finiteness and range."""
+    h, sds = weights
+    code, mel, spkr = vo.synthetic_inputs(16, 400, seed=52)
+    a = make_gen(pkg, h, sds["trained"], "fp32")(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV))
+    b = make_gen(pkg, h, sds["trained"], "bf16")(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV))
+    assert b.shape == (16, 1, 64000)
+    assert torch.isfinite(b).all() and float(b.abs().max()) <= 1.0
+    snr = vo.snr_db(a.cpu(), b.cpu())
+    print(f"[parity] cfg2 bf16 vs fp32-device: snr {snr:.2f} dB max-abs {vo.max_abs(a.cpu(), b.cpu()):.3e}")
+    assert snr >= 35.0
