@@ -52,6 +52,7 @@ struct TcGeom {
   int tmem_cols;     // power of two >= 2 * msub * nt
   int total_items;
   int base_offset_mode;  // 0: descriptor base_offset field left 0; 1: (addr >> 7) & 7
+  int per_tap;           // 1: probe/fallback mode, one A tile per tap by TMA (no row-shifted descriptors)
   uint32_t idesc;
   int smem_bytes;
 };
@@ -113,14 +114,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ni = rem - mi * g.n_ntiles;
         const int row0 = mi * 128 * g.msub + g.min_off;
         for (int kc = 0; kc < g.kc; ++kc) {
-          mbar_wait(&a_empty[ia], pa ^ 1u);
-          mbar_expect_tx(&a_full[ia], (uint32_t)g.slab_bytes);
-          uint8_t* dst = slabA + (size_t)ia * g.slab_bytes;
-          for (int l = 0; l < g.n_loads; ++l)
-            tma_load_3d(dst + (size_t)l * g.box_rows * g.rb, &tmA, &a_full[ia], kc * (g.rb >> 1),
-                        row0 + l * g.box_rows, b);
-          if (++ia == g.sa) { ia = 0; pa ^= 1u; }
+          auto load_slab = [&](int first_row) {
+            mbar_wait(&a_empty[ia], pa ^ 1u);
+            mbar_expect_tx(&a_full[ia], (uint32_t)g.slab_bytes);
+            uint8_t* dst = slabA + (size_t)ia * g.slab_bytes;
+            for (int l = 0; l < g.n_loads; ++l)
+              tma_load_3d(dst + (size_t)l * g.box_rows * g.rb, &tmA, &a_full[ia], kc * (g.rb >> 1),
+                          first_row + l * g.box_rows, b);
+            if (++ia == g.sa) { ia = 0; pa ^= 1u; }
+          };
+          if (!g.per_tap) load_slab(row0);
           for (int ts = 0; ts < g.n_tstages; ++ts) {
+            if (g.per_tap) load_slab(row0 - g.min_off + p.tap_off[ts]);
             mbar_wait(&b_empty[ib], pb ^ 1u);
             mbar_expect_tx(&b_full[ib], (uint32_t)g.bstage_bytes);
             tma_load_3d(stageB + (size_t)ib * g.bstage_bytes, &tmW, &b_full[ib], kc * (g.rb >> 1), ni * g.nt,
@@ -143,17 +148,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         const uint32_t d_base = tmem_base + (uint32_t)(buf * acc_cols);
         for (int kc = 0; kc < g.kc; ++kc) {
-          mbar_wait(&a_full[ia], pa);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(slabA + (size_t)ia * g.slab_bytes);
+          uint32_t a_base = 0;
+          if (!g.per_tap) {
+            mbar_wait(&a_full[ia], pa);
+            tc_fence_after();
+            a_base = smem_u32(slabA + (size_t)ia * g.slab_bytes);
+          }
           for (int ts = 0; ts < g.n_tstages; ++ts) {
+            if (g.per_tap) {
+              mbar_wait(&a_full[ia], pa);
+              tc_fence_after();
+              a_base = smem_u32(slabA + (size_t)ia * g.slab_bytes);
+            }
             mbar_wait(&b_full[ib], pb);
             tc_fence_after();
             const uint32_t b_base = smem_u32(stageB + (size_t)ib * g.bstage_bytes);
             const int t_end = min(g.tb, p.ntaps - ts * g.tb);
             for (int t = 0; t < t_end; ++t) {
               const int tap = ts * g.tb + t;
-              const uint32_t a_tap = a_base + (uint32_t)((p.tap_off[tap] - g.min_off) * g.rb);
+              const uint32_t a_tap = a_base + (g.per_tap ? 0u : (uint32_t)((p.tap_off[tap] - g.min_off) * g.rb));
               const uint32_t b_tap = b_base + (uint32_t)(t * g.nt * g.rb);
               for (int s = 0; s < g.msub; ++s) {
                 const uint32_t a_sub = a_tap + (uint32_t)(s * 128 * g.rb);
@@ -169,9 +182,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             umma_commit(&b_empty[ib]);  // W stage free once these MMAs retire
             if (++ib == g.sb) { ib = 0; pb ^= 1u; }
+            if (g.per_tap) {
+              umma_commit(&a_empty[ia]);
+              if (++ia == g.sa) { ia = 0; pa ^= 1u; }
+            }
           }
-          umma_commit(&a_empty[ia]);    // slab free
-          if (++ia == g.sa) { ia = 0; pa ^= 1u; }
+          if (!g.per_tap) {
+            umma_commit(&a_empty[ia]);    // slab free
+            if (++ia == g.sa) { ia = 0; pa ^= 1u; }
+          }
         }
         umma_commit(&acc_full[buf]);    // accumulators complete -> epilogue
         pacc[buf] ^= 1u;
@@ -264,6 +283,7 @@ struct TcTune {
   int slab_cap = 40960;        // bytes per slab
   int smem_budget = 220 * 1024;
   int base_offset_mode = 0;
+  int per_tap = 0;
   int max_ctas = 0;            // 0: number of SMs
 };
 
@@ -282,7 +302,8 @@ inline bool tc_plan(const ConvParams& c, int batch, const TcTune& tune, TcGeom* 
   int mn = c.tap_off[0], mx = c.tap_off[0];
   for (int j = 1; j < c.ntaps; ++j) { mn = c.tap_off[j] < mn ? c.tap_off[j] : mn; mx = c.tap_off[j] > mx ? c.tap_off[j] : mx; }
   g.min_off = mn;
-  const int span = mx - mn;
+  const int span = tune.per_tap ? 0 : mx - mn;
+  g.per_tap = tune.per_tap;
   int msub = 256 / g.nt;
   if (msub < 1) msub = 1;
   if (msub > tune.max_msub) msub = tune.max_msub;
@@ -297,14 +318,15 @@ inline bool tc_plan(const ConvParams& c, int batch, const TcTune& tune, TcGeom* 
   g.slab_bytes = g.n_loads * g.box_rows * g.rb;
   // W stage: a few taps per stage when a single tap is tiny
   int tb = 1;
-  while (tb < c.ntaps && tb < 16 && (tb * 2) * g.nt * g.rb <= 16384) tb *= 2;
+  while (!tune.per_tap && tb < c.ntaps && tb < 16 && (tb * 2) * g.nt * g.rb <= 16384) tb *= 2;
   if (tb > c.ntaps) tb = c.ntaps;
   g.tb = tb;
   g.n_tstages = (c.ntaps + tb - 1) / tb;
   g.bstage_bytes = tb * g.nt * g.rb;
   // ring depths within the shared-memory budget
-  const int bar_bytes = 1024 + 256;  // alignment slack + barriers
+  const int bar_bytes = 1024 + 512;  // alignment slack + barriers (36 x 8 B) + TMEM slot
   int sa = g.kc + 1 < kTcMaxStagesA ? g.kc + 1 : kTcMaxStagesA;
+  if (tune.per_tap) sa = 4;
   if (sa < 2) sa = 2;
   int sb = 4;
   while (sa > 2 && sa * g.slab_bytes + sb * g.bstage_bytes + bar_bytes > tune.smem_budget) --sa;
@@ -329,11 +351,13 @@ inline bool tc_plan(const ConvParams& c, int batch, const TcTune& tune, TcGeom* 
 
 inline cudaError_t launch_conv_tc(const ConvParams& c, const TcGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmW,
                                   int num_ctas, cudaStream_t stream) {
-  static int configured_smem = 0;
-  if (g.smem_bytes > configured_smem) {
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    configured_smem = 227 * 1024;
+    configured[dev] = true;
   }
   TcParams P;
   P.c = c;

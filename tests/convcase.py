@@ -100,5 +100,13 @@ if __name__ == "__main__":
     import os
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import __graft_entry__ as ge
-    kw = json.loads(sys.argv[1])
-    print("RESULT " + json.dumps(run_case(ge.load_package(), **kw)))
+    # argv[1]: JSON list of [name, kwargs]; one RESULT line per case, in order.  A
+    # faulting case ends the process (the context is gone), later cases stay unreported.
+    pkg_ = ge.load_package()
+    for name, kw in json.loads(sys.argv[1]):
+        try:
+            res = run_case(pkg_, **kw)
+        except Exception as exc:     # noqa: BLE001
+            print("RESULT " + json.dumps([name, {"ok": False, "error": repr(exc)[-300:]}]), flush=True)
+            break
+        print("RESULT " + json.dumps([name, res]), flush=True)

@@ -34,12 +34,22 @@ def test_simt_conv(pkg, shape, act_bf16):
     assert r["ok"], r
 
 
-@pytest.mark.parametrize("shape", SHAPES)
-def test_tcgen05_conv(shape):
+@pytest.fixture(scope="module")
+def tc_results():
     # own process: a faulting kernel would poison this process's CUDA context
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "convcase.py"), json.dumps(dict(shape, impl=1))],
-                       capture_output=True, text=True, timeout=300)
-    line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
-    assert line, (p.stdout + p.stderr)[-800:]
-    r = json.loads(line[-1][7:])
-    assert r["ok"], r
+    batch = [[str(i), dict(sh, impl=1)] for i, sh in enumerate(SHAPES)]
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "convcase.py"), json.dumps(batch)],
+                       capture_output=True, text=True, timeout=600)
+    out = {}
+    for line in p.stdout.splitlines():
+        if line.startswith("RESULT "):
+            name, res = json.loads(line[7:])
+            out[name] = res
+    out["_tail"] = (p.stdout + p.stderr)[-800:]
+    return out
+
+
+@pytest.mark.parametrize("idx", range(len(SHAPES)))
+def test_tcgen05_conv(tc_results, idx):
+    assert str(idx) in tc_results, tc_results["_tail"]
+    assert tc_results[str(idx)]["ok"], tc_results[str(idx)]

@@ -27,23 +27,27 @@ CASES = [
 
 
 def main():
-    impls = [int(a) for a in sys.argv[1:]] or [0, 1, 2]
+    impls = [int(a) for a in sys.argv[1:]] or [0, 1, 2, 3]
     results = {}
     for impl in impls:
-        for name, kw in CASES:
-            arg = dict(kw, impl=impl)
-            try:
-                p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "convcase.py"), json.dumps(arg)],
-                                   capture_output=True, text=True, timeout=180)
-                line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
-                if line:
-                    res = json.loads(line[-1][7:])
-                else:
-                    res = {"ok": False, "error": (p.stderr or p.stdout)[-400:], "rc": p.returncode}
-            except subprocess.TimeoutExpired:
-                res = {"ok": False, "error": "timeout"}
-            results[f"impl{impl}/{name}"] = res
-            print(f"impl{impl}/{name}: {res}", flush=True)
+        batch = [[name, dict(kw, impl=impl)] for name, kw in CASES]
+        try:
+            p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "convcase.py"), json.dumps(batch)],
+                               capture_output=True, text=True, timeout=600)
+            out, tail = p.stdout, (p.stderr or "")[-600:]
+        except subprocess.TimeoutExpired as e:
+            out, tail = (e.stdout or b"").decode() if isinstance(e.stdout, bytes) else (e.stdout or ""), "timeout"
+        seen = set()
+        for line in out.splitlines():
+            if line.startswith("RESULT "):
+                name, res = json.loads(line[7:])
+                results[f"impl{impl}/{name}"] = res
+                seen.add(name)
+                print(f"impl{impl}/{name}: {res}", flush=True)
+        for name, _ in CASES:
+            if name not in seen:
+                results[f"impl{impl}/{name}"] = {"ok": False, "error": "not reached: " + tail}
+                print(f"impl{impl}/{name}: not reached ({tail[-200:]})", flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "conv_probe.json"), "w") as f:
         json.dump(results, f, indent=1)
