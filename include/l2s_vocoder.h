@@ -143,7 +143,8 @@ int l2s_debug_tap(l2s_vocoder* v, const char* name, float* host_dst, int64_t num
 /* Run ONE generic tap-offset convolution (the building block every layer maps
  * onto) on caller-provided device buffers.  impl: 0 = CUDA-core kernel,
  * 1 = tcgen05 kernel (halo slab + row-shifted shared-memory descriptors),
- * 2 = same with the descriptor base-offset field filled in (probe variant),
+ * 2 = retired probe (descriptor base-offset field filled in: measured WRONG on sm_100a,
+ *     row-shifted descriptors need base_offset = 0),
  * 3 = one TMA-loaded A tile per tap, no row-shifted descriptors (probe / fallback).
  * `scale` is the divisor applied in the epilogue.  See csrc/conv_common.cuh. */
 typedef struct l2s_conv_desc {
@@ -168,7 +169,7 @@ int l2s_debug_conv(const l2s_conv_desc* d, int32_t impl, int32_t device, void* s
 int l2s_debug_layer_time(l2s_vocoder* v, int32_t idx, float* ms, double* flops, char* name, int32_t name_len);
 
 /* Override a tuning / descriptor knob (tests and probes only): force_simt,
- * stop_after_stage, stop_after_pre, base_offset_mode, per_tap, max_msub, slab_cap, max_ctas,
+ * stop_after_stage, stop_after_pre, per_tap, max_msub, slab_cap, max_ctas,
  * embed_tap, layer_events. */
 int l2s_debug_set(const char* key, int64_t value);
 

@@ -51,7 +51,6 @@ struct TcGeom {
   int sb;            // W ring depth
   int tmem_cols;     // power of two >= 2 * msub * nt
   int total_items;
-  int base_offset_mode;  // 0: descriptor base_offset field left 0; 1: (addr >> 7) & 7
   int per_tap;           // 1: probe/fallback mode, one A tile per tap by TMA (no row-shifted descriptors)
   uint32_t idesc;
   int smem_bytes;
@@ -61,6 +60,18 @@ struct TcParams {
   ConvParams c;
   TcGeom g;
 };
+
+// K16 consecutive K = 16 slices of one (tap, 64-channel chunk): descriptors advance by 32 bytes.
+template <int K16>
+__device__ __forceinline__ void issue_chunk(bool leader, uint32_t d_addr, uint32_t desc_hi, uint32_t a_lo, uint32_t b_lo,
+                                            uint32_t idesc, uint32_t first) {
+#pragma unroll
+  for (int k = 0; k < K16; ++k) {
+    const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2u * k);
+    const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2u * k);
+    if (leader) umma_bf16(d_addr, da, db, idesc, (first | (uint32_t)k) != 0u ? 1u : 0u);
+  }
+}
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcParams P) {
@@ -104,98 +115,118 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int ia = 0, ib = 0;
-      uint32_t pa = 0, pb = 0;
-      for (int item = blockIdx.x; item < g.total_items; item += gridDim.x) {
-        const int b = item / items_per_b;
-        const int rem = item - b * items_per_b;
-        const int mi = rem / g.n_ntiles;
-        const int ni = rem - mi * g.n_ntiles;
-        const int row0 = mi * 128 * g.msub + g.min_off;
-        for (int kc = 0; kc < g.kc; ++kc) {
-          auto load_slab = [&](int first_row) {
-            mbar_wait(&a_empty[ia], pa ^ 1u);
+    // The whole warp walks the loops in uniform control flow (so addresses and
+    // coordinates live in uniform registers); one elected lane issues.
+    const bool leader = elect_one();
+    int ia = 0, ib = 0;
+    uint32_t pa = 0, pb = 0;
+    const uint32_t box_bytes = (uint32_t)(g.box_rows * g.rb);
+    for (int item = blockIdx.x; item < g.total_items; item += gridDim.x) {
+      const int b = item / items_per_b;
+      const int rem = item - b * items_per_b;
+      const int mi = rem / g.n_ntiles;
+      const int ni = rem - mi * g.n_ntiles;
+      const int row0 = mi * 128 * g.msub + g.min_off;
+      for (int kc = 0; kc < g.kc; ++kc) {
+        const int ch0 = kc * (g.rb >> 1);
+        if (!g.per_tap) {
+          mbar_wait(&a_empty[ia], pa ^ 1u);
+          if (leader) {
             mbar_expect_tx(&a_full[ia], (uint32_t)g.slab_bytes);
             uint8_t* dst = slabA + (size_t)ia * g.slab_bytes;
             for (int l = 0; l < g.n_loads; ++l)
-              tma_load_3d(dst + (size_t)l * g.box_rows * g.rb, &tmA, &a_full[ia], kc * (g.rb >> 1),
-                          first_row + l * g.box_rows, b);
-            if (++ia == g.sa) { ia = 0; pa ^= 1u; }
-          };
-          if (!g.per_tap) load_slab(row0);
-          for (int ts = 0; ts < g.n_tstages; ++ts) {
-            if (g.per_tap) load_slab(row0 - g.min_off + p.tap_off[ts]);
-            mbar_wait(&b_empty[ib], pb ^ 1u);
-            mbar_expect_tx(&b_full[ib], (uint32_t)g.bstage_bytes);
-            tma_load_3d(stageB + (size_t)ib * g.bstage_bytes, &tmW, &b_full[ib], kc * (g.rb >> 1), ni * g.nt,
-                        ts * g.tb);
-            if (++ib == g.sb) { ib = 0; pb ^= 1u; }
+              tma_load_3d(dst + (size_t)l * box_bytes, &tmA, &a_full[ia], ch0, row0 + l * g.box_rows, b);
           }
+          if (++ia == g.sa) { ia = 0; pa ^= 1u; }
+        }
+        for (int ts = 0; ts < g.n_tstages; ++ts) {
+          if (g.per_tap) {
+            mbar_wait(&a_empty[ia], pa ^ 1u);
+            if (leader) {
+              mbar_expect_tx(&a_full[ia], (uint32_t)g.slab_bytes);
+              uint8_t* dst = slabA + (size_t)ia * g.slab_bytes;
+              const int r0 = row0 - g.min_off + p.tap_off[ts];
+              for (int l = 0; l < g.n_loads; ++l)
+                tma_load_3d(dst + (size_t)l * box_bytes, &tmA, &a_full[ia], ch0, r0 + l * g.box_rows, b);
+            }
+            if (++ia == g.sa) { ia = 0; pa ^= 1u; }
+          }
+          mbar_wait(&b_empty[ib], pb ^ 1u);
+          if (leader) {
+            mbar_expect_tx(&b_full[ib], (uint32_t)g.bstage_bytes);
+            tma_load_3d(stageB + (size_t)ib * g.bstage_bytes, &tmW, &b_full[ib], ch0, ni * g.nt, ts * g.tb);
+          }
+          if (++ib == g.sb) { ib = 0; pb ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      const uint64_t tmpl = umma_desc_template((uint32_t)g.rb);
-      int ia = 0, ib = 0;
-      uint32_t pa = 0, pb = 0;
-      uint32_t pacc[2] = {0u, 0u};
-      int buf = 0;
-      for (int item = blockIdx.x; item < g.total_items; item += gridDim.x) {
-        mbar_wait(&acc_empty[buf], pacc[buf] ^ 1u);
-        tc_fence_after();
-        const uint32_t d_base = tmem_base + (uint32_t)(buf * acc_cols);
-        for (int kc = 0; kc < g.kc; ++kc) {
-          uint32_t a_base = 0;
-          if (!g.per_tap) {
+    // Uniform control flow for the whole warp; only the tcgen05.mma / commit
+    // instructions are predicated on the elected lane.  Descriptors differ only in
+    // their low word (start address >> 4), advanced by additions.
+    const bool leader = elect_one();
+    const uint64_t tmpl = umma_desc_template((uint32_t)g.rb);
+    const uint32_t desc_hi = (uint32_t)(tmpl >> 32);
+    const uint32_t desc_lo_fixed = (uint32_t)tmpl;            // LBO field
+    const uint32_t sub_step = (uint32_t)(128 * g.rb) >> 4;   // next 128-row accumulator
+    const uint32_t tapw_step = (uint32_t)(g.nt * g.rb) >> 4; // next tap inside a W stage
+    int ia = 0, ib = 0;
+    uint32_t pa = 0, pb = 0;
+    uint32_t pacc0 = 0, pacc1 = 0;
+    int buf = 0;
+    for (int item = blockIdx.x; item < g.total_items; item += gridDim.x) {
+      mbar_wait(&acc_empty[buf], (buf ? pacc1 : pacc0) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_base = tmem_base + (uint32_t)(buf * acc_cols);
+      for (int kc = 0; kc < g.kc; ++kc) {
+        uint32_t a_lo = 0;
+        if (!g.per_tap) {
+          mbar_wait(&a_full[ia], pa);
+          tc_fence_after();
+          a_lo = desc_lo_fixed | ((smem_u32(slabA + (size_t)ia * g.slab_bytes) & 0x3FFFFu) >> 4);
+        }
+        for (int ts = 0; ts < g.n_tstages; ++ts) {
+          if (g.per_tap) {
             mbar_wait(&a_full[ia], pa);
             tc_fence_after();
-            a_base = smem_u32(slabA + (size_t)ia * g.slab_bytes);
+            a_lo = desc_lo_fixed | ((smem_u32(slabA + (size_t)ia * g.slab_bytes) & 0x3FFFFu) >> 4);
           }
-          for (int ts = 0; ts < g.n_tstages; ++ts) {
-            if (g.per_tap) {
-              mbar_wait(&a_full[ia], pa);
-              tc_fence_after();
-              a_base = smem_u32(slabA + (size_t)ia * g.slab_bytes);
-            }
-            mbar_wait(&b_full[ib], pb);
-            tc_fence_after();
-            const uint32_t b_base = smem_u32(stageB + (size_t)ib * g.bstage_bytes);
-            const int t_end = min(g.tb, p.ntaps - ts * g.tb);
-            for (int t = 0; t < t_end; ++t) {
-              const int tap = ts * g.tb + t;
-              const uint32_t a_tap = a_base + (g.per_tap ? 0u : (uint32_t)((p.tap_off[tap] - g.min_off) * g.rb));
-              const uint32_t b_tap = b_base + (uint32_t)(t * g.nt * g.rb);
-              for (int s = 0; s < g.msub; ++s) {
-                const uint32_t a_sub = a_tap + (uint32_t)(s * 128 * g.rb);
-                for (int k = 0; k < g.k16; ++k) {
-                  const uint32_t a_addr = a_sub + (uint32_t)(k * 32);
-                  uint64_t da = umma_desc(tmpl, a_addr);
-                  if (g.base_offset_mode == 1) da |= (uint64_t)((a_addr >> 7) & 7u) << 49;
-                  const uint64_t db = umma_desc(tmpl, b_tap + (uint32_t)(k * 32));
-                  const uint32_t accumulate = (kc | tap | k) != 0 ? 1u : 0u;
-                  umma_bf16(d_base + (uint32_t)(s * g.nt), da, db, g.idesc, accumulate);
-                }
-              }
-            }
-            umma_commit(&b_empty[ib]);  // W stage free once these MMAs retire
-            if (++ib == g.sb) { ib = 0; pb ^= 1u; }
-            if (g.per_tap) {
-              umma_commit(&a_empty[ia]);
-              if (++ia == g.sa) { ia = 0; pa ^= 1u; }
+          mbar_wait(&b_full[ib], pb);
+          tc_fence_after();
+          uint32_t b_lo = desc_lo_fixed | ((smem_u32(stageB + (size_t)ib * g.bstage_bytes) & 0x3FFFFu) >> 4);
+          const int t_end = min(g.tb, p.ntaps - ts * g.tb);
+          for (int t = 0; t < t_end; ++t, b_lo += tapw_step) {
+            const int tap = ts * g.tb + t;
+            uint32_t a_sub = a_lo + (g.per_tap ? 0u : ((uint32_t)((p.tap_off[tap] - g.min_off) * g.rb) >> 4));
+            const uint32_t first = (uint32_t)(kc | tap);
+            uint32_t d_addr = d_base;
+            if (g.k16 == 4) {
+              for (int sub = 0; sub < g.msub; ++sub, a_sub += sub_step, d_addr += (uint32_t)g.nt)
+                issue_chunk<4>(leader, d_addr, desc_hi, a_sub, b_lo, g.idesc, first);
+            } else if (g.k16 == 2) {
+              for (int sub = 0; sub < g.msub; ++sub, a_sub += sub_step, d_addr += (uint32_t)g.nt)
+                issue_chunk<2>(leader, d_addr, desc_hi, a_sub, b_lo, g.idesc, first);
+            } else {
+              for (int sub = 0; sub < g.msub; ++sub, a_sub += sub_step, d_addr += (uint32_t)g.nt)
+                issue_chunk<1>(leader, d_addr, desc_hi, a_sub, b_lo, g.idesc, first);
             }
           }
-          if (!g.per_tap) {
-            umma_commit(&a_empty[ia]);    // slab free
+          if (leader) umma_commit(&b_empty[ib]);   // W stage free once these MMAs retire
+          if (++ib == g.sb) { ib = 0; pb ^= 1u; }
+          if (g.per_tap) {
+            if (leader) umma_commit(&a_empty[ia]);
             if (++ia == g.sa) { ia = 0; pa ^= 1u; }
           }
         }
-        umma_commit(&acc_full[buf]);    // accumulators complete -> epilogue
-        pacc[buf] ^= 1u;
-        buf ^= 1;
+        if (!g.per_tap) {
+          if (leader) umma_commit(&a_empty[ia]);    // slab free
+          if (++ia == g.sa) { ia = 0; pa ^= 1u; }
+        }
       }
+      if (leader) umma_commit(&acc_full[buf]);      // accumulators complete -> epilogue
+      if (buf) pacc1 ^= 1u; else pacc0 ^= 1u;
+      buf ^= 1;
     }
   } else {
     // ---------------------------------------------------------------- epilogue
@@ -282,7 +313,6 @@ struct TcTune {
   int max_msub = 8;
   int slab_cap = 40960;        // bytes per slab
   int smem_budget = 220 * 1024;
-  int base_offset_mode = 0;
   int per_tap = 0;
   int max_ctas = 0;            // 0: number of SMs
 };
@@ -343,7 +373,6 @@ inline bool tc_plan(const ConvParams& c, int batch, const TcTune& tune, TcGeom* 
   if (cols > 512) return false;
   g.tmem_cols = cols;
   g.total_items = batch * g.m_items * g.n_ntiles;
-  g.base_offset_mode = tune.base_offset_mode;
   g.idesc = umma_idesc_bf16(128u, (uint32_t)g.nt);
   *out = g;
   return true;

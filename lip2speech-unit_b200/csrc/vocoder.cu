@@ -27,7 +27,6 @@ struct Knobs {
   long long force_simt = 0;        // bf16 mode: run the CUDA-core kernel on the bf16 operands
   long long stop_after_stage = -1; // >= 0: stop after that MRF stage (taps stay valid)
   long long stop_after_pre = 0;    // stop after conv_pre
-  long long base_offset_mode = 0;
   long long per_tap = 0;
   long long max_msub = 8;
   long long slab_cap = 40960;
@@ -261,7 +260,6 @@ TcTune current_tune(const l2s_vocoder* v) {
   TcTune t;
   t.max_msub = (int)g_knobs.max_msub;
   t.slab_cap = (int)g_knobs.slab_cap;
-  t.base_offset_mode = (int)g_knobs.base_offset_mode;
   t.per_tap = (int)g_knobs.per_tap;
   t.max_ctas = g_knobs.max_ctas > 0 ? (int)g_knobs.max_ctas : (v ? v->num_sms : 148);
   return t;
@@ -757,7 +755,7 @@ int l2s_debug_conv(const l2s_conv_desc* d, int32_t impl, int32_t device, void* s
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     TcTune tune = current_tune(nullptr);
     if (g_knobs.max_ctas <= 0) tune.max_ctas = sms;
-    tune.base_offset_mode = impl == 2 ? 1 : 0;
+    if (impl == 2) { say("impl 2 (descriptor base-offset probe) was removed: it gives wrong results on sm_100a"); return L2S_ERR_UNSUPPORTED; }
     if (impl == 3) tune.per_tap = 1;
     TcGeom g;
     if (!tc_plan(p, d->batch, tune, &g)) { say("no tcgen05 plan"); return L2S_ERR_UNSUPPORTED; }
@@ -794,7 +792,6 @@ int l2s_debug_set(const char* key, int64_t value) {
   if (k == "force_simt") g_knobs.force_simt = value;
   else if (k == "stop_after_stage") g_knobs.stop_after_stage = value;
   else if (k == "stop_after_pre") g_knobs.stop_after_pre = value;
-  else if (k == "base_offset_mode") g_knobs.base_offset_mode = value;
   else if (k == "per_tap") g_knobs.per_tap = value;
   else if (k == "max_msub") g_knobs.max_msub = value;
   else if (k == "slab_cap") g_knobs.slab_cap = value;

@@ -134,7 +134,8 @@ def test_lazy_fold_matches_removed_weight_norm(pkg, weights):
     code, mel, spkr = vo.synthetic_inputs(1, 20, seed=3)
     a = make_gen(pkg, h, sds["trained"], "fp32", fold=True)(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV))
     b = make_gen(pkg, h, sds["trained"], "fp32", fold=False)(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV))
-    assert torch.equal(a, b)
+    # the lazy fold runs where the parameters live (cuda), remove_weight_norm() folded on the CPU here
+    assert float((a - b).abs().max()) <= 2e-6
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
