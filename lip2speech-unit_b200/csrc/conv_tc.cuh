@@ -50,6 +50,7 @@ struct TcGeom {
   int bstage_bytes;  // tb * nt * rb
   int sb;            // W ring depth
   int tmem_cols;     // power of two >= 2 * msub * nt
+  int cw;            // epilogue chunk width in columns: 32 when nt % 32 == 0, else 16
   int total_items;
   int per_tap;           // 1: probe/fallback mode, one A tile per tap by TMA (no row-shifted descriptors)
   uint32_t idesc;
@@ -60,6 +61,77 @@ struct TcParams {
   ConvParams c;
   TcGeom g;
 };
+
+constexpr int kEpiTileWords = 32 * 33;   // warp-private transpose tile, pitch CW + 1 words
+
+// Epilogue of one [32 rows x CW columns] accumulator chunk owned by one warp.
+// TMEM hands every lane one ROW (32x32b shape); storing that way would make each
+// 16-byte global access of the warp touch 32 different 128-byte lines.  The chunk
+// is therefore transposed through a warp-private shared-memory tile so that the
+// residual / branch-sum loads and the fp32 / bf16 stores are line-contiguous:
+// lane -> (row = i * RPI + lane / LPR, 4 consecutive columns (lane % LPR) * 4).
+template <int CW>
+__device__ __forceinline__ void epilogue_chunk(const ConvParams& p, float* tile, uint32_t taddr, int b, int q_base,
+                                               int n_base, int lane) {
+  constexpr int LPR = CW / 4;        // lanes per row
+  constexpr int RPI = 32 / LPR;      // rows per warp instruction
+  constexpr int ITERS = 32 / RPI;
+  constexpr int PITCH = CW + 1;
+  const int crow = lane / LPR;
+  const int ccol = (lane % LPR) * 4;
+  const int n = n_base + ccol;
+
+  // global index of my granule in row q_base + crow (rows advance by RPI * ntot)
+  const long long idx0 = (long long)(q_base + crow) * p.ntot + n + p.out_shift;
+  const long long row_step = (long long)RPI * p.ntot;
+  const long long gbase = (long long)b * p.out_valid;
+
+  // issue the independent global loads first (they do not depend on the accumulator)
+  float4 rv[ITERS], av[ITERS];
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i) {
+    const long long idx = idx0 + i * row_step;
+    const bool ok = (q_base + crow + i * RPI) < p.mrows && idx >= 0 && idx < p.out_valid;
+    rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok && p.res) rv[i] = *reinterpret_cast<const float4*>(p.res + gbase + idx);
+    if (ok && p.acc_in) av[i] = *reinterpret_cast<const float4*>(p.acc_in + gbase + idx);
+  }
+  const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+
+  uint32_t r[CW];
+  if constexpr (CW == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < CW; ++j) tile[lane * PITCH + j] = __uint_as_float(r[j]);
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i) {
+    const int row = i * RPI + crow;
+    const long long idx = idx0 + i * row_step;
+    const bool ok = (q_base + row) < p.mrows && idx >= 0 && idx < p.out_valid;
+    const float* t = tile + row * PITCH + ccol;
+    float v0 = t[0] + bv.x + rv[i].x + av[i].x;
+    float v1 = t[1] + bv.y + rv[i].y + av[i].y;
+    float v2 = t[2] + bv.z + rv[i].z + av[i].z;
+    float v3 = t[3] + bv.w + rv[i].w + av[i].w;
+    if (p.div != 1.0f) {
+      v0 = __fdiv_rn(v0, p.div); v1 = __fdiv_rn(v1, p.div); v2 = __fdiv_rn(v2, p.div); v3 = __fdiv_rn(v3, p.div);
+    }
+    if (ok) {
+      if (p.out_raw) *reinterpret_cast<float4*>(p.out_raw + gbase + idx) = make_float4(v0, v1, v2, v3);
+      if (p.out_act) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(lrelu(v0, p.slope), lrelu(v1, p.slope));
+        __nv_bfloat162 hi = __floats2bfloat162_rn(lrelu(v2, p.slope), lrelu(v3, p.slope));
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out_act) + gbase + idx) = pk;
+      }
+    }
+  }
+  __syncwarp();   // the tile is rewritten by the next chunk
+}
 
 // K16 consecutive K = 16 slices of one (tap, 64-channel chunk): descriptors advance by 32 bytes.
 template <int K16>
@@ -92,6 +164,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* acc_full = b_empty + kTcMaxStagesB;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* epi_tiles = reinterpret_cast<float*>(bars + 40);   // 36 barriers + slot, 16-byte aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -231,37 +304,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ---------------------------------------------------------------- epilogue
     const int quad = warp & 3;            // TMEM lane quadrant this warp may read
-    const int half = (warp - 2) >> 2;     // two warps share a quadrant, alternate column groups
-    const int groups_per_sub = g.nt >> 4;
-    const int n_groups = g.msub * groups_per_sub;
-    uint32_t pacc[2] = {0u, 0u};
+    const int half = (warp - 2) >> 2;     // two warps share a quadrant, alternate column chunks
+    float* tile = epi_tiles + (size_t)(warp - 2) * kEpiTileWords;
+    uint32_t pacc0 = 0, pacc1 = 0;
     int buf = 0;
     for (int item = blockIdx.x; item < g.total_items; item += gridDim.x) {
       const int b = item / items_per_b;
       const int rem = item - b * items_per_b;
       const int mi = rem / g.n_ntiles;
       const int ni = rem - mi * g.n_ntiles;
-      mbar_wait(&acc_full[buf], pacc[buf]);
+      mbar_wait(&acc_full[buf], buf ? pacc1 : pacc0);
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * acc_cols);
-      for (int grp = half; grp < n_groups; grp += 2) {
-        const int s = grp / groups_per_sub;
-        const int cg = grp - s * groups_per_sub;
-        uint32_t r[16];
-        tmem_ld16(t_base + (uint32_t)(s * g.nt + cg * 16), r);
-        tmem_ld_wait();
-        const int q = (mi * g.msub + s) * 128 + quad * 32 + lane;
-        if (q < p.mrows) {
-          float v[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-          conv_epilogue<__nv_bfloat16, 16>(p, b, q, ni * g.nt + cg * 16, v);
+      if (g.cw == 32) {
+        const int chunks_per_sub = g.nt >> 5;
+        const int n_chunks = g.msub * chunks_per_sub;
+        for (int ch = half; ch < n_chunks; ch += 2) {
+          const int s = ch / chunks_per_sub;
+          const int c0 = (ch - s * chunks_per_sub) << 5;
+          epilogue_chunk<32>(p, tile, t_base + (uint32_t)(s * g.nt + c0), b, (mi * g.msub + s) * 128 + quad * 32,
+                             ni * g.nt + c0, lane);
+        }
+      } else {
+        const int chunks_per_sub = g.nt >> 4;
+        const int n_chunks = g.msub * chunks_per_sub;
+        for (int ch = half; ch < n_chunks; ch += 2) {
+          const int s = ch / chunks_per_sub;
+          const int c0 = (ch - s * chunks_per_sub) << 4;
+          epilogue_chunk<16>(p, tile, t_base + (uint32_t)(s * g.nt + c0), b, (mi * g.msub + s) * 128 + quad * 32,
+                             ni * g.nt + c0, lane);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
-      pacc[buf] ^= 1u;
+      if (buf) pacc1 ^= 1u; else pacc0 ^= 1u;
       buf ^= 1;
     }
   }
@@ -354,7 +431,7 @@ inline bool tc_plan(const ConvParams& c, int batch, const TcTune& tune, TcGeom* 
   g.n_tstages = (c.ntaps + tb - 1) / tb;
   g.bstage_bytes = tb * g.nt * g.rb;
   // ring depths within the shared-memory budget
-  const int bar_bytes = 1024 + 512;  // alignment slack + barriers (36 x 8 B) + TMEM slot
+  const int bar_bytes = 1024 + 320 + kTcEpiWarps * kEpiTileWords * 4;  // alignment slack, barriers + TMEM slot, epilogue tiles
   int sa = g.kc + 1 < kTcMaxStagesA ? g.kc + 1 : kTcMaxStagesA;
   if (tune.per_tap) sa = 4;
   if (sa < 2) sa = 2;
@@ -374,6 +451,7 @@ inline bool tc_plan(const ConvParams& c, int batch, const TcTune& tune, TcGeom* 
   g.tmem_cols = cols;
   g.total_items = batch * g.m_items * g.n_ntiles;
   g.idesc = umma_idesc_bf16(128u, (uint32_t)g.nt);
+  g.cw = g.nt % 32 == 0 ? 32 : 16;
   *out = g;
   return true;
 }
