@@ -62,7 +62,7 @@ struct TcParams {
   TcGeom g;
 };
 
-constexpr int kEpiTileWords = 32 * 33;   // warp-private transpose tile, pitch CW + 1 words
+constexpr int kEpiTileWords = 32 * 32;   // warp-private transpose tile: 32 rows x CW fp32, XOR-swizzled float4 slots
 
 // Epilogue of one [32 rows x CW columns] accumulator chunk owned by one warp.
 // TMEM hands every lane one ROW (32x32b shape); storing that way would make each
@@ -70,16 +70,24 @@ constexpr int kEpiTileWords = 32 * 33;   // warp-private transpose tile, pitch C
 // is therefore transposed through a warp-private shared-memory tile so that the
 // residual / branch-sum loads and the fp32 / bf16 stores are line-contiguous:
 // lane -> (row = i * RPI + lane / LPR, 4 consecutive columns (lane % LPR) * 4).
+// Tile slot of (row, float4 c4): row * LPR + (c4 ^ swz(row)); both the row-per-lane
+// writes and the column-per-lane reads are bank-conflict free.
+template <int CW>
+__device__ __forceinline__ int epi_slot(int row, int c4) {
+  if constexpr (CW == 32) return row * 8 + (c4 ^ (row & 7));
+  else return row * 4 + (c4 ^ ((row >> 1) & 3));
+}
+
 template <int CW>
 __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, float* tile, uint32_t taddr, int b, int q_base,
                                                int n_base, int lane) {
   constexpr int LPR = CW / 4;        // lanes per row
   constexpr int RPI = 32 / LPR;      // rows per warp instruction
   constexpr int ITERS = 32 / RPI;
-  constexpr int PITCH = CW + 1;
   const int crow = lane / LPR;
-  const int ccol = (lane % LPR) * 4;
-  const int n = n_base + ccol;
+  const int c4 = lane % LPR;
+  const int n = n_base + c4 * 4;
+  float4* tile4 = reinterpret_cast<float4*>(tile);
 
   // global index of my granule in row q_base + crow (rows advance by RPI * ntot)
   const long long idx0 = (long long)(q_base + crow) * p.ntot + n + p.out_shift;
@@ -88,14 +96,17 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, float* tile,
 
   // issue the independent global loads first (they do not depend on the accumulator)
   float4 rv[ITERS], av[ITERS];
+  const bool has_res = p.res != nullptr, has_acc = p.acc_in != nullptr;
+  if (has_res || has_acc) {
 #pragma unroll
-  for (int i = 0; i < ITERS; ++i) {
-    const long long idx = idx0 + i * row_step;
-    const bool ok = (q_base + crow + i * RPI) < p.mrows && idx >= 0 && idx < p.out_valid;
-    rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ok && p.res) rv[i] = *reinterpret_cast<const float4*>(p.res + gbase + idx);
-    if (ok && p.acc_in) av[i] = *reinterpret_cast<const float4*>(p.acc_in + gbase + idx);
+    for (int i = 0; i < ITERS; ++i) {
+      const long long idx = idx0 + i * row_step;
+      const bool ok = (q_base + crow + i * RPI) < p.mrows && idx >= 0 && idx < p.out_valid;
+      rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok && has_res) rv[i] = *reinterpret_cast<const float4*>(p.res + gbase + idx);
+      if (ok && has_acc) av[i] = *reinterpret_cast<const float4*>(p.acc_in + gbase + idx);
+    }
   }
   const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
 
@@ -103,18 +114,19 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, float* tile,
   if constexpr (CW == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
   tmem_ld_wait();
 #pragma unroll
-  for (int j = 0; j < CW; ++j) tile[lane * PITCH + j] = __uint_as_float(r[j]);
+  for (int j = 0; j < LPR; ++j)
+    tile4[epi_slot<CW>(lane, j)] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                               __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
   __syncwarp();
 #pragma unroll
   for (int i = 0; i < ITERS; ++i) {
     const int row = i * RPI + crow;
     const long long idx = idx0 + i * row_step;
     const bool ok = (q_base + row) < p.mrows && idx >= 0 && idx < p.out_valid;
-    const float* t = tile + row * PITCH + ccol;
-    float v0 = t[0] + bv.x + rv[i].x + av[i].x;
-    float v1 = t[1] + bv.y + rv[i].y + av[i].y;
-    float v2 = t[2] + bv.z + rv[i].z + av[i].z;
-    float v3 = t[3] + bv.w + rv[i].w + av[i].w;
+    const float4 t = tile4[epi_slot<CW>(row, c4)];
+    float v0 = t.x + bv.x, v1 = t.y + bv.y, v2 = t.z + bv.z, v3 = t.w + bv.w;
+    if (has_res) { v0 += rv[i].x; v1 += rv[i].y; v2 += rv[i].z; v3 += rv[i].w; }
+    if (has_acc) { v0 += av[i].x; v1 += av[i].y; v2 += av[i].z; v3 += av[i].w; }
     if (p.div != 1.0f) {
       v0 = __fdiv_rn(v0, p.div); v1 = __fdiv_rn(v1, p.div); v2 = __fdiv_rn(v2, p.div); v3 = __fdiv_rn(v3, p.div);
     }
