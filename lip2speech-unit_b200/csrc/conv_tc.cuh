@@ -78,34 +78,33 @@ __device__ __forceinline__ int epi_slot(int row, int c4) {
   else return row * 4 + (c4 ^ ((row >> 1) & 3));
 }
 
-template <int CW>
-__device__ __forceinline__ void epilogue_chunk(const ConvParams& p, float* tile, uint32_t taddr, int b, int q_base,
-                                               int n_base, int lane) {
+template <int CW, bool FULL>
+__device__ __forceinline__ void epilogue_body(const ConvParams& p, float4* tile4, uint32_t taddr, long long e0, int step,
+                                              int i_lo, int i_hi, int n, int lane, int crow, int c4) {
   constexpr int LPR = CW / 4;        // lanes per row
   constexpr int RPI = 32 / LPR;      // rows per warp instruction
   constexpr int ITERS = 32 / RPI;
-  const int crow = lane / LPR;
-  const int c4 = lane % LPR;
-  const int n = n_base + c4 * 4;
-  float4* tile4 = reinterpret_cast<float4*>(tile);
-
-  // global index of my granule in row q_base + crow (rows advance by RPI * ntot)
-  const long long idx0 = (long long)(q_base + crow) * p.ntot + n + p.out_shift;
-  const long long row_step = (long long)RPI * p.ntot;
-  const long long gbase = (long long)b * p.out_valid;
-
   // issue the independent global loads first (they do not depend on the accumulator)
-  float4 rv[ITERS], av[ITERS];
+  float4 rv[ITERS];
   const bool has_res = p.res != nullptr, has_acc = p.acc_in != nullptr;
-  if (has_res || has_acc) {
+  if (has_res) {
+    const float* rp = p.res + e0;
 #pragma unroll
-    for (int i = 0; i < ITERS; ++i) {
-      const long long idx = idx0 + i * row_step;
-      const bool ok = (q_base + crow + i * RPI) < p.mrows && idx >= 0 && idx < p.out_valid;
-      rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ok && has_res) rv[i] = *reinterpret_cast<const float4*>(p.res + gbase + idx);
-      if (ok && has_acc) av[i] = *reinterpret_cast<const float4*>(p.acc_in + gbase + idx);
+    for (int i = 0; i < ITERS; ++i, rp += step)
+      rv[i] = (FULL || (i >= i_lo && i < i_hi)) ? *reinterpret_cast<const float4*>(rp) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  // the branch sum (10 of 96 launches) is fetched after the residual has landed, into the same registers
+  if (has_acc) {
+    const float* ap = p.acc_in + e0;
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i, ap += step) {
+      if (FULL || (i >= i_lo && i < i_hi)) {
+        const float4 a = *reinterpret_cast<const float4*>(ap);
+        if (has_res) { rv[i].x += a.x; rv[i].y += a.y; rv[i].z += a.z; rv[i].w += a.w; }
+        else rv[i] = a;
+      } else if (!has_res) {
+        rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
   }
   const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
@@ -118,31 +117,62 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, float* tile,
     tile4[epi_slot<CW>(lane, j)] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
                                                __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
   __syncwarp();
+  float* raw_p = p.out_raw ? p.out_raw + e0 : nullptr;
+  __nv_bfloat16* act_p = p.out_act ? reinterpret_cast<__nv_bfloat16*>(p.out_act) + e0 : nullptr;
+  const float slope = p.slope;
+  // The tensor-core (bf16) mode multiplies by the reciprocal of the branch count; the
+  // fp32 CUDA-core mode keeps the reference's true division (conv_common.cuh).
+  const float inv_div = 1.0f / p.div;
 #pragma unroll
   for (int i = 0; i < ITERS; ++i) {
-    const int row = i * RPI + crow;
-    const long long idx = idx0 + i * row_step;
-    const bool ok = (q_base + row) < p.mrows && idx >= 0 && idx < p.out_valid;
-    const float4 t = tile4[epi_slot<CW>(row, c4)];
+    const float4 t = tile4[epi_slot<CW>(i * RPI + crow, c4)];
     float v0 = t.x + bv.x, v1 = t.y + bv.y, v2 = t.z + bv.z, v3 = t.w + bv.w;
-    if (has_res) { v0 += rv[i].x; v1 += rv[i].y; v2 += rv[i].z; v3 += rv[i].w; }
-    if (has_acc) { v0 += av[i].x; v1 += av[i].y; v2 += av[i].z; v3 += av[i].w; }
-    if (p.div != 1.0f) {
-      v0 = __fdiv_rn(v0, p.div); v1 = __fdiv_rn(v1, p.div); v2 = __fdiv_rn(v2, p.div); v3 = __fdiv_rn(v3, p.div);
-    }
-    if (ok) {
-      if (p.out_raw) *reinterpret_cast<float4*>(p.out_raw + gbase + idx) = make_float4(v0, v1, v2, v3);
-      if (p.out_act) {
-        __nv_bfloat162 lo = __floats2bfloat162_rn(lrelu(v0, p.slope), lrelu(v1, p.slope));
-        __nv_bfloat162 hi = __floats2bfloat162_rn(lrelu(v2, p.slope), lrelu(v3, p.slope));
+    if (has_res || has_acc) { v0 += rv[i].x; v1 += rv[i].y; v2 += rv[i].z; v3 += rv[i].w; }
+    v0 *= inv_div; v1 *= inv_div; v2 *= inv_div; v3 *= inv_div;
+    if (FULL || (i >= i_lo && i < i_hi)) {
+      if (raw_p) *reinterpret_cast<float4*>(raw_p + (long long)i * step) = make_float4(v0, v1, v2, v3);
+      if (act_p) {
+        // leaky_relu for 0 < slope < 1 is max(v, v * slope)
+        __nv_bfloat162 lo = __floats2bfloat162_rn(fmaxf(v0, v0 * slope), fmaxf(v1, v1 * slope));
+        __nv_bfloat162 hi = __floats2bfloat162_rn(fmaxf(v2, v2 * slope), fmaxf(v3, v3 * slope));
         uint2 pk;
         pk.x = *reinterpret_cast<uint32_t*>(&lo);
         pk.y = *reinterpret_cast<uint32_t*>(&hi);
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out_act) + gbase + idx) = pk;
+        *reinterpret_cast<uint2*>(act_p + (long long)i * step) = pk;
       }
     }
   }
   __syncwarp();   // the tile is rewritten by the next chunk
+}
+
+template <int CW>
+__device__ __forceinline__ void epilogue_chunk(const ConvParams& p, float* tile, uint32_t taddr, int b, int q_base,
+                                               int n_base, int lane) {
+  constexpr int LPR = CW / 4;
+  constexpr int RPI = 32 / LPR;
+  constexpr int ITERS = 32 / RPI;
+  const int crow = lane / LPR;
+  const int c4 = lane % LPR;
+  const int n = n_base + c4 * 4;
+  // Element index (within the utterance) of my granule in row q_base + crow; rows
+  // advance by RPI * ntot.  Valid iterations are those with q < mrows and
+  // 0 <= idx < out_valid; idx grows with i, so they form one contiguous range.
+  const int q0 = q_base + crow;
+  const long long idx0 = (long long)q0 * p.ntot + n + p.out_shift;
+  const int step = RPI * p.ntot;
+  const long long e0 = (long long)b * p.out_valid + idx0;
+  const bool simple = idx0 >= 0 && idx0 + (long long)(ITERS - 1) * step < p.out_valid && q0 + (ITERS - 1) * RPI < p.mrows;
+  if (__all_sync(0xffffffffu, simple)) {
+    epilogue_body<CW, true>(p, reinterpret_cast<float4*>(tile), taddr, e0, step, 0, ITERS, n, lane, crow, c4);
+  } else {
+    int i_lo = 0, i_hi = (p.mrows - q0 + RPI - 1) / RPI;
+    if (idx0 < 0) i_lo = (int)((-idx0 + step - 1) / step);
+    const long long room = p.out_valid - idx0;                 // idx0 + i * step < out_valid
+    const int lim = room <= 0 ? 0 : (int)((room + step - 1) / step);
+    i_hi = i_hi < lim ? i_hi : lim;
+    i_hi = i_hi < ITERS ? i_hi : ITERS;
+    epilogue_body<CW, false>(p, reinterpret_cast<float4*>(tile), taddr, e0, step, i_lo, i_hi, n, lane, crow, c4);
+  }
 }
 
 // K16 consecutive K = 16 slices of one (tap, 64-channel chunk): descriptors advance by 32 bytes.
