@@ -60,7 +60,18 @@ struct TcGeom {
 struct TcParams {
   ConvParams c;
   TcGeom g;
+  long long* trace;   // debug: [3 roles][64 items][4] globaltimer stamps of CTA 0 (null in production)
 };
+
+__device__ __forceinline__ long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define L2S_TRACE(role, slot, ev)                                                            \
+  do {                                                                                     \
+    if (P.trace && blockIdx.x == 0 && (slot) < 64 && lane == 0) P.trace[((role) * 64 + (slot)) * 4 + (ev)] = gtime(); \
+  } while (0)
 
 constexpr int kEpiTileWords = 32 * 32;   // warp-private transpose tile: 32 rows x CW fp32, XOR-swizzled float4 slots
 
@@ -78,47 +89,80 @@ __device__ __forceinline__ int epi_slot(int row, int c4) {
   else return row * 4 + (c4 ^ ((row >> 1) & 3));
 }
 
-template <int CW, bool FULL>
-__device__ __forceinline__ void epilogue_body(const ConvParams& p, float4* tile4, uint32_t taddr, long long e0, int step,
-                                              int i_lo, int i_hi, int n, int lane, int crow, int c4) {
-  constexpr int LPR = CW / 4;        // lanes per row
-  constexpr int RPI = 32 / LPR;      // rows per warp instruction
-  constexpr int ITERS = 32 / RPI;
-  // issue the independent global loads first (they do not depend on the accumulator)
-  float4 rv[ITERS];
-  const bool has_res = p.res != nullptr, has_acc = p.acc_in != nullptr;
-  if (has_res) {
-    const float* rp = p.res + e0;
+// Where one chunk of the current item lands in global memory, as seen by this lane.
+struct EpiChunk {
+  long long e0;      // element index (whole batch) of my granule in the chunk's first row group
+  uint32_t taddr;    // TMEM address of the chunk (my quadrant's lanes, first column)
+  uint32_t okmask;   // bit i: row group i is inside the utterance / valid output range
+  int n;             // first of my 4 output columns
+};
+
+template <int CW>
+__device__ __forceinline__ EpiChunk epi_locate(const ConvParams& p, uint32_t taddr, int b, int q_base, int n_base,
+                                               int crow, int c4) {
+  constexpr int LPR = CW / 4, RPI = 32 / LPR, ITERS = 32 / RPI;
+  EpiChunk c;
+  c.n = n_base + c4 * 4;
+  c.taddr = taddr;
+  // Element index (within the utterance) of my granule in row q_base + crow; rows advance by
+  // RPI * ntot.  Valid row groups are those with q < mrows and 0 <= idx < out_valid; idx grows
+  // with i, so they form one contiguous range [i_lo, i_hi).
+  const int q0 = q_base + crow;
+  const long long idx0 = (long long)q0 * p.ntot + c.n + p.out_shift;
+  const int step = RPI * p.ntot;
+  c.e0 = (long long)b * p.out_valid + idx0;
+  if (idx0 >= 0 && idx0 + (long long)(ITERS - 1) * step < p.out_valid && q0 + (ITERS - 1) * RPI < p.mrows) {
+    c.okmask = (1u << ITERS) - 1u;
+  } else {
+    int i_lo = 0, i_hi = (p.mrows - q0 + RPI - 1) / RPI;
+    if (idx0 < 0) i_lo = (int)((-idx0 + step - 1) / step);
+    const long long room = p.out_valid - idx0;
+    const int lim = room <= 0 ? 0 : (int)((room + step - 1) / step);
+    i_hi = i_hi < lim ? i_hi : lim;
+    i_hi = i_hi < ITERS ? i_hi : ITERS;
+    i_lo = i_lo < ITERS ? i_lo : ITERS;
+    c.okmask = i_hi > i_lo ? (((1u << i_hi) - 1u) & ~((1u << i_lo) - 1u)) : 0u;
+  }
+  return c;
+}
+
+// Stage 1 of a chunk: the loads that do not depend on each other (accumulator from TMEM,
+// residual stream from global memory).
+template <int CW>
+__device__ __forceinline__ void epi_issue(const ConvParams& p, const EpiChunk& c, uint32_t (&r)[CW],
+                                          float4 (&rv)[128 / CW]) {
+  constexpr int LPR = CW / 4, RPI = 32 / LPR, ITERS = 32 / RPI;
+  if constexpr (CW == 32) tmem_ld32(c.taddr, r); else tmem_ld16(c.taddr, r);
+  if (p.res) {
+    const float* rp = p.res + c.e0;
+    const int step = RPI * p.ntot;
 #pragma unroll
     for (int i = 0; i < ITERS; ++i, rp += step)
-      rv[i] = (FULL || (i >= i_lo && i < i_hi)) ? *reinterpret_cast<const float4*>(rp) : make_float4(0.f, 0.f, 0.f, 0.f);
+      rv[i] = ((c.okmask >> i) & 1u) ? *reinterpret_cast<const float4*>(rp) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  // the branch sum (10 of 96 launches) is fetched after the residual has landed, into the same registers
-  if (has_acc) {
-    const float* ap = p.acc_in + e0;
-#pragma unroll
-    for (int i = 0; i < ITERS; ++i, ap += step) {
-      if (FULL || (i >= i_lo && i < i_hi)) {
-        const float4 a = *reinterpret_cast<const float4*>(ap);
-        if (has_res) { rv[i].x += a.x; rv[i].y += a.y; rv[i].z += a.z; rv[i].w += a.w; }
-        else rv[i] = a;
-      } else if (!has_res) {
-        rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-  }
-  const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+}
 
-  uint32_t r[CW];
-  if constexpr (CW == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
+// Stage 2: accumulator rows -> transpose tile (one row per lane, swizzled float4 slots).
+template <int CW>
+__device__ __forceinline__ void epi_stage(float4* tile4, const uint32_t (&r)[CW], int lane) {
   tmem_ld_wait();
 #pragma unroll
-  for (int j = 0; j < LPR; ++j)
+  for (int j = 0; j < CW / 4; ++j)
     tile4[epi_slot<CW>(lane, j)] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
                                                __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-  __syncwarp();
-  float* raw_p = p.out_raw ? p.out_raw + e0 : nullptr;
-  __nv_bfloat16* act_p = p.out_act ? reinterpret_cast<__nv_bfloat16*>(p.out_act) + e0 : nullptr;
+}
+
+// Stage 3: read back column-per-lane, apply bias / residual / branch sum / mean / leaky-ReLU, store.
+template <int CW>
+__device__ __forceinline__ void epi_finish(const ConvParams& p, const EpiChunk& c, const float4* tile4,
+                                           const float4 (&rv)[128 / CW], int crow, int c4) {
+  constexpr int LPR = CW / 4, RPI = 32 / LPR, ITERS = 32 / RPI;
+  const int step = RPI * p.ntot;
+  const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + c.n));
+  const bool has_res = p.res != nullptr, has_acc = p.acc_in != nullptr;
+  float* raw_p = p.out_raw ? p.out_raw + c.e0 : nullptr;
+  __nv_bfloat16* act_p = p.out_act ? reinterpret_cast<__nv_bfloat16*>(p.out_act) + c.e0 : nullptr;
+  const float* acc_p = p.acc_in + c.e0;
   const float slope = p.slope;
   // The tensor-core (bf16) mode multiplies by the reciprocal of the branch count; the
   // fp32 CUDA-core mode keeps the reference's true division (conv_common.cuh).
@@ -126,10 +170,15 @@ __device__ __forceinline__ void epilogue_body(const ConvParams& p, float4* tile4
 #pragma unroll
   for (int i = 0; i < ITERS; ++i) {
     const float4 t = tile4[epi_slot<CW>(i * RPI + crow, c4)];
+    const bool ok = (c.okmask >> i) & 1u;
     float v0 = t.x + bv.x, v1 = t.y + bv.y, v2 = t.z + bv.z, v3 = t.w + bv.w;
-    if (has_res || has_acc) { v0 += rv[i].x; v1 += rv[i].y; v2 += rv[i].z; v3 += rv[i].w; }
+    if (has_res) { v0 += rv[i].x; v1 += rv[i].y; v2 += rv[i].z; v3 += rv[i].w; }
+    if (has_acc && ok) {   // branch sum: 10 of 96 launches
+      const float4 a = *reinterpret_cast<const float4*>(acc_p + (long long)i * step);
+      v0 += a.x; v1 += a.y; v2 += a.z; v3 += a.w;
+    }
     v0 *= inv_div; v1 *= inv_div; v2 *= inv_div; v3 *= inv_div;
-    if (FULL || (i >= i_lo && i < i_hi)) {
+    if (ok) {
       if (raw_p) *reinterpret_cast<float4*>(raw_p + (long long)i * step) = make_float4(v0, v1, v2, v3);
       if (act_p) {
         // leaky_relu for 0 < slope < 1 is max(v, v * slope)
@@ -142,36 +191,54 @@ __device__ __forceinline__ void epilogue_body(const ConvParams& p, float4* tile4
       }
     }
   }
-  __syncwarp();   // the tile is rewritten by the next chunk
 }
 
+// All chunks of one item owned by this warp (quadrant `quad`, every second chunk starting at
+// `half`), software pipelined: while chunk k is finished, the TMEM load and the residual loads
+// of chunk k+1 are already in flight.
 template <int CW>
-__device__ __forceinline__ void epilogue_chunk(const ConvParams& p, float* tile, uint32_t taddr, int b, int q_base,
-                                               int n_base, int lane) {
+__device__ __forceinline__ void epilogue_item(const ConvParams& p, const TcGeom& g, float* tile, uint32_t t_base, int b,
+                                              int mi, int ni, int quad, int half, int lane) {
   constexpr int LPR = CW / 4;
-  constexpr int RPI = 32 / LPR;
-  constexpr int ITERS = 32 / RPI;
   const int crow = lane / LPR;
   const int c4 = lane % LPR;
-  const int n = n_base + c4 * 4;
-  // Element index (within the utterance) of my granule in row q_base + crow; rows
-  // advance by RPI * ntot.  Valid iterations are those with q < mrows and
-  // 0 <= idx < out_valid; idx grows with i, so they form one contiguous range.
-  const int q0 = q_base + crow;
-  const long long idx0 = (long long)q0 * p.ntot + n + p.out_shift;
-  const int step = RPI * p.ntot;
-  const long long e0 = (long long)b * p.out_valid + idx0;
-  const bool simple = idx0 >= 0 && idx0 + (long long)(ITERS - 1) * step < p.out_valid && q0 + (ITERS - 1) * RPI < p.mrows;
-  if (__all_sync(0xffffffffu, simple)) {
-    epilogue_body<CW, true>(p, reinterpret_cast<float4*>(tile), taddr, e0, step, 0, ITERS, n, lane, crow, c4);
-  } else {
-    int i_lo = 0, i_hi = (p.mrows - q0 + RPI - 1) / RPI;
-    if (idx0 < 0) i_lo = (int)((-idx0 + step - 1) / step);
-    const long long room = p.out_valid - idx0;                 // idx0 + i * step < out_valid
-    const int lim = room <= 0 ? 0 : (int)((room + step - 1) / step);
-    i_hi = i_hi < lim ? i_hi : lim;
-    i_hi = i_hi < ITERS ? i_hi : ITERS;
-    epilogue_body<CW, false>(p, reinterpret_cast<float4*>(tile), taddr, e0, step, i_lo, i_hi, n, lane, crow, c4);
+  float4* tile4 = reinterpret_cast<float4*>(tile);
+  const int cps = g.nt / CW;                  // chunks per 128-row accumulator
+  const int n_chunks = g.msub * cps;
+  int s = 0, cc = half;
+  while (cc >= cps) { cc -= cps; ++s; }
+  auto locate = [&](int s_, int cc_) {
+    return epi_locate<CW>(p, t_base + (uint32_t)(s_ * g.nt + cc_ * CW), b, (mi * g.msub + s_) * 128 + quad * 32,
+                          ni * g.nt + cc_ * CW, crow, c4);
+  };
+  uint32_t r[CW];
+  float4 rva[128 / CW], rvb[128 / CW];
+  int ch = half;
+  if (ch >= n_chunks) return;
+  EpiChunk cur = locate(s, cc);
+  epi_issue<CW>(p, cur, r, rva);
+  while (true) {
+    // ---- chunk in (cur, rva); prefetch the next into rvb
+    epi_stage<CW>(tile4, r, lane);
+    ch += 2; cc += 2;
+    while (cc >= cps) { cc -= cps; ++s; }
+    bool more = ch < n_chunks;
+    EpiChunk nxt = cur;
+    if (more) { nxt = locate(s, cc); epi_issue<CW>(p, nxt, r, rvb); }
+    __syncwarp();
+    epi_finish<CW>(p, cur, tile4, rva, crow, c4);
+    __syncwarp();
+    if (!more) break;
+    // ---- chunk in (nxt, rvb); prefetch the next into rva
+    epi_stage<CW>(tile4, r, lane);
+    ch += 2; cc += 2;
+    while (cc >= cps) { cc -= cps; ++s; }
+    more = ch < n_chunks;
+    if (more) { cur = locate(s, cc); epi_issue<CW>(p, cur, r, rva); }
+    __syncwarp();
+    epi_finish<CW>(p, nxt, tile4, rvb, crow, c4);
+    __syncwarp();
+    if (!more) break;
   }
 }
 
@@ -236,7 +303,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int ia = 0, ib = 0;
     uint32_t pa = 0, pb = 0;
     const uint32_t box_bytes = (uint32_t)(g.box_rows * g.rb);
-    for (int item = blockIdx.x; item < g.total_items; item += gridDim.x) {
+    int it_no = 0;
+    for (int item = blockIdx.x; item < g.total_items; item += gridDim.x, ++it_no) {
       const int b = item / items_per_b;
       const int rem = item - b * items_per_b;
       const int mi = rem / g.n_ntiles;
@@ -245,7 +313,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kc = 0; kc < g.kc; ++kc) {
         const int ch0 = kc * (g.rb >> 1);
         if (!g.per_tap) {
+          if (kc == 0) L2S_TRACE(0, it_no, 0);
           mbar_wait(&a_empty[ia], pa ^ 1u);
+          if (kc == 0) L2S_TRACE(0, it_no, 1);
           if (leader) {
             mbar_expect_tx(&a_full[ia], (uint32_t)g.slab_bytes);
             uint8_t* dst = slabA + (size_t)ia * g.slab_bytes;
@@ -290,14 +360,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t pa = 0, pb = 0;
     uint32_t pacc0 = 0, pacc1 = 0;
     int buf = 0;
-    for (int item = blockIdx.x; item < g.total_items; item += gridDim.x) {
+    int it_no = 0;
+    for (int item = blockIdx.x; item < g.total_items; item += gridDim.x, ++it_no) {
+      L2S_TRACE(1, it_no, 0);
       mbar_wait(&acc_empty[buf], (buf ? pacc1 : pacc0) ^ 1u);
+      L2S_TRACE(1, it_no, 1);
       tc_fence_after();
       const uint32_t d_base = tmem_base + (uint32_t)(buf * acc_cols);
       for (int kc = 0; kc < g.kc; ++kc) {
         uint32_t a_lo = 0;
         if (!g.per_tap) {
           mbar_wait(&a_full[ia], pa);
+          if (kc == 0) L2S_TRACE(1, it_no, 2);
           tc_fence_after();
           a_lo = desc_lo_fixed | ((smem_u32(slabA + (size_t)ia * g.slab_bytes) & 0x3FFFFu) >> 4);
         }
@@ -340,6 +414,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       if (leader) umma_commit(&acc_full[buf]);      // accumulators complete -> epilogue
+      L2S_TRACE(1, it_no, 3);
       if (buf) pacc1 ^= 1u; else pacc0 ^= 1u;
       buf ^= 1;
     }
@@ -350,36 +425,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* tile = epi_tiles + (size_t)(warp - 2) * kEpiTileWords;
     uint32_t pacc0 = 0, pacc1 = 0;
     int buf = 0;
-    for (int item = blockIdx.x; item < g.total_items; item += gridDim.x) {
+    int it_no = 0;
+    for (int item = blockIdx.x; item < g.total_items; item += gridDim.x, ++it_no) {
       const int b = item / items_per_b;
       const int rem = item - b * items_per_b;
       const int mi = rem / g.n_ntiles;
       const int ni = rem - mi * g.n_ntiles;
+      if (warp == 2) L2S_TRACE(2, it_no, 0);
       mbar_wait(&acc_full[buf], buf ? pacc1 : pacc0);
+      if (warp == 2) L2S_TRACE(2, it_no, 1);
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * acc_cols);
-      if (g.cw == 32) {
-        const int chunks_per_sub = g.nt >> 5;
-        const int n_chunks = g.msub * chunks_per_sub;
-        for (int ch = half; ch < n_chunks; ch += 2) {
-          const int s = ch / chunks_per_sub;
-          const int c0 = (ch - s * chunks_per_sub) << 5;
-          epilogue_chunk<32>(p, tile, t_base + (uint32_t)(s * g.nt + c0), b, (mi * g.msub + s) * 128 + quad * 32,
-                             ni * g.nt + c0, lane);
-        }
-      } else {
-        const int chunks_per_sub = g.nt >> 4;
-        const int n_chunks = g.msub * chunks_per_sub;
-        for (int ch = half; ch < n_chunks; ch += 2) {
-          const int s = ch / chunks_per_sub;
-          const int c0 = (ch - s * chunks_per_sub) << 4;
-          epilogue_chunk<16>(p, tile, t_base + (uint32_t)(s * g.nt + c0), b, (mi * g.msub + s) * 128 + quad * 32,
-                             ni * g.nt + c0, lane);
-        }
-      }
+      if (g.cw == 32) epilogue_item<32>(p, g, tile, t_base, b, mi, ni, quad, half, lane);
+      else epilogue_item<16>(p, g, tile, t_base, b, mi, ni, quad, half, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (warp == 2) L2S_TRACE(2, it_no, 2);
       if (buf) pacc1 ^= 1u; else pacc0 ^= 1u;
       buf ^= 1;
     }
@@ -433,6 +495,7 @@ struct TcTune {
   int slab_cap = 40960;        // bytes per slab
   int smem_budget = 220 * 1024;
   int per_tap = 0;
+  int sa_min = 0;              // force at least this many slab ring slots when they fit
   int max_ctas = 0;            // 0: number of SMs
 };
 
@@ -476,6 +539,7 @@ inline bool tc_plan(const ConvParams& c, int batch, const TcTune& tune, TcGeom* 
   const int bar_bytes = 1024 + 320 + kTcEpiWarps * kEpiTileWords * 4;  // alignment slack, barriers + TMEM slot, epilogue tiles
   int sa = g.kc + 1 < kTcMaxStagesA ? g.kc + 1 : kTcMaxStagesA;
   if (tune.per_tap) sa = 4;
+  if (tune.sa_min > sa) sa = tune.sa_min < kTcMaxStagesA ? tune.sa_min : kTcMaxStagesA;
   if (sa < 2) sa = 2;
   int sb = 4;
   while (sa > 2 && sa * g.slab_bytes + sb * g.bstage_bytes + bar_bytes > tune.smem_budget) --sa;
@@ -499,7 +563,7 @@ inline bool tc_plan(const ConvParams& c, int batch, const TcTune& tune, TcGeom* 
 }
 
 inline cudaError_t launch_conv_tc(const ConvParams& c, const TcGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmW,
-                                  int num_ctas, cudaStream_t stream) {
+                                  int num_ctas, cudaStream_t stream, long long* trace = nullptr) {
   static bool configured[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -511,6 +575,7 @@ inline cudaError_t launch_conv_tc(const ConvParams& c, const TcGeom& g, const CU
   TcParams P;
   P.c = c;
   P.g = g;
+  P.trace = trace;
   int grid = g.total_items < num_ctas ? g.total_items : num_ctas;
   if (grid < 1) grid = 1;
   conv_tc_kernel<<<grid, kTcThreads, g.smem_bytes, stream>>>(tmA, tmW, P);

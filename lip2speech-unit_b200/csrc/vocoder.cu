@@ -28,6 +28,8 @@ struct Knobs {
   long long stop_after_stage = -1; // >= 0: stop after that MRF stage (taps stay valid)
   long long stop_after_pre = 0;    // stop after conv_pre
   long long per_tap = 0;
+  long long sa_min = 0;
+  long long trace_ptr = 0;         // device pointer for the kernel trace of l2s_debug_conv (0: off)
   long long max_msub = 8;
   long long slab_cap = 40960;
   long long max_ctas = 0;
@@ -261,6 +263,7 @@ TcTune current_tune(const l2s_vocoder* v) {
   t.max_msub = (int)g_knobs.max_msub;
   t.slab_cap = (int)g_knobs.slab_cap;
   t.per_tap = (int)g_knobs.per_tap;
+  t.sa_min = (int)g_knobs.sa_min;
   t.max_ctas = g_knobs.max_ctas > 0 ? (int)g_knobs.max_ctas : (v ? v->num_sms : 148);
   return t;
 }
@@ -767,7 +770,7 @@ int l2s_debug_conv(const l2s_conv_desc* d, int32_t impl, int32_t device, void* s
       say("cuTensorMapEncodeTiled failed");
       return L2S_ERR_CUDA;
     }
-    e = launch_conv_tc(p, g, tmA, tmW, tune.max_ctas, st);
+    e = launch_conv_tc(p, g, tmA, tmW, tune.max_ctas, st, reinterpret_cast<long long*>(g_knobs.trace_ptr));
   }
   if (e != cudaSuccess) { say(cudaGetErrorString(e)); return L2S_ERR_CUDA; }
   return L2S_OK;
@@ -793,6 +796,8 @@ int l2s_debug_set(const char* key, int64_t value) {
   else if (k == "stop_after_stage") g_knobs.stop_after_stage = value;
   else if (k == "stop_after_pre") g_knobs.stop_after_pre = value;
   else if (k == "per_tap") g_knobs.per_tap = value;
+  else if (k == "sa_min") g_knobs.sa_min = value;
+  else if (k == "trace_ptr") g_knobs.trace_ptr = value;
   else if (k == "max_msub") g_knobs.max_msub = value;
   else if (k == "slab_cap") g_knobs.slab_cap = value;
   else if (k == "max_ctas") g_knobs.max_ctas = value;

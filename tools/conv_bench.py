@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--impl", type=int, default=1)
     ap.add_argument("--knob", action="append", default=[])
     ap.add_argument("--out", default="")
+    ap.add_argument("--trace", action="store_true", help="dump per-role timestamps of CTA 0 for the last launch")
     args = ap.parse_args()
     pkg = ge.load_package()
     cabi = pkg._cabi
@@ -88,6 +89,21 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             times.append(e0.elapsed_time(e1) * 1e3)
+        if args.trace:
+            tr = torch.zeros(3 * 64 * 4, dtype=torch.int64, device=dev)
+            lib.l2s_debug_set(b"trace_ptr", tr.data_ptr())
+            lib.l2s_debug_conv(C.byref(descs[0]), args.impl, 0, stream, err, 256)
+            torch.cuda.synchronize()
+            lib.l2s_debug_set(b"trace_ptr", 0)
+            t = tr.cpu().view(3, 64, 4)
+            t0 = int(t[t > 0].min())
+            print("trace (ns since first stamp) item: prod[wait_empty,issue] mma[wait_acc,got_acc,got_A,committed] epi[wait,got,done]")
+            for i in range(64):
+                if int(t[1, i, 3]) == 0:
+                    break
+                f = lambda v: int(v) - t0 if int(v) else -1
+                print(f"  {i:2d}: P[{f(t[0,i,0])},{f(t[0,i,1])}] M[{f(t[1,i,0])},{f(t[1,i,1])},{f(t[1,i,2])},{f(t[1,i,3])}] "
+                      f"E[{f(t[2,i,0])},{f(t[2,i,1])},{f(t[2,i,2])}]")
         times.sort()
         med = times[len(times) // 2]
         flops = 2.0 * cin * cout * k * B * L
