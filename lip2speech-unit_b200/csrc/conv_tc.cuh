@@ -126,19 +126,22 @@ __device__ __forceinline__ EpiChunk epi_locate(const ConvParams& p, uint32_t tad
   return c;
 }
 
+// Epilogue mode bits (compile-time: dead paths disappear from the instruction stream).
+constexpr int kEpiRes = 1, kEpiAcc = 2, kEpiRaw = 4, kEpiAct = 8;
+
 // Stage 1 of a chunk: the loads that do not depend on each other (accumulator from TMEM,
 // residual stream from global memory).
-template <int CW>
+template <int CW, int MODE, bool FULL>
 __device__ __forceinline__ void epi_issue(const ConvParams& p, const EpiChunk& c, uint32_t (&r)[CW],
-                                          float4 (&rv)[128 / CW]) {
+                                          float4 (&rv)[CW / 4]) {
   constexpr int LPR = CW / 4, RPI = 32 / LPR, ITERS = 32 / RPI;
   if constexpr (CW == 32) tmem_ld32(c.taddr, r); else tmem_ld16(c.taddr, r);
-  if (p.res) {
+  if constexpr ((MODE & kEpiRes) != 0) {
     const float* rp = p.res + c.e0;
     const int step = RPI * p.ntot;
 #pragma unroll
     for (int i = 0; i < ITERS; ++i, rp += step)
-      rv[i] = ((c.okmask >> i) & 1u) ? *reinterpret_cast<const float4*>(rp) : make_float4(0.f, 0.f, 0.f, 0.f);
+      rv[i] = (FULL || ((c.okmask >> i) & 1u)) ? *reinterpret_cast<const float4*>(rp) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -153,15 +156,14 @@ __device__ __forceinline__ void epi_stage(float4* tile4, const uint32_t (&r)[CW]
 }
 
 // Stage 3: read back column-per-lane, apply bias / residual / branch sum / mean / leaky-ReLU, store.
-template <int CW>
+template <int CW, int MODE, bool FULL>
 __device__ __forceinline__ void epi_finish(const ConvParams& p, const EpiChunk& c, const float4* tile4,
-                                           const float4 (&rv)[128 / CW], int crow, int c4) {
+                                           const float4 (&rv)[CW / 4], int crow, int c4) {
   constexpr int LPR = CW / 4, RPI = 32 / LPR, ITERS = 32 / RPI;
   const int step = RPI * p.ntot;
   const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + c.n));
-  const bool has_res = p.res != nullptr, has_acc = p.acc_in != nullptr;
-  float* raw_p = p.out_raw ? p.out_raw + c.e0 : nullptr;
-  __nv_bfloat16* act_p = p.out_act ? reinterpret_cast<__nv_bfloat16*>(p.out_act) + c.e0 : nullptr;
+  float* raw_p = p.out_raw + c.e0;
+  __nv_bfloat16* act_p = reinterpret_cast<__nv_bfloat16*>(p.out_act) + c.e0;
   const float* acc_p = p.acc_in + c.e0;
   const float slope = p.slope;
   // The tensor-core (bf16) mode multiplies by the reciprocal of the branch count; the
@@ -170,17 +172,20 @@ __device__ __forceinline__ void epi_finish(const ConvParams& p, const EpiChunk& 
 #pragma unroll
   for (int i = 0; i < ITERS; ++i) {
     const float4 t = tile4[epi_slot<CW>(i * RPI + crow, c4)];
-    const bool ok = (c.okmask >> i) & 1u;
+    const bool ok = FULL || ((c.okmask >> i) & 1u);
     float v0 = t.x + bv.x, v1 = t.y + bv.y, v2 = t.z + bv.z, v3 = t.w + bv.w;
-    if (has_res) { v0 += rv[i].x; v1 += rv[i].y; v2 += rv[i].z; v3 += rv[i].w; }
-    if (has_acc && ok) {   // branch sum: 10 of 96 launches
-      const float4 a = *reinterpret_cast<const float4*>(acc_p + (long long)i * step);
-      v0 += a.x; v1 += a.y; v2 += a.z; v3 += a.w;
+    if constexpr ((MODE & kEpiRes) != 0) { v0 += rv[i].x; v1 += rv[i].y; v2 += rv[i].z; v3 += rv[i].w; }
+    if constexpr ((MODE & kEpiAcc) != 0) {
+      if (ok && p.acc_in) {
+        const float4 a = *reinterpret_cast<const float4*>(acc_p + (long long)i * step);
+        v0 += a.x; v1 += a.y; v2 += a.z; v3 += a.w;
+      }
+      v0 *= inv_div; v1 *= inv_div; v2 *= inv_div; v3 *= inv_div;   // div != 1 only on the branch-mean conv
     }
-    v0 *= inv_div; v1 *= inv_div; v2 *= inv_div; v3 *= inv_div;
     if (ok) {
-      if (raw_p) *reinterpret_cast<float4*>(raw_p + (long long)i * step) = make_float4(v0, v1, v2, v3);
-      if (act_p) {
+      if constexpr ((MODE & kEpiRaw) != 0)
+        *reinterpret_cast<float4*>(raw_p + (long long)i * step) = make_float4(v0, v1, v2, v3);
+      if constexpr ((MODE & kEpiAct) != 0) {
         // leaky_relu for 0 < slope < 1 is max(v, v * slope)
         __nv_bfloat162 lo = __floats2bfloat162_rn(fmaxf(v0, v0 * slope), fmaxf(v1, v1 * slope));
         __nv_bfloat162 hi = __floats2bfloat162_rn(fmaxf(v2, v2 * slope), fmaxf(v3, v3 * slope));
@@ -194,9 +199,10 @@ __device__ __forceinline__ void epi_finish(const ConvParams& p, const EpiChunk& 
 }
 
 // All chunks of one item owned by this warp (quadrant `quad`, every second chunk starting at
-// `half`), software pipelined: while chunk k is finished, the TMEM load and the residual loads
-// of chunk k+1 are already in flight.
-template <int CW>
+// `half`).  The TMEM load and its wait stay adjacent: a tcgen05.ld left in flight across other
+// code is not safe (the compiler may move its destination registers before wait::ld; measured
+// wrong results), so latency is hidden by the other epilogue warps instead.
+template <int CW, int MODE>
 __device__ __forceinline__ void epilogue_item(const ConvParams& p, const TcGeom& g, float* tile, uint32_t t_base, int b,
                                               int mi, int ni, int quad, int half, int lane) {
   constexpr int LPR = CW / 4;
@@ -204,41 +210,27 @@ __device__ __forceinline__ void epilogue_item(const ConvParams& p, const TcGeom&
   const int c4 = lane % LPR;
   float4* tile4 = reinterpret_cast<float4*>(tile);
   const int cps = g.nt / CW;                  // chunks per 128-row accumulator
-  const int n_chunks = g.msub * cps;
   int s = 0, cc = half;
   while (cc >= cps) { cc -= cps; ++s; }
-  auto locate = [&](int s_, int cc_) {
-    return epi_locate<CW>(p, t_base + (uint32_t)(s_ * g.nt + cc_ * CW), b, (mi * g.msub + s_) * 128 + quad * 32,
-                          ni * g.nt + cc_ * CW, crow, c4);
-  };
-  uint32_t r[CW];
-  float4 rva[128 / CW], rvb[128 / CW];
-  int ch = half;
-  if (ch >= n_chunks) return;
-  EpiChunk cur = locate(s, cc);
-  epi_issue<CW>(p, cur, r, rva);
-  while (true) {
-    // ---- chunk in (cur, rva); prefetch the next into rvb
-    epi_stage<CW>(tile4, r, lane);
-    ch += 2; cc += 2;
+  while (s < g.msub) {
+    const EpiChunk c = epi_locate<CW>(p, t_base + (uint32_t)(s * g.nt + cc * CW), b, (mi * g.msub + s) * 128 + quad * 32,
+                                      ni * g.nt + cc * CW, crow, c4);
+    uint32_t r[CW];
+    float4 rv[CW / 4];
+    if (__all_sync(0xffffffffu, c.okmask == (1u << (CW / 4)) - 1u)) {
+      epi_issue<CW, MODE, true>(p, c, r, rv);
+      epi_stage<CW>(tile4, r, lane);
+      __syncwarp();
+      epi_finish<CW, MODE, true>(p, c, tile4, rv, crow, c4);
+    } else {
+      epi_issue<CW, MODE, false>(p, c, r, rv);
+      epi_stage<CW>(tile4, r, lane);
+      __syncwarp();
+      epi_finish<CW, MODE, false>(p, c, tile4, rv, crow, c4);
+    }
+    __syncwarp();   // the tile is rewritten by the next chunk
+    cc += 2;
     while (cc >= cps) { cc -= cps; ++s; }
-    bool more = ch < n_chunks;
-    EpiChunk nxt = cur;
-    if (more) { nxt = locate(s, cc); epi_issue<CW>(p, nxt, r, rvb); }
-    __syncwarp();
-    epi_finish<CW>(p, cur, tile4, rva, crow, c4);
-    __syncwarp();
-    if (!more) break;
-    // ---- chunk in (nxt, rvb); prefetch the next into rva
-    epi_stage<CW>(tile4, r, lane);
-    ch += 2; cc += 2;
-    while (cc >= cps) { cc -= cps; ++s; }
-    more = ch < n_chunks;
-    if (more) { cur = locate(s, cc); epi_issue<CW>(p, cur, r, rva); }
-    __syncwarp();
-    epi_finish<CW>(p, nxt, tile4, rvb, crow, c4);
-    __syncwarp();
-    if (!more) break;
   }
 }
 
@@ -254,6 +246,7 @@ __device__ __forceinline__ void issue_chunk(bool leader, uint32_t d_addr, uint32
   }
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -436,8 +429,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (warp == 2) L2S_TRACE(2, it_no, 1);
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * acc_cols);
-      if (g.cw == 32) epilogue_item<32>(p, g, tile, t_base, b, mi, ni, quad, half, lane);
-      else epilogue_item<16>(p, g, tile, t_base, b, mi, ni, quad, half, lane);
+      if (g.cw == 32) epilogue_item<32, MODE>(p, g, tile, t_base, b, mi, ni, quad, half, lane);
+      else epilogue_item<16, MODE>(p, g, tile, t_base, b, mi, ni, quad, half, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
@@ -562,24 +555,38 @@ inline bool tc_plan(const ConvParams& c, int batch, const TcTune& tune, TcGeom* 
   return true;
 }
 
-inline cudaError_t launch_conv_tc(const ConvParams& c, const TcGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmW,
-                                  int num_ctas, cudaStream_t stream, long long* trace = nullptr) {
+template <int MODE>
+inline cudaError_t launch_conv_tc_mode(const TcParams& P, const CUtensorMap& tmA, const CUtensorMap& tmW, int grid,
+                                       cudaStream_t stream) {
   static bool configured[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     configured[dev] = true;
   }
+  conv_tc_kernel<MODE><<<grid, kTcThreads, P.g.smem_bytes, stream>>>(tmA, tmW, P);
+  return cudaGetLastError();
+}
+
+inline cudaError_t launch_conv_tc(const ConvParams& c, const TcGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmW,
+                                  int num_ctas, cudaStream_t stream, long long* trace = nullptr) {
   TcParams P;
   P.c = c;
   P.g = g;
   P.trace = trace;
   int grid = g.total_items < num_ctas ? g.total_items : num_ctas;
   if (grid < 1) grid = 1;
-  conv_tc_kernel<<<grid, kTcThreads, g.smem_bytes, stream>>>(tmA, tmW, P);
-  return cudaGetLastError();
+  const int mode = (c.res ? kEpiRes : 0) | ((c.acc_in || c.div != 1.0f) ? kEpiAcc : 0) | (c.out_raw ? kEpiRaw : 0) |
+                   (c.out_act ? kEpiAct : 0);
+  switch (mode) {
+#define L2S_MODE(m) case m: return launch_conv_tc_mode<m>(P, tmA, tmW, grid, stream);
+    L2S_MODE(4) L2S_MODE(5) L2S_MODE(6) L2S_MODE(7) L2S_MODE(8) L2S_MODE(9) L2S_MODE(10) L2S_MODE(11) L2S_MODE(12)
+    L2S_MODE(13) L2S_MODE(14) L2S_MODE(15)
+#undef L2S_MODE
+    default: return cudaErrorInvalidValue;   // a conv with no output
+  }
 }
 
 }  // namespace l2s
