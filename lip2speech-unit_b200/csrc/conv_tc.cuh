@@ -51,6 +51,7 @@ struct TcGeom {
   int sb;            // W ring depth
   int tmem_cols;     // power of two >= 2 * msub * nt
   int cw;            // epilogue chunk width in columns: 32 when nt % 32 == 0, else 16
+  int ctas_per_sm;   // 2: planned so that two CTAs fit one SM
   int total_items;
   int per_tap;           // 1: probe/fallback mode, one A tile per tap by TMA (no row-shifted descriptors)
   uint32_t idesc;
@@ -247,7 +248,7 @@ __device__ __forceinline__ void issue_chunk(bool leader, uint32_t d_addr, uint32
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcThreads, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcParams P) {
   extern __shared__ uint8_t smem_raw[];
   const ConvParams& p = P.c;
@@ -489,11 +490,14 @@ struct TcTune {
   int smem_budget = 220 * 1024;
   int per_tap = 0;
   int sa_min = 0;              // force at least this many slab ring slots when they fit
+  int dual = 1;                // try the two-CTAs-per-SM plan first
   int max_ctas = 0;            // 0: number of SMs
 };
 
 // Shape-only planning (no device pointers): valid for any batch with the same (lin, mrows).
-inline bool tc_plan(const ConvParams& c, int batch, const TcTune& tune, TcGeom* out) {
+// acc_cols_cap bounds msub * nt (one accumulator buffer), smem_budget the dynamic shared memory.
+inline bool tc_plan_with(const ConvParams& c, int batch, const TcTune& tune, int acc_cols_cap, int smem_budget,
+                         TcGeom* out) {
   TcGeom g{};
   if (c.cin_pad % 16 != 0 || c.ntot % 16 != 0 || c.ntaps < 1 || c.ntaps > kMaxTaps) return false;
   g.rb = (c.cin_pad >= 64 ? 64 : c.cin_pad) * 2;
@@ -503,13 +507,14 @@ inline bool tc_plan(const ConvParams& c, int batch, const TcTune& tune, TcGeom* 
   g.k16 = g.rb / 32;
   g.nt = c.ntot <= 256 ? c.ntot : 256;
   while (c.ntot % g.nt != 0) g.nt -= 16;
+  if (g.nt > acc_cols_cap) return false;
   g.n_ntiles = c.ntot / g.nt;
   int mn = c.tap_off[0], mx = c.tap_off[0];
   for (int j = 1; j < c.ntaps; ++j) { mn = c.tap_off[j] < mn ? c.tap_off[j] : mn; mx = c.tap_off[j] > mx ? c.tap_off[j] : mx; }
   g.min_off = mn;
   const int span = tune.per_tap ? 0 : mx - mn;
   g.per_tap = tune.per_tap;
-  int msub = 256 / g.nt;
+  int msub = acc_cols_cap / g.nt;
   if (msub < 1) msub = 1;
   if (msub > tune.max_msub) msub = tune.max_msub;
   const int need = (c.mrows + 127) / 128;
@@ -535,11 +540,11 @@ inline bool tc_plan(const ConvParams& c, int batch, const TcTune& tune, TcGeom* 
   if (tune.sa_min > sa) sa = tune.sa_min < kTcMaxStagesA ? tune.sa_min : kTcMaxStagesA;
   if (sa < 2) sa = 2;
   int sb = 4;
-  while (sa > 2 && sa * g.slab_bytes + sb * g.bstage_bytes + bar_bytes > tune.smem_budget) --sa;
-  while (sb > 2 && sa * g.slab_bytes + sb * g.bstage_bytes + bar_bytes > tune.smem_budget) --sb;
-  if (sa * g.slab_bytes + sb * g.bstage_bytes + bar_bytes > tune.smem_budget) return false;
+  while (sa > 2 && sa * g.slab_bytes + sb * g.bstage_bytes + bar_bytes > smem_budget) --sa;
+  while (sb > 2 && sa * g.slab_bytes + sb * g.bstage_bytes + bar_bytes > smem_budget) --sb;
+  if (sa * g.slab_bytes + sb * g.bstage_bytes + bar_bytes > smem_budget) return false;
   while (sb < kTcMaxStagesB && sb < g.n_tstages * g.kc &&
-         sa * g.slab_bytes + (sb + 1) * g.bstage_bytes + bar_bytes <= tune.smem_budget && (sb + 1) * g.bstage_bytes <= 96 * 1024)
+         sa * g.slab_bytes + (sb + 1) * g.bstage_bytes + bar_bytes <= smem_budget && (sb + 1) * g.bstage_bytes <= 96 * 1024)
     ++sb;
   g.sa = sa;
   g.sb = sb;
@@ -551,8 +556,20 @@ inline bool tc_plan(const ConvParams& c, int batch, const TcTune& tune, TcGeom* 
   g.total_items = batch * g.m_items * g.n_ntiles;
   g.idesc = umma_idesc_bf16(128u, (uint32_t)g.nt);
   g.cw = g.nt % 32 == 0 ? 32 : 16;
+  g.ctas_per_sm = 1;
   *out = g;
   return true;
+}
+
+// Two co-resident CTAs per SM (TMEM 2 x 256 columns, 2 x <= 110 KB shared memory, <= 96
+// registers) hide the epilogue's latency chains on the layers where they fit (C <= 64);
+// everything else gets the whole SM.
+inline bool tc_plan(const ConvParams& c, int batch, const TcTune& tune, TcGeom* out) {
+  if (tune.dual && tc_plan_with(c, batch, tune, 128, 110 * 1024, out) && out->tmem_cols <= 256) {
+    out->ctas_per_sm = 2;
+    return true;
+  }
+  return tc_plan_with(c, batch, tune, 256, tune.smem_budget, out);
 }
 
 template <int MODE>
@@ -576,7 +593,8 @@ inline cudaError_t launch_conv_tc(const ConvParams& c, const TcGeom& g, const CU
   P.c = c;
   P.g = g;
   P.trace = trace;
-  int grid = g.total_items < num_ctas ? g.total_items : num_ctas;
+  const int cap = num_ctas * (g.ctas_per_sm > 1 ? g.ctas_per_sm : 1);
+  int grid = g.total_items < cap ? g.total_items : cap;
   if (grid < 1) grid = 1;
   const int mode = (c.res ? kEpiRes : 0) | ((c.acc_in || c.div != 1.0f) ? kEpiAcc : 0) | (c.out_raw ? kEpiRaw : 0) |
                    (c.out_act ? kEpiAct : 0);

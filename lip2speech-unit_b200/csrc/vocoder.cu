@@ -29,6 +29,7 @@ struct Knobs {
   long long stop_after_pre = 0;    // stop after conv_pre
   long long per_tap = 0;
   long long sa_min = 0;
+  long long dual = 1;
   long long trace_ptr = 0;         // device pointer for the kernel trace of l2s_debug_conv (0: off)
   long long max_msub = 8;
   long long slab_cap = 40960;
@@ -264,6 +265,7 @@ TcTune current_tune(const l2s_vocoder* v) {
   t.slab_cap = (int)g_knobs.slab_cap;
   t.per_tap = (int)g_knobs.per_tap;
   t.sa_min = (int)g_knobs.sa_min;
+  t.dual = (int)g_knobs.dual;
   t.max_ctas = g_knobs.max_ctas > 0 ? (int)g_knobs.max_ctas : (v ? v->num_sms : 148);
   return t;
 }
@@ -797,6 +799,7 @@ int l2s_debug_set(const char* key, int64_t value) {
   else if (k == "stop_after_pre") g_knobs.stop_after_pre = value;
   else if (k == "per_tap") g_knobs.per_tap = value;
   else if (k == "sa_min") g_knobs.sa_min = value;
+  else if (k == "dual") g_knobs.dual = value;
   else if (k == "trace_ptr") g_knobs.trace_ptr = value;
   else if (k == "max_msub") g_knobs.max_msub = value;
   else if (k == "slab_cap") g_knobs.slab_cap = value;
