@@ -211,6 +211,12 @@ def main():
     ev1.record()
     sync_all()
     ms = ev0.elapsed_time(ev1)
+    # host time to ISSUE one step (no synchronisation): if it approaches ms_per_step the path is launch bound
+    t_h0 = time.perf_counter()
+    for _ in range(args.steps):
+        y = gen(code=code, mel=mel, spkr=spk)
+    host_ms = (time.perf_counter() - t_h0) * 1e3 / args.steps
+    torch.cuda.synchronize()
 
     # ---- end to end through the public class: pinned host inputs -> device, waveform -> pinned host
     out_h = torch.empty((BATCH, 1, FRAMES * HOP), dtype=torch.float32).pin_memory()
@@ -308,6 +314,7 @@ def main():
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
                     "api": "MelCodeGenerator(**kwargs) with pinned host tensors, fp32 waveform copied back"},
             "gpu_launches": launches_per_step * args.steps,
+            "host_issue_ms_per_step": host_ms,
             "clocks": clocks,
         }
         if not args.no_cpu_baseline:

@@ -61,7 +61,7 @@ struct TcGeom {
 struct TcParams {
   ConvParams c;
   TcGeom g;
-  long long* trace;   // debug: [3 roles][64 items][4] globaltimer stamps of CTA 0 (null in production)
+  long long* trace;   // debug: [3 roles][64 items][4] globaltimer stamps of CTA 0, then [512 CTAs][smid, t0, t1] (null in production)
 };
 
 __device__ __forceinline__ long long gtime() {
@@ -247,8 +247,11 @@ __device__ __forceinline__ void issue_chunk(bool leader, uint32_t d_addr, uint32
   }
 }
 
+#ifndef L2S_TC_MAXNREG
+#define L2S_TC_MAXNREG 80
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(kTcThreads, 2)
+__global__ void __maxnreg__(L2S_TC_MAXNREG)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcParams P) {
   extern __shared__ uint8_t smem_raw[];
   const ConvParams& p = P.c;
@@ -271,6 +274,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (P.trace && threadIdx.x == 0 && blockIdx.x < 512) {   // debug: which SM ran this CTA, and when
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    P.trace[768 + blockIdx.x * 3 + 0] = smid;
+    P.trace[768 + blockIdx.x * 3 + 1] = gtime();
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -444,6 +453,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncwarp();
   tc_fence_before();
   __syncthreads();
+  if (P.trace && threadIdx.x == 0 && blockIdx.x < 512) P.trace[768 + blockIdx.x * 3 + 2] = gtime();
   if (warp == 1) tmem_dealloc_dyn(tmem_base, (uint32_t)g.tmem_cols);
 }
 
@@ -565,9 +575,14 @@ inline bool tc_plan_with(const ConvParams& c, int batch, const TcTune& tune, int
 // registers) hide the epilogue's latency chains on the layers where they fit (C <= 64);
 // everything else gets the whole SM.
 inline bool tc_plan(const ConvParams& c, int batch, const TcTune& tune, TcGeom* out) {
-  if (tune.dual && tc_plan_with(c, batch, tune, 128, 110 * 1024, out) && out->tmem_cols <= 256) {
-    out->ctas_per_sm = 2;
-    return true;
+  if (tune.dual) {
+    TcTune t = tune;
+    for (; t.max_msub >= 1; t.max_msub >>= 1) {   // shrink the item until two CTAs' shared memory fits
+      if (tc_plan_with(c, batch, t, 128, 110 * 1024, out) && out->tmem_cols <= 256) {
+        out->ctas_per_sm = 2;
+        return true;
+      }
+    }
   }
   return tc_plan_with(c, batch, tune, 256, tune.smem_budget, out);
 }
@@ -580,6 +595,10 @@ inline cudaError_t launch_conv_tc_mode(const TcParams& P, const CUtensorMap& tmA
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    // all of the SM's unified L1/shared storage as shared memory, so that two ~110 KB CTAs co-reside
+    e = cudaFuncSetAttribute(conv_tc_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     configured[dev] = true;
   }

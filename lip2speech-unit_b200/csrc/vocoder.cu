@@ -30,6 +30,7 @@ struct Knobs {
   long long per_tap = 0;
   long long sa_min = 0;
   long long dual = 1;
+  long long plan_report = 0;       // l2s_debug_conv: write the chosen plan + occupancy into the err buffer
   long long trace_ptr = 0;         // device pointer for the kernel trace of l2s_debug_conv (0: off)
   long long max_msub = 8;
   long long slab_cap = 40960;
@@ -773,6 +774,15 @@ int l2s_debug_conv(const l2s_conv_desc* d, int32_t impl, int32_t device, void* s
       return L2S_ERR_CUDA;
     }
     e = launch_conv_tc(p, g, tmA, tmW, tune.max_ctas, st, reinterpret_cast<long long*>(g_knobs.trace_ptr));
+    if (e == cudaSuccess && err && err_len > 0 && g_knobs.plan_report) {
+      int occ = -1;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_tc_kernel<8>, kTcThreads, g.smem_bytes);
+      cudaFuncAttributes fa{};
+      cudaFuncGetAttributes(&fa, conv_tc_kernel<8>);
+      snprintf(err, (size_t)err_len,
+               "plan msub=%d nt=%d kc=%d tb=%d sa=%d sb=%d smem=%d tmem=%d items=%d ctas_per_sm=%d occ=%d regs=%d",
+               g.msub, g.nt, g.kc, g.tb, g.sa, g.sb, g.smem_bytes, g.tmem_cols, g.total_items, g.ctas_per_sm, occ, fa.numRegs);
+    }
   }
   if (e != cudaSuccess) { say(cudaGetErrorString(e)); return L2S_ERR_CUDA; }
   return L2S_OK;
@@ -800,6 +810,7 @@ int l2s_debug_set(const char* key, int64_t value) {
   else if (k == "per_tap") g_knobs.per_tap = value;
   else if (k == "sa_min") g_knobs.sa_min = value;
   else if (k == "dual") g_knobs.dual = value;
+  else if (k == "plan_report") g_knobs.plan_report = value;
   else if (k == "trace_ptr") g_knobs.trace_ptr = value;
   else if (k == "max_msub") g_knobs.max_msub = value;
   else if (k == "slab_cap") g_knobs.slab_cap = value;

@@ -80,9 +80,9 @@ def run_case(pkg, impl, cin, cout, k, dil=1, lin=300, batch=2, up=0, act_bf16=Tr
     for i, t in enumerate(tap_off):
         d.tap_off[i] = t
     d.out_shift, d.out_valid, d.scale, d.slope = out_shift, out_valid, div, slope
-    err = C.create_string_buffer(256)
+    err = C.create_string_buffer(512)
     torch.cuda.synchronize()
-    st = lib.l2s_debug_conv(C.byref(d), impl, 0, None, err, 256)
+    st = lib.l2s_debug_conv(C.byref(d), impl, 0, None, err, 512)
     if st != 0:
         raise RuntimeError(f"l2s_debug_conv status {st}: {err.value.decode()}")
     torch.cuda.synchronize()
