@@ -100,7 +100,7 @@ struct EpiChunk {
 
 template <int CW>
 __device__ __forceinline__ EpiChunk epi_locate(const ConvParams& p, uint32_t taddr, int b, int q_base, int n_base,
-                                               int crow, int c4) {
+                                               int crow, int c4, int mrows_eff) {
   constexpr int LPR = CW / 4, RPI = 32 / LPR, ITERS = 32 / RPI;
   EpiChunk c;
   c.n = n_base + c4 * 4;
@@ -112,10 +112,10 @@ __device__ __forceinline__ EpiChunk epi_locate(const ConvParams& p, uint32_t tad
   const long long idx0 = (long long)q0 * p.ntot + c.n + p.out_shift;
   const int step = RPI * p.ntot;
   c.e0 = (long long)b * p.out_valid + idx0;
-  if (idx0 >= 0 && idx0 + (long long)(ITERS - 1) * step < p.out_valid && q0 + (ITERS - 1) * RPI < p.mrows) {
+  if (idx0 >= 0 && idx0 + (long long)(ITERS - 1) * step < p.out_valid && q0 + (ITERS - 1) * RPI < mrows_eff) {
     c.okmask = (1u << ITERS) - 1u;
   } else {
-    int i_lo = 0, i_hi = (p.mrows - q0 + RPI - 1) / RPI;
+    int i_lo = 0, i_hi = mrows_eff > q0 ? (mrows_eff - q0 + RPI - 1) / RPI : 0;
     if (idx0 < 0) i_lo = (int)((-idx0 + step - 1) / step);
     const long long room = p.out_valid - idx0;
     const int lim = room <= 0 ? 0 : (int)((room + step - 1) / step);
@@ -200,22 +200,25 @@ __device__ __forceinline__ void epi_finish(const ConvParams& p, const EpiChunk& 
 }
 
 // All chunks of one item owned by this warp (quadrant `quad`, every second chunk starting at
-// `half`).  The TMEM load and its wait stay adjacent: a tcgen05.ld left in flight across other
-// code is not safe (the compiler may move its destination registers before wait::ld; measured
-// wrong results), so latency is hidden by the other epilogue warps instead.
+// `half`): msub accumulators of 128 rows x nt columns at TMEM address t_base; tile row 0 is output
+// row q0 of utterance b, column 0 is output column n_tile_base; rows >= row_lim are not stored.
+// The TMEM load and its wait stay adjacent: a tcgen05.ld left in flight across other code is not
+// safe (the compiler may move its destination registers before wait::ld; measured wrong
+// results), so latency is hidden by the other epilogue warps instead.
 template <int CW, int MODE>
-__device__ __forceinline__ void epilogue_item(const ConvParams& p, const TcGeom& g, float* tile, uint32_t t_base, int b,
-                                              int mi, int ni, int quad, int half, int lane) {
+__device__ __forceinline__ void epilogue_item_rows(const ConvParams& p, float* tile, uint32_t t_base, int b, int q0,
+                                                   int row_lim, int msub, int nt, int quad, int half, int lane,
+                                                   int n_tile_base = 0) {
   constexpr int LPR = CW / 4;
   const int crow = lane / LPR;
   const int c4 = lane % LPR;
   float4* tile4 = reinterpret_cast<float4*>(tile);
-  const int cps = g.nt / CW;                  // chunks per 128-row accumulator
+  const int cps = nt / CW;                    // chunks per 128-row accumulator
   int s = 0, cc = half;
   while (cc >= cps) { cc -= cps; ++s; }
-  while (s < g.msub) {
-    const EpiChunk c = epi_locate<CW>(p, t_base + (uint32_t)(s * g.nt + cc * CW), b, (mi * g.msub + s) * 128 + quad * 32,
-                                      ni * g.nt + cc * CW, crow, c4);
+  while (s < msub) {
+    const EpiChunk c = epi_locate<CW>(p, t_base + (uint32_t)(s * nt + cc * CW), b, q0 + s * 128 + quad * 32,
+                                      n_tile_base + cc * CW, crow, c4, row_lim);
     uint32_t r[CW];
     float4 rv[CW / 4];
     if (__all_sync(0xffffffffu, c.okmask == (1u << (CW / 4)) - 1u)) {
@@ -233,6 +236,12 @@ __device__ __forceinline__ void epilogue_item(const ConvParams& p, const TcGeom&
     cc += 2;
     while (cc >= cps) { cc -= cps; ++s; }
   }
+}
+
+template <int CW, int MODE>
+__device__ __forceinline__ void epilogue_item(const ConvParams& p, const TcGeom& g, float* tile, uint32_t t_base, int b,
+                                              int mi, int ni, int quad, int half, int lane) {
+  epilogue_item_rows<CW, MODE>(p, tile, t_base, b, mi * g.msub * 128, p.mrows, g.msub, g.nt, quad, half, lane, ni * g.nt);
 }
 
 // K16 consecutive K = 16 slices of one (tap, 64-channel chunk): descriptors advance by 32 bytes.

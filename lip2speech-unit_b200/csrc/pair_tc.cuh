@@ -1,0 +1,420 @@
+// Fused ResBlock1 step on tcgen05:   y = x + c2( lrelu( c1( lrelu(x) ) ) )
+// (speech-resynthesis/models.py:34-41, one (dilation d, 1) pair of a ResBlock1).
+//
+// Unfused, c1 writes its activated output to HBM and c2 reads it back; here it goes
+// TMEM -> registers (+bias1, leaky-ReLU, bf16) -> SHARED MEMORY in the K-major swizzled
+// operand layout -> second tcgen05 GEMM, and only c2's epilogue touches global memory.
+//
+// Per work item (MT = 128 * msub rows of the intermediate T, R = MT - (k-1) output rows):
+//   T[i]   = lrelu(b1 + sum_j W1[j] . xa[t0 + i - h1 + j*d]),  t0 = q0 - h2,  zero outside [0, L)
+//   out[r] = b2 + sum_j W2[j] . T[r + j]  + x[q0 + r]  (+ branch sum, mean, lrelu ...)   r < R
+// with h1 = d (k-1)/2, h2 = (k-1)/2.  The last k-1 rows of each c2 tile would need T rows that
+// this item did not compute; they are simply not stored (items advance by R rows).
+//
+//   TMA producer (warp 0): xa halo slab per 64-channel chunk; W1 stages, then W2 stages
+//   MMA issuer  (warp 1): c1 -> D1 (TMEM cols [0, msub*C)), commit d1_full;
+//                         wait t_full (+ d2_empty), c2 from the T slab -> D2, commit d2_full
+//   epilogue (warps 2..9): phase 1  D1 -> T slab (fence.proxy.async, arrive t_full)
+//                          phase 2  D2 -> global (same transposed epilogue as conv_tc.cuh)
+#pragma once
+#include "conv_tc.cuh"
+
+namespace l2s {
+
+struct PairGeom {
+  int c;             // channels (= cin = cout = MMA N)
+  int k, dil;        // kernel size, dilation of c1 (c2 has dilation 1)
+  int h1, h2;        // halos of c1 and c2
+  int rb, kc, k16;
+  int msub, mt, r_out;   // accumulators per item, T rows per item, output rows per item
+  int m_items;           // ceil(L / r_out)
+  int a_rows;            // slab rows = n_loads * box_rows >= mt + 2 h1
+  int box_rows, n_loads, slab_bytes, sa;
+  int t_rows;            // T slab rows per chunk (mt + 2 h2 rounded up to 8)
+  int t_chunk_bytes;     // t_rows * rb
+  int tb, n_tstages, bstage_bytes, sb;
+  int tmem_cols, cw, total_items;
+  uint32_t idesc;
+  int smem_bytes;
+};
+
+struct PairParams {
+  ConvParams c;          // epilogue of c2: bias = b2, res = x, acc_in, out_raw, out_act, div, slope; lin = mrows = L, ntot = C
+  const float* bias1;
+  PairGeom g;
+};
+
+// swizzled 16-byte slot index inside a T row (matches the TMA / UMMA 128B, 64B, 32B swizzles)
+__device__ __forceinline__ int t_swz(int rb, int row, int chunk16) {
+  if (rb == 128) return chunk16 ^ (row & 7);
+  if (rb == 64) return chunk16 ^ ((row >> 1) & 3);
+  return chunk16 ^ ((row >> 2) & 1);
+}
+
+// Phase 1 of one [32 rows x CW columns] chunk of D1: + bias1, leaky-ReLU(0.1), bf16, into the T slab.
+template <int CW>
+__device__ __forceinline__ void pair_phase1_chunk(const PairParams& P, uint8_t* t_slab, uint32_t taddr, int i_row, int c0,
+                                                  bool valid) {
+  const PairGeom& g = P.g;
+  uint32_t r[CW];
+  if constexpr (CW == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
+  tmem_ld_wait();
+  const int ch_per_chunk = g.rb >> 1;                       // channels per K chunk
+  const int kc2 = c0 / ch_per_chunk;
+  const int first16 = ((c0 - kc2 * ch_per_chunk) * 2) >> 4; // first 16-byte slot of these columns in the row
+  uint8_t* row_ptr = t_slab + (size_t)kc2 * g.t_chunk_bytes + (size_t)i_row * g.rb;
+  const float4* b4 = reinterpret_cast<const float4*>(P.bias1 + c0);
+#pragma unroll
+  for (int s = 0; s < CW / 8; ++s) {                        // 8 columns = 16 bytes of bf16
+    const float4 ba = __ldg(b4 + 2 * s), bb = __ldg(b4 + 2 * s + 1);
+    float v[8];
+    v[0] = __uint_as_float(r[8 * s + 0]) + ba.x; v[1] = __uint_as_float(r[8 * s + 1]) + ba.y;
+    v[2] = __uint_as_float(r[8 * s + 2]) + ba.z; v[3] = __uint_as_float(r[8 * s + 3]) + ba.w;
+    v[4] = __uint_as_float(r[8 * s + 4]) + bb.x; v[5] = __uint_as_float(r[8 * s + 5]) + bb.y;
+    v[6] = __uint_as_float(r[8 * s + 6]) + bb.z; v[7] = __uint_as_float(r[8 * s + 7]) + bb.w;
+    uint4 pk;
+    uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float a = valid ? fmaxf(v[2 * e], v[2 * e] * 0.1f) : 0.f;          // LRELU_SLOPE, models.py:13,38
+      const float b = valid ? fmaxf(v[2 * e + 1], v[2 * e + 1] * 0.1f) : 0.f;
+      __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+      pw[e] = *reinterpret_cast<uint32_t*>(&t);
+    }
+    *reinterpret_cast<uint4*>(row_ptr + (t_swz(g.rb, i_row, first16 + s) << 4)) = pk;
+  }
+}
+
+template <int MODE>
+__global__ void __maxnreg__(128)
+pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
+               const __grid_constant__ CUtensorMap tmW2, const PairParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const ConvParams& p = P.c;
+  const PairGeom& g = P.g;
+
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* slabA = smem;
+  uint8_t* slabT = slabA + (size_t)g.sa * g.slab_bytes;
+  uint8_t* stageB = slabT + (size_t)g.kc * g.t_chunk_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stageB + (size_t)g.sb * g.bstage_bytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + kTcMaxStagesA;
+  uint64_t* b_full = a_empty + kTcMaxStagesA;
+  uint64_t* b_empty = b_full + kTcMaxStagesB;
+  uint64_t* d1_full = b_empty + kTcMaxStagesB;
+  uint64_t* t_full = d1_full + 1;
+  uint64_t* d2_full = t_full + 1;
+  uint64_t* d2_empty = d2_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_empty + 1);
+  float* epi_tiles = reinterpret_cast<float*>(bars + 40);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+    for (int i = 0; i < g.sa; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < g.sb; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    mbar_init(d1_full, 1);
+    mbar_init(t_full, kTcEpiWarps);
+    mbar_init(d2_full, 1);
+    mbar_init(d2_empty, kTcEpiWarps);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_dyn(tmem_slot, (uint32_t)g.tmem_cols);
+  if (warp >= 2) {
+    // rows [mt, t_rows) of every T chunk are read by the last taps of c2 but never written: zero them once
+    const int tail_bytes = (g.t_rows - g.mt) * g.rb;
+    for (int kc2 = 0; kc2 < g.kc; ++kc2) {
+      uint8_t* base = slabT + (size_t)kc2 * g.t_chunk_bytes + (size_t)g.mt * g.rb;
+      for (int o = (threadIdx.x - 64) * 16; o < tail_bytes; o += (kTcThreads - 64) * 16)
+        *reinterpret_cast<uint4*>(base + o) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int acc_cols = g.msub * g.c;          // D1 at [0, acc_cols), D2 at [acc_cols, 2 acc_cols)
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    const bool leader = elect_one();
+    int ia = 0, ib = 0;
+    uint32_t pa = 0, pb = 0;
+    const uint32_t box_bytes = (uint32_t)(g.box_rows * g.rb);
+    for (int item = blockIdx.x; item < g.total_items; item += gridDim.x) {
+      const int b = item / g.m_items;
+      const int mi = item - b * g.m_items;
+      const int row0 = mi * g.r_out - g.h2 - g.h1;          // first xa row of the slab
+      for (int kc = 0; kc < g.kc; ++kc) {
+        const int ch0 = kc * (g.rb >> 1);
+        mbar_wait(&a_empty[ia], pa ^ 1u);
+        if (leader) {
+          mbar_expect_tx(&a_full[ia], (uint32_t)g.slab_bytes);
+          uint8_t* dst = slabA + (size_t)ia * g.slab_bytes;
+          for (int l = 0; l < g.n_loads; ++l)
+            tma_load_3d(dst + (size_t)l * box_bytes, &tmA, &a_full[ia], ch0, row0 + l * g.box_rows, b);
+        }
+        if (++ia == g.sa) { ia = 0; pa ^= 1u; }
+        for (int ts = 0; ts < g.n_tstages; ++ts) {
+          mbar_wait(&b_empty[ib], pb ^ 1u);
+          if (leader) {
+            mbar_expect_tx(&b_full[ib], (uint32_t)g.bstage_bytes);
+            tma_load_3d(stageB + (size_t)ib * g.bstage_bytes, &tmW1, &b_full[ib], ch0, 0, ts * g.tb);
+          }
+          if (++ib == g.sb) { ib = 0; pb ^= 1u; }
+        }
+      }
+      for (int kc = 0; kc < g.kc; ++kc) {
+        const int ch0 = kc * (g.rb >> 1);
+        for (int ts = 0; ts < g.n_tstages; ++ts) {
+          mbar_wait(&b_empty[ib], pb ^ 1u);
+          if (leader) {
+            mbar_expect_tx(&b_full[ib], (uint32_t)g.bstage_bytes);
+            tma_load_3d(stageB + (size_t)ib * g.bstage_bytes, &tmW2, &b_full[ib], ch0, 0, ts * g.tb);
+          }
+          if (++ib == g.sb) { ib = 0; pb ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    const bool leader = elect_one();
+    const uint64_t tmpl = umma_desc_template((uint32_t)g.rb);
+    const uint32_t desc_hi = (uint32_t)(tmpl >> 32);
+    const uint32_t desc_lo_fixed = (uint32_t)tmpl;
+    const uint32_t sub_step = (uint32_t)(128 * g.rb) >> 4;
+    const uint32_t tapw_step = (uint32_t)(g.c * g.rb) >> 4;
+    const uint32_t row_step = (uint32_t)g.rb >> 4;            // one row, in descriptor units
+    const uint32_t t_lo0 = desc_lo_fixed | ((smem_u32(slabT) & 0x3FFFFu) >> 4);
+    int ia = 0, ib = 0;
+    uint32_t pa = 0, pb = 0, pt = 0, pd2 = 0;
+    for (int item = blockIdx.x; item < g.total_items; item += gridDim.x) {
+      // ---- c1: D1 += xa(slab, row shift j*d) . W1[j]
+      for (int kc = 0; kc < g.kc; ++kc) {
+        mbar_wait(&a_full[ia], pa);
+        tc_fence_after();
+        const uint32_t a_lo = desc_lo_fixed | ((smem_u32(slabA + (size_t)ia * g.slab_bytes) & 0x3FFFFu) >> 4);
+        for (int ts = 0; ts < g.n_tstages; ++ts) {
+          mbar_wait(&b_full[ib], pb);
+          tc_fence_after();
+          uint32_t b_lo = desc_lo_fixed | ((smem_u32(stageB + (size_t)ib * g.bstage_bytes) & 0x3FFFFu) >> 4);
+          const int t_end = min(g.tb, g.k - ts * g.tb);
+          for (int t = 0; t < t_end; ++t, b_lo += tapw_step) {
+            const int tap = ts * g.tb + t;
+            uint32_t a_sub = a_lo + (uint32_t)(tap * g.dil) * row_step;
+            const uint32_t first = (uint32_t)(kc | tap);
+            uint32_t d_addr = tmem_base;
+            if (g.k16 == 4) {
+              for (int s = 0; s < g.msub; ++s, a_sub += sub_step, d_addr += (uint32_t)g.c)
+                issue_chunk<4>(leader, d_addr, desc_hi, a_sub, b_lo, g.idesc, first);
+            } else if (g.k16 == 2) {
+              for (int s = 0; s < g.msub; ++s, a_sub += sub_step, d_addr += (uint32_t)g.c)
+                issue_chunk<2>(leader, d_addr, desc_hi, a_sub, b_lo, g.idesc, first);
+            } else {
+              for (int s = 0; s < g.msub; ++s, a_sub += sub_step, d_addr += (uint32_t)g.c)
+                issue_chunk<1>(leader, d_addr, desc_hi, a_sub, b_lo, g.idesc, first);
+            }
+          }
+          if (leader) umma_commit(&b_empty[ib]);
+          if (++ib == g.sb) { ib = 0; pb ^= 1u; }
+        }
+        if (leader) umma_commit(&a_empty[ia]);
+        if (++ia == g.sa) { ia = 0; pa ^= 1u; }
+      }
+      if (leader) umma_commit(d1_full);
+      // ---- c2: D2 += T(slab, row shift j) . W2[j]   (T written by the epilogue warps)
+      mbar_wait(t_full, pt);
+      pt ^= 1u;
+      mbar_wait(d2_empty, pd2 ^ 1u);
+      pd2 ^= 1u;
+      tc_fence_after();
+      for (int kc = 0; kc < g.kc; ++kc) {
+        const uint32_t t_lo = t_lo0 + (uint32_t)(kc * g.t_chunk_bytes >> 4);
+        for (int ts = 0; ts < g.n_tstages; ++ts) {
+          mbar_wait(&b_full[ib], pb);
+          tc_fence_after();
+          uint32_t b_lo = desc_lo_fixed | ((smem_u32(stageB + (size_t)ib * g.bstage_bytes) & 0x3FFFFu) >> 4);
+          const int t_end = min(g.tb, g.k - ts * g.tb);
+          for (int t = 0; t < t_end; ++t, b_lo += tapw_step) {
+            const int tap = ts * g.tb + t;
+            uint32_t a_sub = t_lo + (uint32_t)tap * row_step;
+            const uint32_t first = (uint32_t)(kc | tap);
+            uint32_t d_addr = tmem_base + (uint32_t)acc_cols;
+            if (g.k16 == 4) {
+              for (int s = 0; s < g.msub; ++s, a_sub += sub_step, d_addr += (uint32_t)g.c)
+                issue_chunk<4>(leader, d_addr, desc_hi, a_sub, b_lo, g.idesc, first);
+            } else if (g.k16 == 2) {
+              for (int s = 0; s < g.msub; ++s, a_sub += sub_step, d_addr += (uint32_t)g.c)
+                issue_chunk<2>(leader, d_addr, desc_hi, a_sub, b_lo, g.idesc, first);
+            } else {
+              for (int s = 0; s < g.msub; ++s, a_sub += sub_step, d_addr += (uint32_t)g.c)
+                issue_chunk<1>(leader, d_addr, desc_hi, a_sub, b_lo, g.idesc, first);
+            }
+          }
+          if (leader) umma_commit(&b_empty[ib]);
+          if (++ib == g.sb) { ib = 0; pb ^= 1u; }
+        }
+      }
+      if (leader) umma_commit(d2_full);
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    float* tile = epi_tiles + (size_t)(warp - 2) * kEpiTileWords;
+    uint32_t pd1 = 0, pd2 = 0;
+    for (int item = blockIdx.x; item < g.total_items; item += gridDim.x) {
+      const int b = item / g.m_items;
+      const int mi = item - b * g.m_items;
+      const int q0 = mi * g.r_out;
+      // ---- phase 1: D1 -> T slab
+      mbar_wait(d1_full, pd1);
+      pd1 ^= 1u;
+      tc_fence_after();
+      {
+        const uint32_t t1 = tmem_base + ((uint32_t)(quad * 32) << 16);
+        const int cps = g.c / g.cw;
+        int s = 0, cc = half;
+        while (cc >= cps) { cc -= cps; ++s; }
+        while (s < g.msub) {
+          const int i_row = s * 128 + quad * 32 + lane;
+          const int t = q0 - g.h2 + i_row;
+          const bool valid = t >= 0 && t < p.lin;
+          if (g.cw == 32) pair_phase1_chunk<32>(P, slabT, t1 + (uint32_t)(s * g.c + cc * 32), i_row, cc * 32, valid);
+          else pair_phase1_chunk<16>(P, slabT, t1 + (uint32_t)(s * g.c + cc * 16), i_row, cc * 16, valid);
+          cc += 2;
+          while (cc >= cps) { cc -= cps; ++s; }
+        }
+      }
+      fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_full);
+      // ---- phase 2: D2 -> global
+      mbar_wait(d2_full, pd2);
+      pd2 ^= 1u;
+      tc_fence_after();
+      {
+        const uint32_t t2 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc_cols;
+        const int row_lim = min(p.lin, q0 + g.r_out);       // rows >= r_out of a tile are not computable here
+        if (g.cw == 32) epilogue_item_rows<32, MODE>(p, tile, t2, b, q0, row_lim, g.msub, g.c, quad, half, lane);
+        else epilogue_item_rows<16, MODE>(p, tile, t2, b, q0, row_lim, g.msub, g.c, quad, half, lane);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d2_empty);
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc_dyn(tmem_base, (uint32_t)g.tmem_cols);
+}
+
+// ------------------------------------------------------------------ host side
+
+inline bool pair_plan(int c, int k, int dil, int lin, int batch, int smem_budget, PairGeom* out) {
+  PairGeom g{};
+  if (c % 16 != 0 || c > 256 || k < 1 || k > kMaxTaps || (k & 1) == 0) return false;
+  g.c = c; g.k = k; g.dil = dil;
+  g.h1 = dil * (k - 1) / 2;
+  g.h2 = (k - 1) / 2;
+  g.rb = (c >= 64 ? 64 : c) * 2;
+  if (g.rb != 32 && g.rb != 64 && g.rb != 128) return false;
+  g.kc = c * 2 / g.rb;
+  g.k16 = g.rb / 32;
+  g.cw = c % 32 == 0 ? 32 : 16;
+  int tb = 1;
+  while (tb < k && tb < 16 && (tb * 2) * c * g.rb <= 16384) tb *= 2;
+  if (tb > k) tb = k;
+  g.tb = tb;
+  g.n_tstages = (k + tb - 1) / tb;
+  g.bstage_bytes = tb * c * g.rb;
+  const int bar_bytes = 1024 + 320 + kTcEpiWarps * kEpiTileWords * 4;
+  int msub = 256 / c;
+  if (msub < 1) msub = 1;
+  if (msub > 8) msub = 8;
+  const int need = (lin + 2 * g.h2 + 127) / 128;
+  if (msub > need) msub = need;
+  for (; msub >= 1; --msub) {
+    g.msub = msub;
+    g.mt = msub * 128;
+    g.r_out = g.mt - 2 * g.h2;
+    if (g.r_out < 1) continue;
+    const int slab_rows = g.mt + 2 * g.h1;
+    g.n_loads = (slab_rows + 255) / 256;
+    g.box_rows = (((slab_rows + g.n_loads - 1) / g.n_loads) + 7) & ~7;
+    g.a_rows = g.n_loads * g.box_rows;
+    g.slab_bytes = g.a_rows * g.rb;
+    g.t_rows = (g.mt + 2 * g.h2 + 7) & ~7;
+    g.t_chunk_bytes = g.t_rows * g.rb;
+    const int fixed = g.kc * g.t_chunk_bytes + bar_bytes;
+    int sa = g.kc + 1 < 4 ? g.kc + 1 : 4, sb = 4;
+    while (sa > 2 && sa * g.slab_bytes + sb * g.bstage_bytes + fixed > smem_budget) --sa;
+    while (sb > 2 && sa * g.slab_bytes + sb * g.bstage_bytes + fixed > smem_budget) --sb;
+    if (sa * g.slab_bytes + sb * g.bstage_bytes + fixed > smem_budget) continue;
+    while (sb < kTcMaxStagesB && sb < 2 * g.n_tstages * g.kc && (sb + 1) * g.bstage_bytes <= 64 * 1024 &&
+           sa * g.slab_bytes + (sb + 1) * g.bstage_bytes + fixed <= smem_budget)
+      ++sb;
+    g.sa = sa;
+    g.sb = sb;
+    g.smem_bytes = sa * g.slab_bytes + sb * g.bstage_bytes + fixed;
+    int cols = 32;
+    while (cols < 2 * msub * c) cols <<= 1;
+    if (cols > 512) continue;
+    g.tmem_cols = cols;
+    g.m_items = (lin + g.r_out - 1) / g.r_out;
+    g.total_items = batch * g.m_items;
+    g.idesc = umma_idesc_bf16(128u, (uint32_t)c);
+    *out = g;
+    return true;
+  }
+  return false;
+}
+
+template <int MODE>
+inline cudaError_t launch_pair_mode(const PairParams& P, const CUtensorMap& tmA, const CUtensorMap& tmW1,
+                                    const CUtensorMap& tmW2, int grid, cudaStream_t stream) {
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(pair_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(pair_tc_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    configured[dev] = true;
+  }
+  pair_tc_kernel<MODE><<<grid, kTcThreads, P.g.smem_bytes, stream>>>(tmA, tmW1, tmW2, P);
+  return cudaGetLastError();
+}
+
+// c: the c2 epilogue description (bias = b2, res, acc_in, outputs, div, slope, lin = mrows = L, ntot = C, out_valid = L * C).
+inline cudaError_t launch_pair_tc(const ConvParams& c, const float* bias1, const PairGeom& g, const CUtensorMap& tmA,
+                                  const CUtensorMap& tmW1, const CUtensorMap& tmW2, int num_ctas, cudaStream_t stream) {
+  PairParams P;
+  P.c = c;
+  P.bias1 = bias1;
+  P.g = g;
+  int grid = g.total_items < num_ctas ? g.total_items : num_ctas;
+  if (grid < 1) grid = 1;
+  const int mode = (c.res ? kEpiRes : 0) | ((c.acc_in || c.div != 1.0f) ? kEpiAcc : 0) | (c.out_raw ? kEpiRaw : 0) |
+                   (c.out_act ? kEpiAct : 0);
+  switch (mode) {
+#define L2S_PMODE(m) case m: return launch_pair_mode<m>(P, tmA, tmW1, tmW2, grid, stream);
+    L2S_PMODE(5) L2S_PMODE(7) L2S_PMODE(11) L2S_PMODE(13) L2S_PMODE(15)
+#undef L2S_PMODE
+    default: return cudaErrorInvalidValue;   // a ResBlock step always has the residual and an output
+  }
+}
+
+}  // namespace l2s

@@ -16,6 +16,7 @@
 #include "conv_common.cuh"
 #include "conv_simt.cuh"
 #include "conv_tc.cuh"
+#include "pair_tc.cuh"
 #include "frontend.cuh"
 
 using namespace l2s;
@@ -30,6 +31,7 @@ struct Knobs {
   long long per_tap = 0;
   long long sa_min = 0;
   long long dual = 1;
+  long long fuse_pairs = 1;        // bf16 mode: one kernel per ResBlock (c1, c2) step
   long long plan_report = 0;       // l2s_debug_conv: write the chosen plan + occupancy into the err buffer
   long long trace_ptr = 0;         // device pointer for the kernel trace of l2s_debug_conv (0: off)
   long long max_msub = 8;
@@ -341,6 +343,59 @@ int run_conv(l2s_vocoder* v, ConvLayer& L, cudaStream_t st, int batch, int lin, 
   return L2S_OK;
 }
 
+bool ensure_w_map(ConvLayer& L, int rb, int nt, int tb) {
+  if (L.has_tmW && L.tm_nt == nt && L.tm_tb == tb) return true;
+  if (!make_tmap_bf16_3d(&L.tmW, L.w_dev, (uint64_t)L.cin_pad, (uint64_t)L.ntot, (uint64_t)L.ntaps, (uint32_t)(rb / 2),
+                         (uint32_t)nt, (uint32_t)tb))
+    return false;
+  L.has_tmW = true;
+  L.tm_nt = nt;
+  L.tm_tb = tb;
+  return true;
+}
+
+bool pairs_fused(const l2s_vocoder* v) { return is_bf16(v) && !g_knobs.force_simt && g_knobs.fuse_pairs; }
+
+// One fused ResBlock step  y = x + c2(lrelu(c1(xa)))  (bf16 tensor-core mode).  Returns
+// L2S_ERR_UNSUPPORTED when no fused plan exists (the caller then runs the two convs).
+int run_pair(l2s_vocoder* v, ConvLayer& c1, ConvLayer& c2, cudaStream_t st, int batch, int lin, const void* in_act,
+             const float* res, float* out_raw, void* out_act, const float* acc_in, float div, float slope) {
+  if (c1.cin != c1.cout || c2.cin != c2.cout || c1.cin != c2.cin || c1.cin_pad != c1.cin || c1.k != c2.k || c2.dil != 1)
+    return L2S_ERR_UNSUPPORTED;
+  PairGeom g;
+  if (!pair_plan(c1.cin, c1.k, c1.dil, lin, batch, 220 * 1024, &g)) return L2S_ERR_UNSUPPORTED;
+  if (!ensure_w_map(c1, g.rb, g.c, g.tb) || !ensure_w_map(c2, g.rb, g.c, g.tb))
+    return fail(v, L2S_ERR_CUDA, "cuTensorMapEncodeTiled failed for the weights of " + c1.name);
+  CUtensorMap tmA;
+  if (!make_tmap_bf16_3d(&tmA, in_act, (uint64_t)c1.cin_pad, (uint64_t)lin, (uint64_t)batch, (uint32_t)(g.rb / 2),
+                         (uint32_t)g.box_rows, 1u))
+    return fail(v, L2S_ERR_CUDA, "cuTensorMapEncodeTiled failed for the input of " + c1.name);
+  ConvParams p{};
+  p.in = in_act;
+  p.w = c2.w_dev;
+  p.bias = c2.bias_dev;
+  p.out_raw = out_raw;
+  p.out_act = out_act;
+  p.res = res;
+  p.acc_in = acc_in;
+  p.batch = batch;
+  p.lin = lin;
+  p.cin_pad = c2.cin_pad;
+  p.ntaps = c2.ntaps;
+  p.ntot = c2.ntot;
+  p.mrows = lin;
+  p.out_shift = 0;
+  p.out_valid = (long long)lin * c2.cout;
+  p.div = div;
+  p.slope = slope;
+  timed_begin(v, st, c1.name + "+c2", 4.0 * c1.cin * c1.cout * c1.k * (double)batch * lin);
+  const int ctas = g_knobs.max_ctas > 0 ? (int)g_knobs.max_ctas : v->num_sms;
+  cudaError_t e = launch_pair_tc(p, c1.bias_dev, g, tmA, c1.tmW, c2.tmW, ctas, st);
+  timed_end(v, st);
+  if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, std::string("launch pair ") + c1.name + ": " + cudaGetErrorString(e));
+  return L2S_OK;
+}
+
 struct Workspace {
   void* cond;
   void* ma[2];
@@ -487,22 +542,48 @@ int forward_impl(l2s_vocoder* v, void* stream, const int64_t* code, const void* 
     const long long numel = (long long)batch * len * ch;
     const bool last_stage = i == c.n_ups - 1;
     const bool want_raw = last_stage || g_knobs.stop_after_stage == i;
+    // A fused step reads its activated input WITH HALO while other CTAs already write the activated
+    // output, so fused stages ping-pong the activated buffers (xa -> ya -> ta -> ...); the fp32
+    // residual is updated in place (each element is read and written by the same thread).
+    bool stage_fused = pairs_fused(v);
+    for (int j = 0; stage_fused && j < c.n_rk; ++j)
+      for (int m = 0; m < c.n_dil; ++m) {
+        const ConvLayer& a1 = v->convs[v->rb_c1[i][j][m]];
+        const ConvLayer& a2 = v->convs[v->rb_c2[i][j][m]];
+        PairGeom pg;
+        if (a1.cin != a1.cout || a1.cin_pad != a1.cin || a1.k != a2.k || a2.dil != 1 ||
+            !pair_plan(a1.cin, a1.k, a1.dil, (int)len, batch, 220 * 1024, &pg))
+          stage_fused = false;
+      }
     for (int j = 0; j < c.n_rk; ++j) {
       for (int m = 0; m < c.n_dil; ++m) {
         ConvLayer& c1 = v->convs[v->rb_c1[i][j][m]];
         ConvLayer& c2 = v->convs[v->rb_c2[i][j][m]];
-        const void* in1 = m == 0 ? ws.xa : ws.ya;
+        void* act_pp[2] = {ws.ya, ws.ta};
+        const void* in1 = m == 0 ? ws.xa : (stage_fused ? act_pp[(m - 1) & 1] : ws.ya);
+        void* mid_act = stage_fused ? act_pp[m & 1] : ws.ya;     // activated output of a non-final step
         const float* res = m == 0 ? ws.x : ws.y;
-        rc = run_conv(v, c1, st, batch, (int)len, in1, nullptr, ws.ta, nullptr, nullptr, 1.f, 0.1f);
-        if (rc) return rc;
-        if (m < c.n_dil - 1) {
-          rc = run_conv(v, c2, st, batch, (int)len, ws.ta, ws.y, ws.ya, res, nullptr, 1.f, 0.1f);
-        } else if (j < c.n_rk - 1) {
-          rc = run_conv(v, c2, st, batch, (int)len, ws.ta, ws.acc, nullptr, res, j == 0 ? nullptr : ws.acc, 1.f, 0.1f);
-        } else {
+        // per (j, m): which outputs the step produces
+        float* o_raw;
+        void* o_act;
+        const float* a_in = nullptr;
+        float dv = 1.f;
+        if (m < c.n_dil - 1) { o_raw = ws.y; o_act = mid_act; }
+        else if (j < c.n_rk - 1) { o_raw = ws.acc; o_act = nullptr; a_in = j == 0 ? nullptr : ws.acc; }
+        else {
           // last branch: mean over branches (true division by num_kernels, models.py:109)
-          rc = run_conv(v, c2, st, batch, (int)len, ws.ta, want_raw ? ws.acc : nullptr, last_stage ? nullptr : ws.ma[cur ^ 1],
-                        res, c.n_rk == 1 ? nullptr : ws.acc, (float)c.n_rk, 0.1f);
+          o_raw = want_raw ? ws.acc : nullptr;
+          o_act = last_stage ? nullptr : ws.ma[cur ^ 1];
+          a_in = c.n_rk == 1 ? nullptr : ws.acc;
+          dv = (float)c.n_rk;
+        }
+        if (stage_fused) {
+          rc = run_pair(v, c1, c2, st, batch, (int)len, in1, res, o_raw, o_act, a_in, dv, 0.1f);
+          if (rc == L2S_ERR_UNSUPPORTED) return fail(v, L2S_ERR_STATE, "fused plan vanished for " + c1.name);
+        } else {
+          rc = run_conv(v, c1, st, batch, (int)len, in1, nullptr, ws.ta, nullptr, nullptr, 1.f, 0.1f);
+          if (rc) return rc;
+          rc = run_conv(v, c2, st, batch, (int)len, ws.ta, o_raw, o_act, res, a_in, dv, 0.1f);
         }
         if (rc) return rc;
       }
@@ -703,6 +784,7 @@ int32_t l2s_launch_count(l2s_vocoder* v, int32_t batch, int32_t frames) {
   (void)batch; (void)frames;
   const l2s_config& c = v->cfg;
   int n = (int)v->convs.size() + 1 /* post */ + 1 /* cond */;
+  if (pairs_fused(v)) n -= c.n_ups * c.n_rk * c.n_dil;   // one launch per (c1, c2) step
   if (c.variant == L2S_VARIANT_MULTI_INPUT && c.multispkr) n += 1;
   return n;
 }
@@ -810,6 +892,7 @@ int l2s_debug_set(const char* key, int64_t value) {
   else if (k == "per_tap") g_knobs.per_tap = value;
   else if (k == "sa_min") g_knobs.sa_min = value;
   else if (k == "dual") g_knobs.dual = value;
+  else if (k == "fuse_pairs") g_knobs.fuse_pairs = value;
   else if (k == "plan_report") g_knobs.plan_report = value;
   else if (k == "trace_ptr") g_knobs.trace_ptr = value;
   else if (k == "max_msub") g_knobs.max_msub = value;

@@ -37,8 +37,14 @@ def test_create_validates_without_cuda(pkg):
     hnd = C.c_void_p()
     assert lib.l2s_create(C.byref(cfg), C.byref(hnd)) == pkg._cabi.OK
     assert lib.l2s_hop(hnd) == 160
-    # 1 speaker projection + 1 conditioning + conv_pre + 5 ups + 90 resblock convs + conv_post
-    assert lib.l2s_launch_count(hnd, 16, 400) == 99
+    # bf16 mode: 1 speaker projection + 1 conditioning + conv_pre + 5 ups + 45 fused ResBlock steps + conv_post
+    assert lib.l2s_launch_count(hnd, 16, 400) == 54
+    cfg32 = _cfg(pkg)
+    cfg32.precision = pkg._cabi.PREC_FP32
+    h32 = C.c_void_p()
+    assert lib.l2s_create(C.byref(cfg32), C.byref(h32)) == pkg._cabi.OK
+    assert lib.l2s_launch_count(h32, 16, 400) == 99      # fp32 mode: every conv is its own launch
+    lib.l2s_destroy(h32)
     assert lib.l2s_workspace_bytes(hnd, 16, 400) > 0
     assert lib.l2s_workspace_bytes(hnd, 0, 400) < 0
     # forward before finalize is a state error, not a crash

@@ -217,6 +217,27 @@ def test_chunked_long_form_equals_full(pkg, weights, precision):
     assert float((chunked - full).abs().max()) <= (1e-6 if precision == "fp32" else 1e-6)
 
 
+@pytest.mark.parametrize("frames", [6, 100, 428])
+def test_fused_resblock_steps_equal_unfused(pkg, weights, frames):
+    """The fused (c1 -> smem -> c2) kernel must give the SAME bits as the two separate tcgen05 convs:
+    identical operands, identical per-row accumulation order."""
+    h, sds = weights
+    code, mel, spkr = vo.synthetic_inputs(2, frames, seed=21)
+    g = make_gen(pkg, h, sds["trained"], "bf16")
+    lib = pkg._cabi.load()
+    try:
+        lib.l2s_debug_set(b"fuse_pairs", 1)
+        a = g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV)).clone()
+        assert g.launch_count(2, frames, DEV) == 54
+        lib.l2s_debug_set(b"fuse_pairs", 0)
+        b = g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV)).clone()
+        assert g.launch_count(2, frames, DEV) == 99
+    finally:
+        lib.l2s_debug_set(b"fuse_pairs", 1)
+    assert torch.isfinite(a).all()
+    assert torch.equal(a, b), float((a - b).abs().max())
+
+
 def test_cfg2_shape_bf16_vs_fp32_device_reference(pkg, weights):
     """configs[1] at full size (16 x 4 s): bf16 tensor-core path against the fp32
     CUDA-core mode of the same library, plus finiteness and range."""
