@@ -130,26 +130,42 @@ __device__ __forceinline__ EpiChunk epi_locate(const ConvParams& p, uint32_t tad
 // Epilogue mode bits (compile-time: dead paths disappear from the instruction stream).
 constexpr int kEpiRes = 1, kEpiAcc = 2, kEpiRaw = 4, kEpiAct = 8;
 
-// Stage 1 of a chunk: the loads that do not depend on each other (accumulator from TMEM,
-// residual stream from global memory).
-template <int CW, int MODE, bool FULL>
-__device__ __forceinline__ void epi_issue(const ConvParams& p, const EpiChunk& c, uint32_t (&r)[CW],
-                                          float4 (&rv)[CW / 4]) {
+// Residual-stream / branch-sum loads of a chunk: plain global loads that do not depend on the
+// accumulator, so they are issued as early as possible (one chunk ahead, and before waiting for the MMAs).
+template <int CW, int MODE>
+__device__ __forceinline__ void epi_load_res(const ConvParams& p, const EpiChunk& c, float4 (&rv)[CW / 4]) {
   constexpr int LPR = CW / 4, RPI = 32 / LPR, ITERS = 32 / RPI;
-  if constexpr (CW == 32) tmem_ld32(c.taddr, r); else tmem_ld16(c.taddr, r);
   if constexpr ((MODE & kEpiRes) != 0) {
     const float* rp = p.res + c.e0;
     const int step = RPI * p.ntot;
 #pragma unroll
     for (int i = 0; i < ITERS; ++i, rp += step)
-      rv[i] = (FULL || ((c.okmask >> i) & 1u)) ? *reinterpret_cast<const float4*>(rp) : make_float4(0.f, 0.f, 0.f, 0.f);
+      rv[i] = ((c.okmask >> i) & 1u) ? *reinterpret_cast<const float4*>(rp) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+template <int CW, int MODE>
+__device__ __forceinline__ void epi_load_acc(const ConvParams& p, const EpiChunk& c, float4 (&av)[CW / 4]) {
+  constexpr int LPR = CW / 4, RPI = 32 / LPR, ITERS = 32 / RPI;
+  if constexpr ((MODE & kEpiAcc) != 0) {
+    if (p.acc_in) {
+      const float* ap = p.acc_in + c.e0;
+      const int step = RPI * p.ntot;
+#pragma unroll
+      for (int i = 0; i < ITERS; ++i, ap += step)
+        av[i] = ((c.okmask >> i) & 1u) ? *reinterpret_cast<const float4*>(ap) : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+#pragma unroll
+      for (int i = 0; i < ITERS; ++i) av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
 }
 
 // Stage 2: accumulator rows -> transpose tile (one row per lane, swizzled float4 slots).
 template <int CW>
-__device__ __forceinline__ void epi_stage(float4* tile4, const uint32_t (&r)[CW], int lane) {
-  tmem_ld_wait();
+__device__ __forceinline__ void epi_stage(float4* tile4, uint32_t taddr, int lane) {
+  uint32_t r[CW];
+  if constexpr (CW == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
+  tmem_ld_wait();      // kept adjacent to the load: see epilogue_item_rows
 #pragma unroll
   for (int j = 0; j < CW / 4; ++j)
     tile4[epi_slot<CW>(lane, j)] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
@@ -159,13 +175,12 @@ __device__ __forceinline__ void epi_stage(float4* tile4, const uint32_t (&r)[CW]
 // Stage 3: read back column-per-lane, apply bias / residual / branch sum / mean / leaky-ReLU, store.
 template <int CW, int MODE, bool FULL>
 __device__ __forceinline__ void epi_finish(const ConvParams& p, const EpiChunk& c, const float4* tile4,
-                                           const float4 (&rv)[CW / 4], int crow, int c4) {
+                                           const float4 (&rv)[CW / 4], const float4 (&av)[CW / 4], int crow, int c4) {
   constexpr int LPR = CW / 4, RPI = 32 / LPR, ITERS = 32 / RPI;
   const int step = RPI * p.ntot;
   const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + c.n));
   float* raw_p = p.out_raw + c.e0;
   __nv_bfloat16* act_p = reinterpret_cast<__nv_bfloat16*>(p.out_act) + c.e0;
-  const float* acc_p = p.acc_in + c.e0;
   const float slope = p.slope;
   // The tensor-core (bf16) mode multiplies by the reciprocal of the branch count; the
   // fp32 CUDA-core mode keeps the reference's true division (conv_common.cuh).
@@ -177,10 +192,7 @@ __device__ __forceinline__ void epi_finish(const ConvParams& p, const EpiChunk& 
     float v0 = t.x + bv.x, v1 = t.y + bv.y, v2 = t.z + bv.z, v3 = t.w + bv.w;
     if constexpr ((MODE & kEpiRes) != 0) { v0 += rv[i].x; v1 += rv[i].y; v2 += rv[i].z; v3 += rv[i].w; }
     if constexpr ((MODE & kEpiAcc) != 0) {
-      if (ok && p.acc_in) {
-        const float4 a = *reinterpret_cast<const float4*>(acc_p + (long long)i * step);
-        v0 += a.x; v1 += a.y; v2 += a.z; v3 += a.w;
-      }
+      v0 += av[i].x; v1 += av[i].y; v2 += av[i].z; v3 += av[i].w;
       v0 *= inv_div; v1 *= inv_div; v2 *= inv_div; v3 *= inv_div;   // div != 1 only on the branch-mean conv
     }
     if (ok) {
@@ -202,46 +214,62 @@ __device__ __forceinline__ void epi_finish(const ConvParams& p, const EpiChunk& 
 // All chunks of one item owned by this warp (quadrant `quad`, every second chunk starting at
 // `half`): msub accumulators of 128 rows x nt columns at TMEM address t_base; tile row 0 is output
 // row q0 of utterance b, column 0 is output column n_tile_base; rows >= row_lim are not stored.
+// `bar` is the accumulator-ready barrier: the first chunk's residual loads are issued BEFORE
+// waiting on it, and chunk j+1's residual loads while chunk j is finished (two chunks of
+// residual in flight per warp; with one, exposed DRAM latency capped a CTA at ~3 TB/s / 148).
 // The TMEM load and its wait stay adjacent: a tcgen05.ld left in flight across other code is not
-// safe (the compiler may move its destination registers before wait::ld; measured wrong
-// results), so latency is hidden by the other epilogue warps instead.
-template <int CW, int MODE>
+// safe (the compiler may move its destination registers before wait::ld; measured wrong results).
+template <int CW, int MODE, bool PIPE>
 __device__ __forceinline__ void epilogue_item_rows(const ConvParams& p, float* tile, uint32_t t_base, int b, int q0,
                                                    int row_lim, int msub, int nt, int quad, int half, int lane,
-                                                   int n_tile_base = 0) {
+                                                   int n_tile_base, uint64_t* bar, uint32_t parity) {
   constexpr int LPR = CW / 4;
+  constexpr uint32_t kAll = (1u << (CW / 4)) - 1u;
+  // PIPE: double-buffer the residual registers (needs the 168-register budget of the fused kernel)
+  constexpr bool kPipe = PIPE && (MODE & kEpiRes) != 0 && (MODE & kEpiAcc) == 0;
   const int crow = lane / LPR;
   const int c4 = lane % LPR;
   float4* tile4 = reinterpret_cast<float4*>(tile);
   const int cps = nt / CW;                    // chunks per 128-row accumulator
+  auto locate = [&](int s_, int cc_) {
+    return epi_locate<CW>(p, t_base + (uint32_t)(s_ * nt + cc_ * CW), b, q0 + s_ * 128 + quad * 32, n_tile_base + cc_ * CW,
+                          crow, c4, row_lim);
+  };
+  auto finish = [&](const EpiChunk& c, const float4 (&rv)[CW / 4], const float4 (&av)[CW / 4]) {
+    if (__all_sync(0xffffffffu, c.okmask == kAll)) epi_finish<CW, MODE, true>(p, c, tile4, rv, av, crow, c4);
+    else epi_finish<CW, MODE, false>(p, c, tile4, rv, av, crow, c4);
+  };
   int s = 0, cc = half;
   while (cc >= cps) { cc -= cps; ++s; }
-  while (s < msub) {
-    const EpiChunk c = epi_locate<CW>(p, t_base + (uint32_t)(s * nt + cc * CW), b, q0 + s * 128 + quad * 32,
-                                      n_tile_base + cc * CW, crow, c4, row_lim);
-    uint32_t r[CW];
-    float4 rv[CW / 4];
-    if (__all_sync(0xffffffffu, c.okmask == (1u << (CW / 4)) - 1u)) {
-      epi_issue<CW, MODE, true>(p, c, r, rv);
-      epi_stage<CW>(tile4, r, lane);
-      __syncwarp();
-      epi_finish<CW, MODE, true>(p, c, tile4, rv, crow, c4);
-    } else {
-      epi_issue<CW, MODE, false>(p, c, r, rv);
-      epi_stage<CW>(tile4, r, lane);
-      __syncwarp();
-      epi_finish<CW, MODE, false>(p, c, tile4, rv, crow, c4);
-    }
-    __syncwarp();   // the tile is rewritten by the next chunk
+  bool have = s < msub;
+  EpiChunk ca{}, cb{};
+  float4 rva[CW / 4], rvb[CW / 4], av[CW / 4];
+  if (have) { ca = locate(s, cc); epi_load_res<CW, MODE>(p, ca, rva); }
+  mbar_wait(bar, parity);
+  tc_fence_after();
+  while (have) {
+    // ---- chunk A
     cc += 2;
     while (cc >= cps) { cc -= cps; ++s; }
+    bool more = s < msub;
+    epi_load_acc<CW, MODE>(p, ca, av);
+    epi_stage<CW>(tile4, ca.taddr, lane);
+    if (kPipe && more) { cb = locate(s, cc); epi_load_res<CW, MODE>(p, cb, rvb); }
+    __syncwarp();
+    finish(ca, rva, av);
+    __syncwarp();   // the tile is rewritten by the next chunk
+    if (!more) break;
+    if (!kPipe) { ca = locate(s, cc); epi_load_res<CW, MODE>(p, ca, rva); continue; }
+    // ---- chunk B (residual already in flight)
+    cc += 2;
+    while (cc >= cps) { cc -= cps; ++s; }
+    have = s < msub;
+    epi_stage<CW>(tile4, cb.taddr, lane);
+    if (have) { ca = locate(s, cc); epi_load_res<CW, MODE>(p, ca, rva); }
+    __syncwarp();
+    finish(cb, rvb, av);
+    __syncwarp();
   }
-}
-
-template <int CW, int MODE>
-__device__ __forceinline__ void epilogue_item(const ConvParams& p, const TcGeom& g, float* tile, uint32_t t_base, int b,
-                                              int mi, int ni, int quad, int half, int lane) {
-  epilogue_item_rows<CW, MODE>(p, tile, t_base, b, mi * g.msub * 128, p.mrows, g.msub, g.nt, quad, half, lane, ni * g.nt);
 }
 
 // K16 consecutive K = 16 slices of one (tap, 64-channel chunk): descriptors advance by 32 bytes.
@@ -444,12 +472,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int mi = rem / g.n_ntiles;
       const int ni = rem - mi * g.n_ntiles;
       if (warp == 2) L2S_TRACE(2, it_no, 0);
-      mbar_wait(&acc_full[buf], buf ? pacc1 : pacc0);
-      if (warp == 2) L2S_TRACE(2, it_no, 1);
-      tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * acc_cols);
-      if (g.cw == 32) epilogue_item<32, MODE>(p, g, tile, t_base, b, mi, ni, quad, half, lane);
-      else epilogue_item<16, MODE>(p, g, tile, t_base, b, mi, ni, quad, half, lane);
+      const uint32_t par = buf ? pacc1 : pacc0;
+      if (g.cw == 32)
+        epilogue_item_rows<32, MODE, false>(p, tile, t_base, b, mi * g.msub * 128, p.mrows, g.msub, g.nt, quad, half, lane, ni * g.nt,
+                                     &acc_full[buf], par);
+      else
+        epilogue_item_rows<16, MODE, false>(p, tile, t_base, b, mi * g.msub * 128, p.mrows, g.msub, g.nt, quad, half, lane, ni * g.nt,
+                                     &acc_full[buf], par);
+      if (warp == 2) L2S_TRACE(2, it_no, 1);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);

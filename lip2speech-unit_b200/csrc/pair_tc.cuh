@@ -42,6 +42,7 @@ struct PairParams {
   ConvParams c;          // epilogue of c2: bias = b2, res = x, acc_in, out_raw, out_act, div, slope; lin = mrows = L, ntot = C
   const float* bias1;
   PairGeom g;
+  long long* trace;      // debug timestamps of CTA 0 (see conv_tc.cuh), null in production
 };
 
 // swizzled 16-byte slot index inside a T row (matches the TMA / UMMA 128B, 64B, 32B swizzles)
@@ -86,7 +87,7 @@ __device__ __forceinline__ void pair_phase1_chunk(const PairParams& P, uint8_t* 
 }
 
 template <int MODE>
-__global__ void __maxnreg__(128)
+__global__ void __maxnreg__(168)
 pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
                const __grid_constant__ CUtensorMap tmW2, const PairParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -148,13 +149,16 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int ia = 0, ib = 0;
     uint32_t pa = 0, pb = 0;
     const uint32_t box_bytes = (uint32_t)(g.box_rows * g.rb);
-    for (int item = blockIdx.x; item < g.total_items; item += gridDim.x) {
+    int it_no = 0;
+    for (int item = blockIdx.x; item < g.total_items; item += gridDim.x, ++it_no) {
       const int b = item / g.m_items;
       const int mi = item - b * g.m_items;
       const int row0 = mi * g.r_out - g.h2 - g.h1;          // first xa row of the slab
       for (int kc = 0; kc < g.kc; ++kc) {
         const int ch0 = kc * (g.rb >> 1);
+        if (kc == 0) L2S_TRACE(0, it_no, 0);
         mbar_wait(&a_empty[ia], pa ^ 1u);
+        if (kc == 0) L2S_TRACE(0, it_no, 1);
         if (leader) {
           mbar_expect_tx(&a_full[ia], (uint32_t)g.slab_bytes);
           uint8_t* dst = slabA + (size_t)ia * g.slab_bytes;
@@ -195,10 +199,13 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t t_lo0 = desc_lo_fixed | ((smem_u32(slabT) & 0x3FFFFu) >> 4);
     int ia = 0, ib = 0;
     uint32_t pa = 0, pb = 0, pt = 0, pd2 = 0;
-    for (int item = blockIdx.x; item < g.total_items; item += gridDim.x) {
+    int it_no = 0;
+    for (int item = blockIdx.x; item < g.total_items; item += gridDim.x, ++it_no) {
       // ---- c1: D1 += xa(slab, row shift j*d) . W1[j]
       for (int kc = 0; kc < g.kc; ++kc) {
+        if (kc == 0) L2S_TRACE(1, it_no, 0);
         mbar_wait(&a_full[ia], pa);
+        if (kc == 0) L2S_TRACE(1, it_no, 1);
         tc_fence_after();
         const uint32_t a_lo = desc_lo_fixed | ((smem_u32(slabA + (size_t)ia * g.slab_bytes) & 0x3FFFFu) >> 4);
         for (int ts = 0; ts < g.n_tstages; ++ts) {
@@ -229,11 +236,13 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++ia == g.sa) { ia = 0; pa ^= 1u; }
       }
       if (leader) umma_commit(d1_full);
+      L2S_TRACE(1, it_no, 2);
       // ---- c2: D2 += T(slab, row shift j) . W2[j]   (T written by the epilogue warps)
       mbar_wait(t_full, pt);
       pt ^= 1u;
       mbar_wait(d2_empty, pd2 ^ 1u);
       pd2 ^= 1u;
+      L2S_TRACE(1, it_no, 3);
       tc_fence_after();
       for (int kc = 0; kc < g.kc; ++kc) {
         const uint32_t t_lo = t_lo0 + (uint32_t)(kc * g.t_chunk_bytes >> 4);
@@ -270,12 +279,14 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int half = (warp - 2) >> 2;
     float* tile = epi_tiles + (size_t)(warp - 2) * kEpiTileWords;
     uint32_t pd1 = 0, pd2 = 0;
-    for (int item = blockIdx.x; item < g.total_items; item += gridDim.x) {
+    int it_no = 0;
+    for (int item = blockIdx.x; item < g.total_items; item += gridDim.x, ++it_no) {
       const int b = item / g.m_items;
       const int mi = item - b * g.m_items;
       const int q0 = mi * g.r_out;
       // ---- phase 1: D1 -> T slab
       mbar_wait(d1_full, pd1);
+      if (warp == 2) L2S_TRACE(2, it_no, 0);
       pd1 ^= 1u;
       tc_fence_after();
       {
@@ -297,19 +308,20 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(t_full);
-      // ---- phase 2: D2 -> global
-      mbar_wait(d2_full, pd2);
-      pd2 ^= 1u;
-      tc_fence_after();
+      if (warp == 2) L2S_TRACE(2, it_no, 1);
+      // ---- phase 2: D2 -> global (the wait on d2_full happens inside, after the first residual loads are issued)
       {
         const uint32_t t2 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc_cols;
         const int row_lim = min(p.lin, q0 + g.r_out);       // rows >= r_out of a tile are not computable here
-        if (g.cw == 32) epilogue_item_rows<32, MODE>(p, tile, t2, b, q0, row_lim, g.msub, g.c, quad, half, lane);
-        else epilogue_item_rows<16, MODE>(p, tile, t2, b, q0, row_lim, g.msub, g.c, quad, half, lane);
+        if (g.cw == 32) epilogue_item_rows<32, MODE, true>(p, tile, t2, b, q0, row_lim, g.msub, g.c, quad, half, lane, 0, d2_full, pd2);
+        else epilogue_item_rows<16, MODE, true>(p, tile, t2, b, q0, row_lim, g.msub, g.c, quad, half, lane, 0, d2_full, pd2);
+        pd2 ^= 1u;
       }
+      if (warp == 2) L2S_TRACE(2, it_no, 2);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(d2_empty);
+      if (warp == 2) L2S_TRACE(2, it_no, 3);
     }
   }
 
@@ -400,11 +412,13 @@ inline cudaError_t launch_pair_mode(const PairParams& P, const CUtensorMap& tmA,
 
 // c: the c2 epilogue description (bias = b2, res, acc_in, outputs, div, slope, lin = mrows = L, ntot = C, out_valid = L * C).
 inline cudaError_t launch_pair_tc(const ConvParams& c, const float* bias1, const PairGeom& g, const CUtensorMap& tmA,
-                                  const CUtensorMap& tmW1, const CUtensorMap& tmW2, int num_ctas, cudaStream_t stream) {
+                                  const CUtensorMap& tmW1, const CUtensorMap& tmW2, int num_ctas, cudaStream_t stream,
+                                  long long* trace = nullptr) {
   PairParams P;
   P.c = c;
   P.bias1 = bias1;
   P.g = g;
+  P.trace = trace;
   int grid = g.total_items < num_ctas ? g.total_items : num_ctas;
   if (grid < 1) grid = 1;
   const int mode = (c.res ? kEpiRes : 0) | ((c.acc_in || c.div != 1.0f) ? kEpiAcc : 0) | (c.out_raw ? kEpiRaw : 0) |

@@ -31,6 +31,7 @@ struct Knobs {
   long long per_tap = 0;
   long long sa_min = 0;
   long long dual = 1;
+  long long trace_launch = -1;     // index of the fused-step launch of a forward that gets trace_ptr
   long long fuse_pairs = 1;        // bf16 mode: one kernel per ResBlock (c1, c2) step
   long long plan_report = 0;       // l2s_debug_conv: write the chosen plan + occupancy into the err buffer
   long long trace_ptr = 0;         // device pointer for the kernel trace of l2s_debug_conv (0: off)
@@ -95,6 +96,7 @@ struct l2s_vocoder {
   struct Timed { std::string name; cudaEvent_t a, b; double flops; };
   std::vector<Timed> timed;
   size_t timed_used = 0;
+  long long pair_launches = 0;     // fused-step launches issued by the current forward
 };
 
 namespace {
@@ -390,7 +392,9 @@ int run_pair(l2s_vocoder* v, ConvLayer& c1, ConvLayer& c2, cudaStream_t st, int 
   p.slope = slope;
   timed_begin(v, st, c1.name + "+c2", 4.0 * c1.cin * c1.cout * c1.k * (double)batch * lin);
   const int ctas = g_knobs.max_ctas > 0 ? (int)g_knobs.max_ctas : v->num_sms;
-  cudaError_t e = launch_pair_tc(p, c1.bias_dev, g, tmA, c1.tmW, c2.tmW, ctas, st);
+  long long* trace = (g_knobs.trace_ptr && g_knobs.trace_launch == v->pair_launches) ? reinterpret_cast<long long*>(g_knobs.trace_ptr) : nullptr;
+  ++v->pair_launches;
+  cudaError_t e = launch_pair_tc(p, c1.bias_dev, g, tmA, c1.tmW, c2.tmW, ctas, st, trace);
   timed_end(v, st);
   if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, std::string("launch pair ") + c1.name + ": " + cudaGetErrorString(e));
   return L2S_OK;
@@ -475,6 +479,7 @@ int forward_impl(l2s_vocoder* v, void* stream, const int64_t* code, const void* 
   const int E = c.embedding_dim;
   v->taps.clear();
   v->timed_used = 0;
+  v->pair_launches = 0;
   cudaError_t e;
   ConvLayer& pre = v->convs[v->conv_pre];
 
@@ -893,6 +898,7 @@ int l2s_debug_set(const char* key, int64_t value) {
   else if (k == "sa_min") g_knobs.sa_min = value;
   else if (k == "dual") g_knobs.dual = value;
   else if (k == "fuse_pairs") g_knobs.fuse_pairs = value;
+  else if (k == "trace_launch") g_knobs.trace_launch = value;
   else if (k == "plan_report") g_knobs.plan_report = value;
   else if (k == "trace_ptr") g_knobs.trace_ptr = value;
   else if (k == "max_msub") g_knobs.max_msub = value;
