@@ -149,6 +149,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--knob", action="append", default=[], help="debug knob k=v passed to l2s_debug_set")
     ap.add_argument("--layers", action="store_true", help="also print a per-launch time table to stderr")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -173,6 +174,9 @@ def main():
     ge.build()
     pkg = ge.load_package()
     lib = pkg._cabi.load()
+    for kv in args.knob:
+        k, v = kv.split("=")
+        assert lib.l2s_debug_set(k.encode(), int(v)) == 0, kv
 
     h = vo.shipped_config()
     sd = vo.init_state_dict(h, seed=1234, style="ref")

@@ -96,6 +96,7 @@ struct EpiChunk {
   uint32_t taddr;    // TMEM address of the chunk (my quadrant's lanes, first column)
   uint32_t okmask;   // bit i: row group i is inside the utterance / valid output range
   int n;             // first of my 4 output columns
+  float4 bv;         // bias of my 4 columns, fetched at locate time (its latency hides behind the TMEM load)
 };
 
 template <int CW>
@@ -105,6 +106,7 @@ __device__ __forceinline__ EpiChunk epi_locate(const ConvParams& p, uint32_t tad
   EpiChunk c;
   c.n = n_base + c4 * 4;
   c.taddr = taddr;
+  c.bv = __ldg(reinterpret_cast<const float4*>(p.bias + c.n));
   // Element index (within the utterance) of my granule in row q_base + crow; rows advance by
   // RPI * ntot.  Valid row groups are those with q < mrows and 0 <= idx < out_valid; idx grows
   // with i, so they form one contiguous range [i_lo, i_hi).
@@ -178,7 +180,7 @@ __device__ __forceinline__ void epi_finish(const ConvParams& p, const EpiChunk& 
                                            const float4 (&rv)[CW / 4], const float4 (&av)[CW / 4], int crow, int c4) {
   constexpr int LPR = CW / 4, RPI = 32 / LPR, ITERS = 32 / RPI;
   const int step = RPI * p.ntot;
-  const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + c.n));
+  const float4 bv = c.bv;
   float* raw_p = p.out_raw + c.e0;
   __nv_bfloat16* act_p = reinterpret_cast<__nv_bfloat16*>(p.out_act) + c.e0;
   const float slope = p.slope;

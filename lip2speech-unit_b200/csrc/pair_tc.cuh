@@ -57,6 +57,13 @@ template <int CW>
 __device__ __forceinline__ void pair_phase1_chunk(const PairParams& P, uint8_t* t_slab, uint32_t taddr, int i_row, int c0,
                                                   bool valid) {
   const PairGeom& g = P.g;
+  // bias first: its global-load latency hides behind the TMEM load
+  float4 bias[CW / 4];
+  {
+    const float4* b4 = reinterpret_cast<const float4*>(P.bias1 + c0);
+#pragma unroll
+    for (int s = 0; s < CW / 4; ++s) bias[s] = __ldg(b4 + s);
+  }
   uint32_t r[CW];
   if constexpr (CW == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
   tmem_ld_wait();
@@ -64,10 +71,9 @@ __device__ __forceinline__ void pair_phase1_chunk(const PairParams& P, uint8_t* 
   const int kc2 = c0 / ch_per_chunk;
   const int first16 = ((c0 - kc2 * ch_per_chunk) * 2) >> 4; // first 16-byte slot of these columns in the row
   uint8_t* row_ptr = t_slab + (size_t)kc2 * g.t_chunk_bytes + (size_t)i_row * g.rb;
-  const float4* b4 = reinterpret_cast<const float4*>(P.bias1 + c0);
 #pragma unroll
   for (int s = 0; s < CW / 8; ++s) {                        // 8 columns = 16 bytes of bf16
-    const float4 ba = __ldg(b4 + 2 * s), bb = __ldg(b4 + 2 * s + 1);
+    const float4 ba = bias[2 * s], bb = bias[2 * s + 1];
     float v[8];
     v[0] = __uint_as_float(r[8 * s + 0]) + ba.x; v[1] = __uint_as_float(r[8 * s + 1]) + ba.y;
     v[2] = __uint_as_float(r[8 * s + 2]) + ba.z; v[3] = __uint_as_float(r[8 * s + 3]) + ba.w;
