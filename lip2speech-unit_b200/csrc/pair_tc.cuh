@@ -34,6 +34,8 @@ struct PairGeom {
   int t_chunk_bytes;     // t_rows * rb
   int tb, n_tstages, bstage_bytes, sb;
   int tmem_cols, cw, total_items;
+  int dual;              // planned so that two CTAs share one SM (<= 110 KB smem, <= 256 TMEM columns, 80 registers)
+  int tile_words;        // fp32 words of one warp's transpose tile (32 rows x cw)
   uint32_t idesc;
   int smem_bytes;
 };
@@ -92,8 +94,8 @@ __device__ __forceinline__ void pair_phase1_chunk(const PairParams& P, uint8_t* 
   }
 }
 
-template <int MODE>
-__global__ void __maxnreg__(168)
+template <int MODE, bool DUAL>
+__global__ void __maxnreg__(DUAL ? 80 : 168)
 pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
                const __grid_constant__ CUtensorMap tmW2, const PairParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -283,7 +285,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ---------------------------------------------------------------- epilogue
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
-    float* tile = epi_tiles + (size_t)(warp - 2) * kEpiTileWords;
+    float* tile = epi_tiles + (size_t)(warp - 2) * g.tile_words;
     uint32_t pd1 = 0, pd2 = 0;
     int it_no = 0;
     for (int item = blockIdx.x; item < g.total_items; item += gridDim.x, ++it_no) {
@@ -304,7 +306,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int i_row = s * 128 + quad * 32 + lane;
           const int t = q0 - g.h2 + i_row;
           const bool valid = t >= 0 && t < p.lin;
-          if (g.cw == 32) pair_phase1_chunk<32>(P, slabT, t1 + (uint32_t)(s * g.c + cc * 32), i_row, cc * 32, valid);
+          if (!DUAL && g.cw == 32) pair_phase1_chunk<32>(P, slabT, t1 + (uint32_t)(s * g.c + cc * 32), i_row, cc * 32, valid);
           else pair_phase1_chunk<16>(P, slabT, t1 + (uint32_t)(s * g.c + cc * 16), i_row, cc * 16, valid);
           cc += 2;
           while (cc >= cps) { cc -= cps; ++s; }
@@ -319,8 +321,12 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       {
         const uint32_t t2 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc_cols;
         const int row_lim = min(p.lin, q0 + g.r_out);       // rows >= r_out of a tile are not computable here
-        if (g.cw == 32) epilogue_item_rows<32, MODE, true>(p, tile, t2, b, q0, row_lim, g.msub, g.c, quad, half, lane, 0, d2_full, pd2);
-        else epilogue_item_rows<16, MODE, true>(p, tile, t2, b, q0, row_lim, g.msub, g.c, quad, half, lane, 0, d2_full, pd2);
+        if constexpr (DUAL) {   // 80-register budget: 16-column chunks, no residual double buffer
+          epilogue_item_rows<16, MODE, false>(p, tile, t2, b, q0, row_lim, g.msub, g.c, quad, half, lane, 0, d2_full, pd2);
+        } else {
+          if (g.cw == 32) epilogue_item_rows<32, MODE, true>(p, tile, t2, b, q0, row_lim, g.msub, g.c, quad, half, lane, 0, d2_full, pd2);
+          else epilogue_item_rows<16, MODE, true>(p, tile, t2, b, q0, row_lim, g.msub, g.c, quad, half, lane, 0, d2_full, pd2);
+        }
         pd2 ^= 1u;
       }
       if (warp == 2) L2S_TRACE(2, it_no, 2);
@@ -339,7 +345,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 // ------------------------------------------------------------------ host side
 
-inline bool pair_plan(int c, int k, int dil, int lin, int batch, int smem_budget, PairGeom* out) {
+inline bool pair_plan_with(int c, int k, int dil, int lin, int batch, int smem_budget, bool dual, PairGeom* out) {
   PairGeom g{};
   if (c % 16 != 0 || c > 256 || k < 1 || k > kMaxTaps || (k & 1) == 0) return false;
   g.c = c; g.k = k; g.dil = dil;
@@ -349,15 +355,17 @@ inline bool pair_plan(int c, int k, int dil, int lin, int batch, int smem_budget
   if (g.rb != 32 && g.rb != 64 && g.rb != 128) return false;
   g.kc = c * 2 / g.rb;
   g.k16 = g.rb / 32;
-  g.cw = c % 32 == 0 ? 32 : 16;
+  g.cw = (!dual && c % 32 == 0) ? 32 : 16;
+  g.dual = dual ? 1 : 0;
+  g.tile_words = 32 * g.cw;
   int tb = 1;
   while (tb < k && tb < 16 && (tb * 2) * c * g.rb <= 16384) tb *= 2;
   if (tb > k) tb = k;
   g.tb = tb;
   g.n_tstages = (k + tb - 1) / tb;
   g.bstage_bytes = tb * c * g.rb;
-  const int bar_bytes = 1024 + 320 + kTcEpiWarps * kEpiTileWords * 4;
-  int msub = 256 / c;
+  const int bar_bytes = 1024 + 320 + kTcEpiWarps * g.tile_words * 4;
+  int msub = (dual ? 128 : 256) / c;
   if (msub < 1) msub = 1;
   if (msub > 8) msub = 8;
   const int need = (lin + 2 * g.h2 + 127) / 128;
@@ -387,7 +395,7 @@ inline bool pair_plan(int c, int k, int dil, int lin, int batch, int smem_budget
     g.smem_bytes = sa * g.slab_bytes + sb * g.bstage_bytes + fixed;
     int cols = 32;
     while (cols < 2 * msub * c) cols <<= 1;
-    if (cols > 512) continue;
+    if (cols > (dual ? 256 : 512)) continue;
     g.tmem_cols = cols;
     g.m_items = (lin + g.r_out - 1) / g.r_out;
     g.total_items = batch * g.m_items;
@@ -398,21 +406,29 @@ inline bool pair_plan(int c, int k, int dil, int lin, int batch, int smem_budget
   return false;
 }
 
-template <int MODE>
+// Two co-resident CTAs per SM when the step fits twice (C <= 64 in the shipped config): one CTA's
+// MMA / phase 1 overlaps the other's load/store-heavy phase 2.  (Measured: with half the CTAs every
+// stage takes ~1.7x longer, i.e. the kernels are per-SM latency bound, not chip-memory bound.)
+inline bool pair_plan(int c, int k, int dil, int lin, int batch, int smem_budget, bool allow_dual, PairGeom* out) {
+  if (allow_dual && pair_plan_with(c, k, dil, lin, batch, 110 * 1024, true, out)) return true;
+  return pair_plan_with(c, k, dil, lin, batch, smem_budget, false, out);
+}
+
+template <int MODE, bool DUAL>
 inline cudaError_t launch_pair_mode(const PairParams& P, const CUtensorMap& tmA, const CUtensorMap& tmW1,
                                     const CUtensorMap& tmW2, int grid, cudaStream_t stream) {
   static bool configured[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(pair_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(pair_tc_kernel<MODE, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(pair_tc_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(pair_tc_kernel<MODE, DUAL>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     configured[dev] = true;
   }
-  pair_tc_kernel<MODE><<<grid, kTcThreads, P.g.smem_bytes, stream>>>(tmA, tmW1, tmW2, P);
+  pair_tc_kernel<MODE, DUAL><<<grid, kTcThreads, P.g.smem_bytes, stream>>>(tmA, tmW1, tmW2, P);
   return cudaGetLastError();
 }
 
@@ -425,12 +441,16 @@ inline cudaError_t launch_pair_tc(const ConvParams& c, const float* bias1, const
   P.bias1 = bias1;
   P.g = g;
   P.trace = trace;
-  int grid = g.total_items < num_ctas ? g.total_items : num_ctas;
+  const int cap = num_ctas * (g.dual ? 2 : 1);
+  int grid = g.total_items < cap ? g.total_items : cap;
   if (grid < 1) grid = 1;
   const int mode = (c.res ? kEpiRes : 0) | ((c.acc_in || c.div != 1.0f) ? kEpiAcc : 0) | (c.out_raw ? kEpiRaw : 0) |
                    (c.out_act ? kEpiAct : 0);
   switch (mode) {
-#define L2S_PMODE(m) case m: return launch_pair_mode<m>(P, tmA, tmW1, tmW2, grid, stream);
+#define L2S_PMODE(m)                                                                          \
+  case m:                                                                                     \
+    return g.dual ? launch_pair_mode<m, true>(P, tmA, tmW1, tmW2, grid, stream)               \
+                  : launch_pair_mode<m, false>(P, tmA, tmW1, tmW2, grid, stream);
     L2S_PMODE(5) L2S_PMODE(7) L2S_PMODE(11) L2S_PMODE(13) L2S_PMODE(15)
 #undef L2S_PMODE
     default: return cudaErrorInvalidValue;   // a ResBlock step always has the residual and an output

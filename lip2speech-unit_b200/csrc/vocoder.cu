@@ -365,7 +365,7 @@ int run_pair(l2s_vocoder* v, ConvLayer& c1, ConvLayer& c2, cudaStream_t st, int 
   if (c1.cin != c1.cout || c2.cin != c2.cout || c1.cin != c2.cin || c1.cin_pad != c1.cin || c1.k != c2.k || c2.dil != 1)
     return L2S_ERR_UNSUPPORTED;
   PairGeom g;
-  if (!pair_plan(c1.cin, c1.k, c1.dil, lin, batch, 220 * 1024, &g)) return L2S_ERR_UNSUPPORTED;
+  if (!pair_plan(c1.cin, c1.k, c1.dil, lin, batch, 220 * 1024, g_knobs.dual != 0, &g)) return L2S_ERR_UNSUPPORTED;
   if (!ensure_w_map(c1, g.rb, g.c, g.tb) || !ensure_w_map(c2, g.rb, g.c, g.tb))
     return fail(v, L2S_ERR_CUDA, "cuTensorMapEncodeTiled failed for the weights of " + c1.name);
   CUtensorMap tmA;
@@ -557,7 +557,7 @@ int forward_impl(l2s_vocoder* v, void* stream, const int64_t* code, const void* 
         const ConvLayer& a2 = v->convs[v->rb_c2[i][j][m]];
         PairGeom pg;
         if (a1.cin != a1.cout || a1.cin_pad != a1.cin || a1.k != a2.k || a2.dil != 1 ||
-            !pair_plan(a1.cin, a1.k, a1.dil, (int)len, batch, 220 * 1024, &pg))
+            !pair_plan(a1.cin, a1.k, a1.dil, (int)len, batch, 220 * 1024, g_knobs.dual != 0, &pg))
           stage_fused = false;
       }
     for (int j = 0; j < c.n_rk; ++j) {
