@@ -169,7 +169,7 @@ int l2s_debug_conv(const l2s_conv_desc* d, int32_t impl, int32_t device, void* s
 int l2s_debug_layer_time(l2s_vocoder* v, int32_t idx, float* ms, double* flops, char* name, int32_t name_len);
 
 /* Override a tuning / descriptor knob (tests and probes only): force_simt,
- * stop_after_stage, stop_after_pre, per_tap, sa_min, dual, trace_ptr, max_msub, slab_cap, max_ctas,
+ * stop_after_stage, stop_after_pre, per_tap, sa_min, dual, cluster, fuse_pairs, trace_launch, plan_report, trace_ptr, max_msub, slab_cap, max_ctas,
  * embed_tap, layer_events. */
 int l2s_debug_set(const char* key, int64_t value);
 

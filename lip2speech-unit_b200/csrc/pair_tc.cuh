@@ -16,6 +16,13 @@
 //                         wait t_full (+ d2_empty), c2 from the T slab -> D2, commit d2_full
 //   epilogue (warps 2..9): phase 1  D1 -> T slab (fence.proxy.async, arrive t_full)
 //                          phase 2  D2 -> global (same transposed epilogue as conv_tc.cuh)
+//
+// Weight re-streaming is what bounds the C >= 128 layers (every 118..246-row item needs all taps of
+// both convs: ~18 TB/s of L2->SM traffic at C = 256 if each CTA fetched its own copy).  With
+// g.cluster == 2 the grid is launched as CTA pairs; each CTA TMA-loads HALF of every weight stage
+// and multicasts it to both, a stage is released when BOTH CTAs' MMAs have consumed it
+// (tcgen05.commit multicast), and the pair walks its items in lockstep (a missing item becomes a
+// dummy whose results are not stored).
 #pragma once
 #include "conv_tc.cuh"
 
@@ -34,6 +41,7 @@ struct PairGeom {
   int t_chunk_bytes;     // t_rows * rb
   int tb, n_tstages, bstage_bytes, sb;
   int tmem_cols, cw, total_items;
+  int cluster;           // 1, or 2: CTA pairs fetch each weight stage from L2 once (TMA multicast)
   int dual;              // planned so that two CTAs share one SM (<= 110 KB smem, <= 256 TMEM columns, 80 registers)
   int tile_words;        // fp32 words of one warp's transpose tile (32 rows x cw)
   uint32_t idesc;
@@ -127,7 +135,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
     for (int i = 0; i < g.sa; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < g.sb; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < g.sb; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], (uint32_t)g.cluster); }
     mbar_init(d1_full, 1);
     mbar_init(t_full, kTcEpiWarps);
     mbar_init(d2_full, 1);
@@ -147,9 +155,17 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if (g.cluster > 1) cluster_sync_all();      // the partner's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int acc_cols = g.msub * g.c;          // D1 at [0, acc_cols), D2 at [acc_cols, 2 acc_cols)
+  // item walk: a CTA pair advances in lockstep (pair p handles items 2j + rank, j = p, p + pairs, ...)
+  const int crank = g.cluster > 1 ? (int)cluster_ctarank() : 0;
+  const int walkers = g.cluster > 1 ? (int)gridDim.x / 2 : (int)gridDim.x;
+  const int walk0 = g.cluster > 1 ? (int)blockIdx.x / 2 : (int)blockIdx.x;
+  const int walk_n = g.cluster > 1 ? (g.total_items + 1) / 2 : g.total_items;
+  const uint16_t mc_mask = (uint16_t)((1u << g.cluster) - 1u);
+  const int half_rows = g.c / g.cluster;      // weight rows (output channels) this CTA fetches per stage
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -158,7 +174,8 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t pa = 0, pb = 0;
     const uint32_t box_bytes = (uint32_t)(g.box_rows * g.rb);
     int it_no = 0;
-    for (int item = blockIdx.x; item < g.total_items; item += gridDim.x, ++it_no) {
+    for (int w = walk0; w < walk_n; w += walkers, ++it_no) {
+      const int item = g.cluster > 1 ? 2 * w + crank : w;   // may be == total_items (dummy): b == batch, TMA zero fills
       const int b = item / g.m_items;
       const int mi = item - b * g.m_items;
       const int row0 = mi * g.r_out - g.h2 - g.h1;          // first xa row of the slab
@@ -178,7 +195,11 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&b_empty[ib], pb ^ 1u);
           if (leader) {
             mbar_expect_tx(&b_full[ib], (uint32_t)g.bstage_bytes);
-            tma_load_3d(stageB + (size_t)ib * g.bstage_bytes, &tmW1, &b_full[ib], ch0, 0, ts * g.tb);
+            if (g.cluster > 1)
+              tma_load_3d_mc(stageB + (size_t)ib * g.bstage_bytes + (size_t)crank * half_rows * g.rb, &tmW1, &b_full[ib], ch0,
+                             crank * half_rows, ts * g.tb, mc_mask);
+            else
+              tma_load_3d(stageB + (size_t)ib * g.bstage_bytes, &tmW1, &b_full[ib], ch0, 0, ts * g.tb);
           }
           if (++ib == g.sb) { ib = 0; pb ^= 1u; }
         }
@@ -189,7 +210,11 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&b_empty[ib], pb ^ 1u);
           if (leader) {
             mbar_expect_tx(&b_full[ib], (uint32_t)g.bstage_bytes);
-            tma_load_3d(stageB + (size_t)ib * g.bstage_bytes, &tmW2, &b_full[ib], ch0, 0, ts * g.tb);
+            if (g.cluster > 1)
+              tma_load_3d_mc(stageB + (size_t)ib * g.bstage_bytes + (size_t)crank * half_rows * g.rb, &tmW2, &b_full[ib], ch0,
+                             crank * half_rows, ts * g.tb, mc_mask);
+            else
+              tma_load_3d(stageB + (size_t)ib * g.bstage_bytes, &tmW2, &b_full[ib], ch0, 0, ts * g.tb);
           }
           if (++ib == g.sb) { ib = 0; pb ^= 1u; }
         }
@@ -208,7 +233,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int ia = 0, ib = 0;
     uint32_t pa = 0, pb = 0, pt = 0, pd2 = 0;
     int it_no = 0;
-    for (int item = blockIdx.x; item < g.total_items; item += gridDim.x, ++it_no) {
+    for (int w = walk0; w < walk_n; w += walkers, ++it_no) {
       // ---- c1: D1 += xa(slab, row shift j*d) . W1[j]
       for (int kc = 0; kc < g.kc; ++kc) {
         if (kc == 0) L2S_TRACE(1, it_no, 0);
@@ -237,7 +262,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 issue_chunk<1>(leader, d_addr, desc_hi, a_sub, b_lo, g.idesc, first);
             }
           }
-          if (leader) umma_commit(&b_empty[ib]);
+          if (leader) { if (g.cluster > 1) umma_commit_mc(&b_empty[ib], mc_mask); else umma_commit(&b_empty[ib]); }
           if (++ib == g.sb) { ib = 0; pb ^= 1u; }
         }
         if (leader) umma_commit(&a_empty[ia]);
@@ -275,7 +300,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 issue_chunk<1>(leader, d_addr, desc_hi, a_sub, b_lo, g.idesc, first);
             }
           }
-          if (leader) umma_commit(&b_empty[ib]);
+          if (leader) { if (g.cluster > 1) umma_commit_mc(&b_empty[ib], mc_mask); else umma_commit(&b_empty[ib]); }
           if (++ib == g.sb) { ib = 0; pb ^= 1u; }
         }
       }
@@ -288,7 +313,9 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* tile = epi_tiles + (size_t)(warp - 2) * g.tile_words;
     uint32_t pd1 = 0, pd2 = 0;
     int it_no = 0;
-    for (int item = blockIdx.x; item < g.total_items; item += gridDim.x, ++it_no) {
+    for (int w = walk0; w < walk_n; w += walkers, ++it_no) {
+      const int item = g.cluster > 1 ? 2 * w + crank : w;
+      const bool dummy = item >= g.total_items;             // odd item count: the pair's last partner stores nothing
       const int b = item / g.m_items;
       const int mi = item - b * g.m_items;
       const int q0 = mi * g.r_out;
@@ -305,7 +332,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         while (s < g.msub) {
           const int i_row = s * 128 + quad * 32 + lane;
           const int t = q0 - g.h2 + i_row;
-          const bool valid = t >= 0 && t < p.lin;
+          const bool valid = t >= 0 && t < p.lin && !dummy;
           if (!DUAL && g.cw == 32) pair_phase1_chunk<32>(P, slabT, t1 + (uint32_t)(s * g.c + cc * 32), i_row, cc * 32, valid);
           else pair_phase1_chunk<16>(P, slabT, t1 + (uint32_t)(s * g.c + cc * 16), i_row, cc * 16, valid);
           cc += 2;
@@ -320,7 +347,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ---- phase 2: D2 -> global (the wait on d2_full happens inside, after the first residual loads are issued)
       {
         const uint32_t t2 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc_cols;
-        const int row_lim = min(p.lin, q0 + g.r_out);       // rows >= r_out of a tile are not computable here
+        const int row_lim = dummy ? 0 : min(p.lin, q0 + g.r_out);   // rows >= r_out of a tile are not computable here
         if constexpr (DUAL) {   // 80-register budget: 16-column chunks, no residual double buffer
           epilogue_item_rows<16, MODE, false>(p, tile, t2, b, q0, row_lim, g.msub, g.c, quad, half, lane, 0, d2_full, pd2);
         } else {
@@ -340,12 +367,14 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncwarp();
   tc_fence_before();
   __syncthreads();
+  if (g.cluster > 1) cluster_sync_all();      // no CTA leaves while its partner may still multicast into it
   if (warp == 1) tmem_dealloc_dyn(tmem_base, (uint32_t)g.tmem_cols);
 }
 
 // ------------------------------------------------------------------ host side
 
-inline bool pair_plan_with(int c, int k, int dil, int lin, int batch, int smem_budget, bool dual, PairGeom* out) {
+inline bool pair_plan_with(int c, int k, int dil, int lin, int batch, int smem_budget, bool dual, bool cluster_ok,
+                           PairGeom* out) {
   PairGeom g{};
   if (c % 16 != 0 || c > 256 || k < 1 || k > kMaxTaps || (k & 1) == 0) return false;
   g.c = c; g.k = k; g.dil = dil;
@@ -400,6 +429,8 @@ inline bool pair_plan_with(int c, int k, int dil, int lin, int batch, int smem_b
     g.m_items = (lin + g.r_out - 1) / g.r_out;
     g.total_items = batch * g.m_items;
     g.idesc = umma_idesc_bf16(128u, (uint32_t)c);
+    // weight multicast pays where weights dominate the L2 traffic and a stage is one tap (tb == 1): C >= 128
+    g.cluster = (!dual && cluster_ok && c >= 128 && g.tb == 1 && (c / 2) % 8 == 0 && g.total_items >= 2) ? 2 : 1;
     *out = g;
     return true;
   }
@@ -409,9 +440,10 @@ inline bool pair_plan_with(int c, int k, int dil, int lin, int batch, int smem_b
 // Two co-resident CTAs per SM when the step fits twice (C <= 64 in the shipped config): one CTA's
 // MMA / phase 1 overlaps the other's load/store-heavy phase 2.  (Measured: with half the CTAs every
 // stage takes ~1.7x longer, i.e. the kernels are per-SM latency bound, not chip-memory bound.)
-inline bool pair_plan(int c, int k, int dil, int lin, int batch, int smem_budget, bool allow_dual, PairGeom* out) {
-  if (allow_dual && pair_plan_with(c, k, dil, lin, batch, 110 * 1024, true, out)) return true;
-  return pair_plan_with(c, k, dil, lin, batch, smem_budget, false, out);
+inline bool pair_plan(int c, int k, int dil, int lin, int batch, int smem_budget, bool allow_dual, bool allow_cluster,
+                      PairGeom* out) {
+  if (allow_dual && pair_plan_with(c, k, dil, lin, batch, 110 * 1024, true, false, out)) return true;
+  return pair_plan_with(c, k, dil, lin, batch, smem_budget, false, allow_cluster, out);
 }
 
 template <int MODE, bool DUAL>
@@ -427,6 +459,21 @@ inline cudaError_t launch_pair_mode(const PairParams& P, const CUtensorMap& tmA,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     configured[dev] = true;
+  }
+  if (P.g.cluster > 1) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = (size_t)P.g.smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)P.g.cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, pair_tc_kernel<MODE, DUAL>, tmA, tmW1, tmW2, P);
   }
   pair_tc_kernel<MODE, DUAL><<<grid, kTcThreads, P.g.smem_bytes, stream>>>(tmA, tmW1, tmW2, P);
   return cudaGetLastError();
@@ -444,6 +491,12 @@ inline cudaError_t launch_pair_tc(const ConvParams& c, const float* bias1, const
   const int cap = num_ctas * (g.dual ? 2 : 1);
   int grid = g.total_items < cap ? g.total_items : cap;
   if (grid < 1) grid = 1;
+  if (g.cluster > 1) {                       // CTA pairs: even grid, one pair per two items at most
+    const int pairs_needed = (g.total_items + 1) / 2;
+    int pairs = cap / 2 < pairs_needed ? cap / 2 : pairs_needed;
+    if (pairs < 1) pairs = 1;
+    grid = 2 * pairs;
+  }
   const int mode = (c.res ? kEpiRes : 0) | ((c.acc_in || c.div != 1.0f) ? kEpiAcc : 0) | (c.out_raw ? kEpiRaw : 0) |
                    (c.out_act ? kEpiAct : 0);
   switch (mode) {

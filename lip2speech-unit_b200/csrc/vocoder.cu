@@ -32,6 +32,7 @@ struct Knobs {
   long long sa_min = 0;
   long long dual = 1;
   long long trace_launch = -1;     // index of the fused-step launch of a forward that gets trace_ptr
+  long long cluster = 1;           // fused steps with C >= 128: CTA pairs share weight loads (TMA multicast)
   long long fuse_pairs = 1;        // bf16 mode: one kernel per ResBlock (c1, c2) step
   long long plan_report = 0;       // l2s_debug_conv: write the chosen plan + occupancy into the err buffer
   long long trace_ptr = 0;         // device pointer for the kernel trace of l2s_debug_conv (0: off)
@@ -365,8 +366,9 @@ int run_pair(l2s_vocoder* v, ConvLayer& c1, ConvLayer& c2, cudaStream_t st, int 
   if (c1.cin != c1.cout || c2.cin != c2.cout || c1.cin != c2.cin || c1.cin_pad != c1.cin || c1.k != c2.k || c2.dil != 1)
     return L2S_ERR_UNSUPPORTED;
   PairGeom g;
-  if (!pair_plan(c1.cin, c1.k, c1.dil, lin, batch, 220 * 1024, g_knobs.dual != 0, &g)) return L2S_ERR_UNSUPPORTED;
-  if (!ensure_w_map(c1, g.rb, g.c, g.tb) || !ensure_w_map(c2, g.rb, g.c, g.tb))
+  if (!pair_plan(c1.cin, c1.k, c1.dil, lin, batch, 220 * 1024, g_knobs.dual != 0, g_knobs.cluster != 0, &g)) return L2S_ERR_UNSUPPORTED;
+  // with CTA-pair multicast each CTA fetches half of the output-channel rows of a weight stage
+  if (!ensure_w_map(c1, g.rb, g.c / g.cluster, g.tb) || !ensure_w_map(c2, g.rb, g.c / g.cluster, g.tb))
     return fail(v, L2S_ERR_CUDA, "cuTensorMapEncodeTiled failed for the weights of " + c1.name);
   CUtensorMap tmA;
   if (!make_tmap_bf16_3d(&tmA, in_act, (uint64_t)c1.cin_pad, (uint64_t)lin, (uint64_t)batch, (uint32_t)(g.rb / 2),
@@ -557,7 +559,7 @@ int forward_impl(l2s_vocoder* v, void* stream, const int64_t* code, const void* 
         const ConvLayer& a2 = v->convs[v->rb_c2[i][j][m]];
         PairGeom pg;
         if (a1.cin != a1.cout || a1.cin_pad != a1.cin || a1.k != a2.k || a2.dil != 1 ||
-            !pair_plan(a1.cin, a1.k, a1.dil, (int)len, batch, 220 * 1024, g_knobs.dual != 0, &pg))
+            !pair_plan(a1.cin, a1.k, a1.dil, (int)len, batch, 220 * 1024, g_knobs.dual != 0, g_knobs.cluster != 0, &pg))
           stage_fused = false;
       }
     for (int j = 0; j < c.n_rk; ++j) {
@@ -898,6 +900,7 @@ int l2s_debug_set(const char* key, int64_t value) {
   else if (k == "sa_min") g_knobs.sa_min = value;
   else if (k == "dual") g_knobs.dual = value;
   else if (k == "fuse_pairs") g_knobs.fuse_pairs = value;
+  else if (k == "cluster") g_knobs.cluster = value;
   else if (k == "trace_launch") g_knobs.trace_launch = value;
   else if (k == "plan_report") g_knobs.plan_report = value;
   else if (k == "trace_ptr") g_knobs.trace_ptr = value;
