@@ -32,7 +32,8 @@ struct Knobs {
   long long sa_min = 0;
   long long dual = 1;
   long long trace_launch = -1;     // index of the fused-step launch of a forward that gets trace_ptr
-  long long cluster = 1;           // fused steps with C >= 128: CTA pairs share weight loads (TMA multicast)
+  long long cluster = 0;           // fused steps with C >= 128: CTA pairs share weight loads (TMA multicast); measured
+                                   // neutral on B200 (the weight ring depth, not L2 read volume, bounds those layers)
   long long fuse_pairs = 1;        // bf16 mode: one kernel per ResBlock (c1, c2) step
   long long plan_report = 0;       // l2s_debug_conv: write the chosen plan + occupancy into the err buffer
   long long trace_ptr = 0;         // device pointer for the kernel trace of l2s_debug_conv (0: off)

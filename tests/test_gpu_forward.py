@@ -238,6 +238,26 @@ def test_fused_resblock_steps_equal_unfused(pkg, weights, frames):
     assert torch.equal(a, b), float((a - b).abs().max())
 
 
+@pytest.mark.parametrize("knob", ["dual", "cluster"])
+def test_fused_kernel_variants_agree(pkg, weights, knob):
+    """Two-CTAs-per-SM plans (dual) and CTA-pair weight multicast (cluster) change scheduling only:
+    the waveform must not change by a bit."""
+    h, sds = weights
+    code, mel, spkr = vo.synthetic_inputs(3, 150, seed=33)
+    g = make_gen(pkg, h, sds["trained"], "bf16")
+    lib = pkg._cabi.load()
+    outs = []
+    try:
+        for v in (0, 1):
+            lib.l2s_debug_set(knob.encode(), v)
+            outs.append(g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV)).clone())
+    finally:
+        lib.l2s_debug_set(b"dual", 1)
+        lib.l2s_debug_set(b"cluster", 0)
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1]), float((outs[0] - outs[1]).abs().max())
+
+
 def test_cfg2_shape_bf16_vs_fp32_device_reference(pkg, weights):
     """configs[1] at full size (16 x 4 s): bf16 tensor-core path against the fp32
     CUDA-core mode of the same library, plus finiteness and range."""

@@ -1,10 +1,15 @@
 #!/bin/bash
-# One GPU-box session: parity tests, smoke, bench.  Everything lands in gpurun_out/.
+# One GPU-box session: parity tests, smoke, bench, ncu launch list + one full capture.  Everything lands in gpurun_out/.
 set +e
 mkdir -p gpurun_out
 python -m pytest tests -q -s -m gpu > gpurun_out/pytest_all.log 2>&1
 grep "\[parity\]" gpurun_out/pytest_all.log > gpurun_out/parity.txt
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
-python bench.py --steps 20 --warmup 5 --layers > gpurun_out/bench_bf16.json 2> gpurun_out/bench_bf16.err
+python bench.py --steps 50 --warmup 5 --layers > gpurun_out/bench_bf16.json 2> gpurun_out/bench_bf16.err
+python bench.py --impl reference --steps 2 --warmup 3 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
+python tools/one_forward.py 3 > gpurun_out/plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -s 108 -c 54 --csv --log-file gpurun_out/launches_final.csv python tools/one_forward.py 3 > gpurun_out/ncu_launch.log 2>&1
+python tools/one_forward.py 2 > gpurun_out/plain2.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:pair_tc_kernel -s 54 -c 45 -o gpurun_out/prof_pairs python tools/one_forward.py 2 > gpurun_out/ncu_full.log 2>&1
 tail -n 3 gpurun_out/pytest_all.log; tail -n 2 gpurun_out/smoke.log
 cat gpurun_out/bench_bf16.json
