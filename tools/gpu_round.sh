@@ -1,5 +1,6 @@
 #!/bin/bash
-# One GPU-box session: parity tests, smoke, bench, ncu launch list + one full capture.  Everything lands in gpurun_out/.
+# One GPU-box session: parity tests, smoke, bench, ncu launch list, per-kernel metrics, one full capture.
+# Everything lands in gpurun_out/ (keep it under 64 MiB: one --set full kernel only).
 set +e
 mkdir -p gpurun_out
 python -m pytest tests -q -s -m gpu > gpurun_out/pytest_all.log 2>&1
@@ -10,6 +11,8 @@ python bench.py --impl reference --steps 2 --warmup 3 > gpurun_out/bench_referen
 python tools/one_forward.py 3 > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -s 108 -c 54 --csv --log-file gpurun_out/launches_final.csv python tools/one_forward.py 3 > gpurun_out/ncu_launch.log 2>&1
 python tools/one_forward.py 2 > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:pair_tc_kernel -s 54 -c 45 -o gpurun_out/prof_pairs python tools/one_forward.py 2 > gpurun_out/ncu_full.log 2>&1
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,lts__t_bytes.sum,smsp__inst_executed.sum,launch__registers_per_thread,launch__shared_mem_per_block_dynamic,launch__grid_size --clock-control none -k regex:pair_tc_kernel -s 45 -c 45 --csv --log-file gpurun_out/pairs_metrics.csv python tools/one_forward.py 2 > gpurun_out/ncu_pairs.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:pair_tc_kernel -s 56 -c 1 -o gpurun_out/prof_pair_stage1 python tools/one_forward.py 2 > gpurun_out/ncu_full.log 2>&1
+du -sh gpurun_out
 tail -n 3 gpurun_out/pytest_all.log; tail -n 2 gpurun_out/smoke.log
 cat gpurun_out/bench_bf16.json
