@@ -74,6 +74,21 @@ __device__ __forceinline__ long long gtime() {
     if (P.trace && blockIdx.x == 0 && (slot) < 64 && lane == 0) P.trace[((role) * 64 + (slot)) * 4 + (ev)] = gtime(); \
   } while (0)
 
+// debug cycle accounting of one epilogue warp (CTA 0, warp 2): [0] tmem ld+wait, [1] transpose stores, [2] finish, [3] chunks,
+// [4] locate + residual issue, [5] barrier wait
+__device__ long long g_epi_prof[8];
+__device__ int g_epi_prof_on = 0;
+// accumulated in shared memory (a global read-modify-write per region would itself cost ~700 cycles), flushed at kernel end
+__device__ __forceinline__ long long* epi_prof_smem() {
+  __shared__ long long s_prof[8];
+  return s_prof;
+}
+#ifdef L2S_EPI_PROF   // build with -DL2S_EPI_PROF to enable the epilogue cycle accounting
+#define L2S_PROF_ON (g_epi_prof_on && blockIdx.x == 0 && (threadIdx.x >> 5) == 2)
+#else
+#define L2S_PROF_ON false
+#endif
+
 constexpr int kEpiTileWords = 32 * 32;   // warp-private transpose tile: 32 rows x CW fp32, XOR-swizzled float4 slots
 
 // Epilogue of one [32 rows x CW columns] accumulator chunk owned by one warp.
@@ -111,6 +126,14 @@ __device__ __forceinline__ EpiChunk epi_locate(const ConvParams& p, uint32_t tad
   // RPI * ntot.  Valid row groups are those with q < mrows and 0 <= idx < out_valid; idx grows
   // with i, so they form one contiguous range [i_lo, i_hi).
   const int q0 = q_base + crow;
+  if (p.out_shift == 0 && p.mrows == p.lin) {
+    // plain convolutions (everything but the polyphase ConvTranspose1d): validity is a row test
+    c.e0 = ((long long)b * p.lin + q0) * p.ntot + c.n;      // out_valid == lin * ntot
+    const int left = mrows_eff - q0;                          // valid rows from q0 on
+    const int n_ok = left <= 0 ? 0 : (left + RPI - 1) / RPI;
+    c.okmask = n_ok >= ITERS ? (1u << ITERS) - 1u : (1u << n_ok) - 1u;
+    return c;
+  }
   const long long idx0 = (long long)q0 * p.ntot + c.n + p.out_shift;
   const int step = RPI * p.ntot;
   c.e0 = (long long)b * p.out_valid + idx0;
@@ -166,12 +189,26 @@ __device__ __forceinline__ void epi_load_acc(const ConvParams& p, const EpiChunk
 template <int CW>
 __device__ __forceinline__ void epi_stage(float4* tile4, uint32_t taddr, int lane) {
   uint32_t r[CW];
+  const bool prof = L2S_PROF_ON;
+  long long t0 = 0;
+  if (prof) t0 = clock64();
   if constexpr (CW == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
   tmem_ld_wait();      // kept adjacent to the load: see epilogue_item_rows
+  long long t1 = 0;
+  if (prof) {
+    // force the loaded registers to be consumed before reading the clock: true TMEM -> RF latency
+    uint32_t x = 0;
+#pragma unroll
+    for (int j = 0; j < CW; ++j) x ^= r[j];
+    if (x == 0x7fc12345u) epi_prof_smem()[7] += 1;
+    t1 = clock64();
+    if ((threadIdx.x & 31) == 0) epi_prof_smem()[0] += t1 - t0;
+  }
 #pragma unroll
   for (int j = 0; j < CW / 4; ++j)
     tile4[epi_slot<CW>(lane, j)] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
                                                __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+  if (prof && (threadIdx.x & 31) == 0) { epi_prof_smem()[1] += clock64() - t1; epi_prof_smem()[3] += 1; }
 }
 
 // Stage 3: read back column-per-lane, apply bias / residual / branch sum / mean / leaky-ReLU, store.
@@ -183,7 +220,7 @@ __device__ __forceinline__ void epi_finish(const ConvParams& p, const EpiChunk& 
   const float4 bv = c.bv;
   float* raw_p = p.out_raw + c.e0;
   __nv_bfloat16* act_p = reinterpret_cast<__nv_bfloat16*>(p.out_act) + c.e0;
-  const float slope = p.slope;
+  const __nv_bfloat162 slope2 = __float2bfloat162_rn(p.slope);
   // The tensor-core (bf16) mode multiplies by the reciprocal of the branch count; the
   // fp32 CUDA-core mode keeps the reference's true division (conv_common.cuh).
   const float inv_div = 1.0f / p.div;
@@ -201,12 +238,9 @@ __device__ __forceinline__ void epi_finish(const ConvParams& p, const EpiChunk& 
       if constexpr ((MODE & kEpiRaw) != 0)
         *reinterpret_cast<float4*>(raw_p + (long long)i * step) = make_float4(v0, v1, v2, v3);
       if constexpr ((MODE & kEpiAct) != 0) {
-        // leaky_relu for 0 < slope < 1 is max(v, v * slope)
-        __nv_bfloat162 lo = __floats2bfloat162_rn(fmaxf(v0, v0 * slope), fmaxf(v1, v1 * slope));
-        __nv_bfloat162 hi = __floats2bfloat162_rn(fmaxf(v2, v2 * slope), fmaxf(v3, v3 * slope));
-        uint2 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&lo);
-        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        uint2 pk;   // leaky_relu for 0 < slope < 1 is max(v, v * slope)
+        pk.x = lrelu_bf16x2(v0, v1, slope2);
+        pk.y = lrelu_bf16x2(v2, v3, slope2);
         *reinterpret_cast<uint2*>(act_p + (long long)i * step) = pk;
       }
     }
@@ -238,16 +272,25 @@ __device__ __forceinline__ void epilogue_item_rows(const ConvParams& p, float* t
                           crow, c4, row_lim);
   };
   auto finish = [&](const EpiChunk& c, const float4 (&rv)[CW / 4], const float4 (&av)[CW / 4]) {
+    const bool prof = L2S_PROF_ON;
+    long long t0 = 0;
+    if (prof) t0 = clock64();
     if (__all_sync(0xffffffffu, c.okmask == kAll)) epi_finish<CW, MODE, true>(p, c, tile4, rv, av, crow, c4);
     else epi_finish<CW, MODE, false>(p, c, tile4, rv, av, crow, c4);
+    if (prof && lane == 0) epi_prof_smem()[2] += clock64() - t0;
   };
   int s = 0, cc = half;
   while (cc >= cps) { cc -= cps; ++s; }
   bool have = s < msub;
   EpiChunk ca{}, cb{};
   float4 rva[CW / 4], rvb[CW / 4], av[CW / 4];
+  long long tw0 = 0;
+  if (L2S_PROF_ON) tw0 = clock64();
   if (have) { ca = locate(s, cc); epi_load_res<CW, MODE>(p, ca, rva); }
+  long long tw1 = 0;
+  if (L2S_PROF_ON) { tw1 = clock64(); if (lane == 0) epi_prof_smem()[4] += tw1 - tw0; }
   mbar_wait(bar, parity);
+  if (L2S_PROF_ON && lane == 0) epi_prof_smem()[5] += clock64() - tw1;
   tc_fence_after();
   while (have) {
     // ---- chunk A
@@ -313,6 +356,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#ifdef L2S_EPI_PROF
+  if (g_epi_prof_on && threadIdx.x < 8) epi_prof_smem()[threadIdx.x] = 0;
+#endif
   if (P.trace && threadIdx.x == 0 && blockIdx.x < 512) {   // debug: which SM ran this CTA, and when
     uint32_t smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -495,6 +541,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncwarp();
   tc_fence_before();
   __syncthreads();
+#ifdef L2S_EPI_PROF
+  if (g_epi_prof_on && blockIdx.x == 0 && threadIdx.x < 8) atomicAdd(reinterpret_cast<unsigned long long*>(&g_epi_prof[threadIdx.x]), (unsigned long long)epi_prof_smem()[threadIdx.x]);
+#endif
   if (P.trace && threadIdx.x == 0 && blockIdx.x < 512) P.trace[768 + blockIdx.x * 3 + 2] = gtime();
   if (warp == 1) tmem_dealloc_dyn(tmem_base, (uint32_t)g.tmem_cols);
 }

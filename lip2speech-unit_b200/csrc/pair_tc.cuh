@@ -41,6 +41,8 @@ struct PairGeom {
   int t_chunk_bytes;     // t_rows * rb
   int tb, n_tstages, bstage_bytes, sb;
   int tmem_cols, cw, total_items;
+  int alias_at;          // 1: the A-slab ring lives inside the T-slab region (c1's inputs are dead once T is written)
+  int region_bytes;      // shared memory of the A ring + T slab (max of the two when aliased)
   int cluster;           // 1, or 2: CTA pairs fetch each weight stage from L2 once (TMA multicast)
   int dual;              // planned so that two CTAs share one SM (<= 110 KB smem, <= 256 TMEM columns, 80 registers)
   int tile_words;        // fp32 words of one warp's transpose tile (32 rows x cw)
@@ -91,13 +93,9 @@ __device__ __forceinline__ void pair_phase1_chunk(const PairParams& P, uint8_t* 
     v[6] = __uint_as_float(r[8 * s + 6]) + bb.z; v[7] = __uint_as_float(r[8 * s + 7]) + bb.w;
     uint4 pk;
     uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+    const __nv_bfloat162 slope2 = __float2bfloat162_rn(0.1f);                  // LRELU_SLOPE, models.py:13,38
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float a = valid ? fmaxf(v[2 * e], v[2 * e] * 0.1f) : 0.f;          // LRELU_SLOPE, models.py:13,38
-      const float b = valid ? fmaxf(v[2 * e + 1], v[2 * e + 1] * 0.1f) : 0.f;
-      __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-      pw[e] = *reinterpret_cast<uint32_t*>(&t);
-    }
+    for (int e = 0; e < 4; ++e) pw[e] = valid ? lrelu_bf16x2(v[2 * e], v[2 * e + 1], slope2) : 0u;
     *reinterpret_cast<uint4*>(row_ptr + (t_swz(g.rb, i_row, first16 + s) << 4)) = pk;
   }
 }
@@ -113,8 +111,8 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* slabA = smem;
-  uint8_t* slabT = slabA + (size_t)g.sa * g.slab_bytes;
-  uint8_t* stageB = slabT + (size_t)g.kc * g.t_chunk_bytes;
+  uint8_t* slabT = g.alias_at ? smem : slabA + (size_t)g.sa * g.slab_bytes;
+  uint8_t* stageB = smem + (size_t)g.region_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(stageB + (size_t)g.sb * g.bstage_bytes);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kTcMaxStagesA;
@@ -124,11 +122,15 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* t_full = d1_full + 1;
   uint64_t* d2_full = t_full + 1;
   uint64_t* d2_empty = d2_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_empty + 1);
+  uint64_t* t_free = d2_empty + 1;      // c2 has finished reading the T slab (gates the aliased A-slab loads)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_free + 1);
   float* epi_tiles = reinterpret_cast<float*>(bars + 40);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#ifdef L2S_EPI_PROF
+  if (g_epi_prof_on && threadIdx.x < 8) epi_prof_smem()[threadIdx.x] = 0;
+#endif
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -140,6 +142,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_init(t_full, kTcEpiWarps);
     mbar_init(d2_full, 1);
     mbar_init(d2_empty, kTcEpiWarps);
+    mbar_init(t_free, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_dyn(tmem_slot, (uint32_t)g.tmem_cols);
@@ -171,7 +174,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------ TMA producer
     const bool leader = elect_one();
     int ia = 0, ib = 0;
-    uint32_t pa = 0, pb = 0;
+    uint32_t pa = 0, pb = 0, ptf = 0;
     const uint32_t box_bytes = (uint32_t)(g.box_rows * g.rb);
     int it_no = 0;
     for (int w = walk0; w < walk_n; w += walkers, ++it_no) {
@@ -179,6 +182,10 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int b = item / g.m_items;
       const int mi = item - b * g.m_items;
       const int row0 = mi * g.r_out - g.h2 - g.h1;          // first xa row of the slab
+      if (g.alias_at && it_no > 0) {                        // the slabs overwrite the T slab of the previous item
+        mbar_wait(t_free, ptf);
+        ptf ^= 1u;
+      }
       for (int kc = 0; kc < g.kc; ++kc) {
         const int ch0 = kc * (g.rb >> 1);
         if (kc == 0) L2S_TRACE(0, it_no, 0);
@@ -304,7 +311,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++ib == g.sb) { ib = 0; pb ^= 1u; }
         }
       }
-      if (leader) umma_commit(d2_full);
+      if (leader) { umma_commit(d2_full); umma_commit(t_free); }
     }
   } else {
     // ---------------------------------------------------------------- epilogue
@@ -367,6 +374,9 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncwarp();
   tc_fence_before();
   __syncthreads();
+#ifdef L2S_EPI_PROF
+  if (g_epi_prof_on && blockIdx.x == 0 && threadIdx.x < 8) atomicAdd(reinterpret_cast<unsigned long long*>(&g_epi_prof[threadIdx.x]), (unsigned long long)epi_prof_smem()[threadIdx.x]);
+#endif
   if (g.cluster > 1) cluster_sync_all();      // no CTA leaves while its partner may still multicast into it
   if (warp == 1) tmem_dealloc_dyn(tmem_base, (uint32_t)g.tmem_cols);
 }
@@ -374,7 +384,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------ host side
 
 inline bool pair_plan_with(int c, int k, int dil, int lin, int batch, int smem_budget, bool dual, bool cluster_ok,
-                           PairGeom* out) {
+                           bool alias_ok, PairGeom* out) {
   PairGeom g{};
   if (c % 16 != 0 || c > 256 || k < 1 || k > kMaxTaps || (k & 1) == 0) return false;
   g.c = c; g.k = k; g.dil = dil;
@@ -384,7 +394,7 @@ inline bool pair_plan_with(int c, int k, int dil, int lin, int batch, int smem_b
   if (g.rb != 32 && g.rb != 64 && g.rb != 128) return false;
   g.kc = c * 2 / g.rb;
   g.k16 = g.rb / 32;
-  g.cw = (!dual && c % 32 == 0) ? 32 : 16;
+  g.cw = (!dual && c % 32 == 0 && !(alias_ok && c >= 128)) ? 32 : 16;   // C >= 128: small tiles, the room goes to the weight ring
   g.dual = dual ? 1 : 0;
   g.tile_words = 32 * g.cw;
   int tb = 1;
@@ -411,17 +421,26 @@ inline bool pair_plan_with(int c, int k, int dil, int lin, int batch, int smem_b
     g.slab_bytes = g.a_rows * g.rb;
     g.t_rows = (g.mt + 2 * g.h2 + 7) & ~7;
     g.t_chunk_bytes = g.t_rows * g.rb;
-    const int fixed = g.kc * g.t_chunk_bytes + bar_bytes;
+    // C >= 128 is bound by how many weight bytes are in flight (ring depth x stage size / L2 latency):
+    // give the ring the room by letting the A-slab ring share the T-slab region.
+    g.alias_at = (alias_ok && c >= 128) ? 1 : 0;
+    const int t_bytes = g.kc * g.t_chunk_bytes;
     int sa = g.kc + 1 < 4 ? g.kc + 1 : 4, sb = 4;
-    while (sa > 2 && sa * g.slab_bytes + sb * g.bstage_bytes + fixed > smem_budget) --sa;
-    while (sb > 2 && sa * g.slab_bytes + sb * g.bstage_bytes + fixed > smem_budget) --sb;
-    if (sa * g.slab_bytes + sb * g.bstage_bytes + fixed > smem_budget) continue;
-    while (sb < kTcMaxStagesB && sb < 2 * g.n_tstages * g.kc && (sb + 1) * g.bstage_bytes <= 64 * 1024 &&
-           sa * g.slab_bytes + (sb + 1) * g.bstage_bytes + fixed <= smem_budget)
+    auto region = [&](int sa_) {
+      const int a_bytes = sa_ * g.slab_bytes;
+      return g.alias_at ? (a_bytes > t_bytes ? a_bytes : t_bytes) : a_bytes + t_bytes;
+    };
+    if (g.alias_at) while (sa > 2 && sa * g.slab_bytes > t_bytes) --sa;      // aliased slabs are free up to the T size
+    while (sa > 2 && region(sa) + sb * g.bstage_bytes + bar_bytes > smem_budget) --sa;
+    while (sb > 2 && region(sa) + sb * g.bstage_bytes + bar_bytes > smem_budget) --sb;
+    if (region(sa) + sb * g.bstage_bytes + bar_bytes > smem_budget) continue;
+    while (sb < kTcMaxStagesB && sb < 2 * g.n_tstages * g.kc && (sb + 1) * g.bstage_bytes <= 160 * 1024 &&
+           region(sa) + (sb + 1) * g.bstage_bytes + bar_bytes <= smem_budget)
       ++sb;
     g.sa = sa;
     g.sb = sb;
-    g.smem_bytes = sa * g.slab_bytes + sb * g.bstage_bytes + fixed;
+    g.region_bytes = (region(sa) + 1023) & ~1023;
+    g.smem_bytes = g.region_bytes + sb * g.bstage_bytes + bar_bytes;
     int cols = 32;
     while (cols < 2 * msub * c) cols <<= 1;
     if (cols > (dual ? 256 : 512)) continue;
@@ -441,9 +460,9 @@ inline bool pair_plan_with(int c, int k, int dil, int lin, int batch, int smem_b
 // MMA / phase 1 overlaps the other's load/store-heavy phase 2.  (Measured: with half the CTAs every
 // stage takes ~1.7x longer, i.e. the kernels are per-SM latency bound, not chip-memory bound.)
 inline bool pair_plan(int c, int k, int dil, int lin, int batch, int smem_budget, bool allow_dual, bool allow_cluster,
-                      PairGeom* out) {
-  if (allow_dual && pair_plan_with(c, k, dil, lin, batch, 110 * 1024, true, false, out)) return true;
-  return pair_plan_with(c, k, dil, lin, batch, smem_budget, false, allow_cluster, out);
+                      bool allow_alias, PairGeom* out) {
+  if (allow_dual && pair_plan_with(c, k, dil, lin, batch, 110 * 1024, true, false, allow_alias, out)) return true;
+  return pair_plan_with(c, k, dil, lin, batch, smem_budget, false, allow_cluster, allow_alias, out);
 }
 
 template <int MODE, bool DUAL>

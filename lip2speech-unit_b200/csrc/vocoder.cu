@@ -34,6 +34,7 @@ struct Knobs {
   long long trace_launch = -1;     // index of the fused-step launch of a forward that gets trace_ptr
   long long cluster = 0;           // fused steps with C >= 128: CTA pairs share weight loads (TMA multicast); measured
                                    // neutral on B200 (the weight ring depth, not L2 read volume, bounds those layers)
+  long long alias_at = 1;          // fused steps with C >= 128: A-slab ring shares the T-slab shared memory
   long long fuse_pairs = 1;        // bf16 mode: one kernel per ResBlock (c1, c2) step
   long long plan_report = 0;       // l2s_debug_conv: write the chosen plan + occupancy into the err buffer
   long long trace_ptr = 0;         // device pointer for the kernel trace of l2s_debug_conv (0: off)
@@ -367,7 +368,7 @@ int run_pair(l2s_vocoder* v, ConvLayer& c1, ConvLayer& c2, cudaStream_t st, int 
   if (c1.cin != c1.cout || c2.cin != c2.cout || c1.cin != c2.cin || c1.cin_pad != c1.cin || c1.k != c2.k || c2.dil != 1)
     return L2S_ERR_UNSUPPORTED;
   PairGeom g;
-  if (!pair_plan(c1.cin, c1.k, c1.dil, lin, batch, 220 * 1024, g_knobs.dual != 0, g_knobs.cluster != 0, &g)) return L2S_ERR_UNSUPPORTED;
+  if (!pair_plan(c1.cin, c1.k, c1.dil, lin, batch, 220 * 1024, g_knobs.dual != 0, g_knobs.cluster != 0, g_knobs.alias_at != 0, &g)) return L2S_ERR_UNSUPPORTED;
   // with CTA-pair multicast each CTA fetches half of the output-channel rows of a weight stage
   if (!ensure_w_map(c1, g.rb, g.c / g.cluster, g.tb) || !ensure_w_map(c2, g.rb, g.c / g.cluster, g.tb))
     return fail(v, L2S_ERR_CUDA, "cuTensorMapEncodeTiled failed for the weights of " + c1.name);
@@ -560,7 +561,7 @@ int forward_impl(l2s_vocoder* v, void* stream, const int64_t* code, const void* 
         const ConvLayer& a2 = v->convs[v->rb_c2[i][j][m]];
         PairGeom pg;
         if (a1.cin != a1.cout || a1.cin_pad != a1.cin || a1.k != a2.k || a2.dil != 1 ||
-            !pair_plan(a1.cin, a1.k, a1.dil, (int)len, batch, 220 * 1024, g_knobs.dual != 0, g_knobs.cluster != 0, &pg))
+            !pair_plan(a1.cin, a1.k, a1.dil, (int)len, batch, 220 * 1024, g_knobs.dual != 0, g_knobs.cluster != 0, g_knobs.alias_at != 0, &pg))
           stage_fused = false;
       }
     for (int j = 0; j < c.n_rk; ++j) {
@@ -891,6 +892,16 @@ int l2s_debug_layer_time(l2s_vocoder* v, int32_t idx, float* ms, double* flops, 
   return L2S_OK;
 }
 
+// debug: read (and reset) the epilogue cycle accounting; enable with l2s_debug_set("epi_prof", 1)
+int l2s_debug_epi_prof(long long* out8) {
+  if (!out8) return L2S_ERR_INVALID;
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out8, g_epi_prof, 8 * sizeof(long long)) != cudaSuccess) return L2S_ERR_CUDA;
+  long long z[8] = {0};
+  cudaMemcpyToSymbol(g_epi_prof, z, sizeof z);
+  return L2S_OK;
+}
+
 int l2s_debug_set(const char* key, int64_t value) {
   if (!key) return L2S_ERR_INVALID;
   const std::string k(key);
@@ -902,6 +913,8 @@ int l2s_debug_set(const char* key, int64_t value) {
   else if (k == "dual") g_knobs.dual = value;
   else if (k == "fuse_pairs") g_knobs.fuse_pairs = value;
   else if (k == "cluster") g_knobs.cluster = value;
+  else if (k == "alias_at") g_knobs.alias_at = value;
+  else if (k == "epi_prof") { int on = (int)value; cudaMemcpyToSymbol(g_epi_prof_on, &on, sizeof on); }
   else if (k == "trace_launch") g_knobs.trace_launch = value;
   else if (k == "plan_report") g_knobs.plan_report = value;
   else if (k == "trace_ptr") g_knobs.trace_ptr = value;

@@ -238,7 +238,7 @@ def test_fused_resblock_steps_equal_unfused(pkg, weights, frames):
     assert torch.equal(a, b), float((a - b).abs().max())
 
 
-@pytest.mark.parametrize("knob", ["dual", "cluster"])
+@pytest.mark.parametrize("knob", ["dual", "cluster", "alias_at"])
 def test_fused_kernel_variants_agree(pkg, weights, knob):
     """Two-CTAs-per-SM plans (dual) and CTA-pair weight multicast (cluster) change scheduling only:
     the waveform must not change by a bit."""
@@ -254,6 +254,7 @@ def test_fused_kernel_variants_agree(pkg, weights, knob):
     finally:
         lib.l2s_debug_set(b"dual", 1)
         lib.l2s_debug_set(b"cluster", 0)
+        lib.l2s_debug_set(b"alias_at", 1)
     assert torch.isfinite(outs[0]).all()
     assert torch.equal(outs[0], outs[1]), float((outs[0] - outs[1]).abs().max())
 
