@@ -60,7 +60,8 @@ struct CondParams {
   int batch, units, frames, e, num_mels, num_embeddings, cin_pad, has_spk;
 };
 
-constexpr int kCondFrames = 8;   // frames per block (even start)
+constexpr int kCondFrames = 8;   // frames per block (even start).  Measured on cfg2: 8 -> 82 us, 16 -> 114 us, 32 -> 158 us:
+                                 // the kernel is parallelism bound (few warps per SM), not bound by re-reading the weights from L2.
 constexpr int kCondE = 128;      // embedding_dim this kernel is specialised for
 
 template <typename Ta>
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(kCondE) cond_multi_kernel(const CondParams p) 
   const float bias = p.wt_bias[c];
 #pragma unroll
   for (int f = 0; f < kCondFrames; ++f) acc[f] = bias;
+#pragma unroll 4
   for (int ci = 0; ci < kCondE; ++ci) {
     const float w0 = p.wt[(0 * kCondE + ci) * kCondE + c];
     const float w1 = p.wt[(1 * kCondE + ci) * kCondE + c];
@@ -119,6 +121,7 @@ __global__ void __launch_bounds__(kCondE) cond_multi_kernel(const CondParams p) 
   const float fb = p.fc_bias[c];
 #pragma unroll
   for (int f = 0; f < kCondFrames; ++f) acc[f] = fb;
+#pragma unroll 8
   for (int k = 0; k < kCondE; ++k) {
     const float w = p.fc_t[k * kCondE + c];
 #pragma unroll
@@ -202,25 +205,31 @@ struct PostParams {
 };
 
 constexpr int kPostTile = 256;
+constexpr int kPostMaxC = 64;
+
+// pitch (floats) of a staged row: a multiple of 4 (float4 reads) that spreads 8 consecutive rows over all banks
+__host__ __device__ inline int post_pitch(int c) { return c + 4; }
 
 __global__ void __launch_bounds__(kPostTile) post_kernel(const PostParams p) {
-  extern __shared__ float s_x[];                 // [(kPostTile + 6)][C + 1]
-  __shared__ float s_w[7 * 64];
+  extern __shared__ __align__(16) float s_x[];   // [(kPostTile + 6)][post_pitch(C)]
+  __shared__ __align__(16) float s_w[7 * kPostMaxC];
   const int b = blockIdx.y;
   const int l0 = blockIdx.x * kPostTile;
-  const int c = p.c, pitch = c + 1;
+  const int c = p.c, pitch = post_pitch(c), c4 = c >> 2;
   for (int i = threadIdx.x; i < 7 * c; i += kPostTile) s_w[i] = p.w[i];
-  const float* in = p.in + (long long)b * p.len * c;
-  const int n = (kPostTile + 6) * c;
-  for (int i = threadIdx.x; i < n; i += kPostTile) {
-    const int r = i / c, ch = i - r * c;
+  const float4* in4 = reinterpret_cast<const float4*>(p.in + (long long)b * p.len * c);
+  const int n4 = (kPostTile + 6) * c4;
+  for (int i = threadIdx.x; i < n4; i += kPostTile) {
+    const int r = i / c4, q = i - r * c4;
     const int l = l0 - 3 + r;
-    float v = 0.f;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (l >= 0 && l < p.len) {
-      v = in[(long long)l * c + ch];
-      v = v > 0.f ? v : v * 0.01f;               // F.leaky_relu default slope, models.py:110
+      v = in4[(long long)l * c4 + q];
+      // F.leaky_relu default slope 0.01, models.py:110
+      v.x = v.x > 0.f ? v.x : v.x * 0.01f; v.y = v.y > 0.f ? v.y : v.y * 0.01f;
+      v.z = v.z > 0.f ? v.z : v.z * 0.01f; v.w = v.w > 0.f ? v.w : v.w * 0.01f;
     }
-    s_x[r * pitch + ch] = v;
+    *reinterpret_cast<float4*>(s_x + r * pitch + q * 4) = v;
   }
   __syncthreads();
   const int l = l0 + threadIdx.x;
@@ -228,9 +237,12 @@ __global__ void __launch_bounds__(kPostTile) post_kernel(const PostParams p) {
   float acc = p.bias;
 #pragma unroll
   for (int j = 0; j < 7; ++j) {
-    const float* xr = s_x + (threadIdx.x + j) * pitch;
-    const float* wr = s_w + j * c;
-    for (int ch = 0; ch < c; ++ch) acc = fmaf(xr[ch], wr[ch], acc);
+    const float4* xr = reinterpret_cast<const float4*>(s_x + (threadIdx.x + j) * pitch);
+    const float4* wr = reinterpret_cast<const float4*>(s_w + j * c);
+    for (int q = 0; q < c4; ++q) {
+      const float4 x = xr[q], w = wr[q];
+      acc = fmaf(x.x, w.x, acc); acc = fmaf(x.y, w.y, acc); acc = fmaf(x.z, w.z, acc); acc = fmaf(x.w, w.w, acc);
+    }
   }
   const float y = tanhf(acc);
   const long long o = (long long)b * p.len + l;

@@ -617,7 +617,7 @@ int forward_impl(l2s_vocoder* v, void* stream, const int64_t* code, const void* 
   pp.c = v->stage_ch.back();
   dim3 grid((unsigned)((len + kPostTile - 1) / kPostTile), batch);
   timed_begin(v, st, "conv_post", 2.0 * pp.c * 7 * (double)batch * len);
-  post_kernel<<<grid, kPostTile, (kPostTile + 6) * (pp.c + 1) * sizeof(float), st>>>(pp);
+  post_kernel<<<grid, kPostTile, (kPostTile + 6) * post_pitch(pp.c) * sizeof(float), st>>>(pp);
   timed_end(v, st);
   if ((e = cudaGetLastError()) != cudaSuccess) return fail(v, L2S_ERR_CUDA, std::string("post: ") + cudaGetErrorString(e));
   return L2S_OK;
