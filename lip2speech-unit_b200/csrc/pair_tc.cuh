@@ -384,7 +384,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------ host side
 
 inline bool pair_plan_with(int c, int k, int dil, int lin, int batch, int smem_budget, bool dual, bool cluster_ok,
-                           bool alias_ok, PairGeom* out) {
+                           bool alias_ok, int cw_pref, int min_sb, PairGeom* out) {
   PairGeom g{};
   if (c % 16 != 0 || c > 256 || k < 1 || k > kMaxTaps || (k & 1) == 0) return false;
   g.c = c; g.k = k; g.dil = dil;
@@ -394,7 +394,7 @@ inline bool pair_plan_with(int c, int k, int dil, int lin, int batch, int smem_b
   if (g.rb != 32 && g.rb != 64 && g.rb != 128) return false;
   g.kc = c * 2 / g.rb;
   g.k16 = g.rb / 32;
-  g.cw = (!dual && c % 32 == 0 && !(alias_ok && c >= 128)) ? 32 : 16;   // C >= 128: small tiles, the room goes to the weight ring
+  g.cw = (!dual && c % 32 == 0 && cw_pref == 32) ? 32 : 16;
   g.dual = dual ? 1 : 0;
   g.tile_words = 32 * g.cw;
   int tb = 1;
@@ -437,6 +437,7 @@ inline bool pair_plan_with(int c, int k, int dil, int lin, int batch, int smem_b
     while (sb < kTcMaxStagesB && sb < 2 * g.n_tstages * g.kc && (sb + 1) * g.bstage_bytes <= 160 * 1024 &&
            region(sa) + (sb + 1) * g.bstage_bytes + bar_bytes <= smem_budget)
       ++sb;
+    if (sb < min_sb) continue;
     g.sa = sa;
     g.sb = sb;
     g.region_bytes = (region(sa) + 1023) & ~1023;
@@ -461,8 +462,11 @@ inline bool pair_plan_with(int c, int k, int dil, int lin, int batch, int smem_b
 // stage takes ~1.7x longer, i.e. the kernels are per-SM latency bound, not chip-memory bound.)
 inline bool pair_plan(int c, int k, int dil, int lin, int batch, int smem_budget, bool allow_dual, bool allow_cluster,
                       bool allow_alias, PairGeom* out) {
-  if (allow_dual && pair_plan_with(c, k, dil, lin, batch, 110 * 1024, true, false, allow_alias, out)) return true;
-  return pair_plan_with(c, k, dil, lin, batch, smem_budget, false, allow_cluster, allow_alias, out);
+  if (allow_dual && pair_plan_with(c, k, dil, lin, batch, 110 * 1024, true, false, allow_alias, 16, 2, out)) return true;
+  // single CTA per SM: 32-column epilogue chunks (full 128-byte lines) as long as >= 3 weight stages still fit,
+  // else 16-column chunks (smaller transpose tiles) so the room goes to the weight ring
+  if (pair_plan_with(c, k, dil, lin, batch, smem_budget, false, allow_cluster, allow_alias, 32, c >= 128 ? 3 : 2, out)) return true;
+  return pair_plan_with(c, k, dil, lin, batch, smem_budget, false, allow_cluster, allow_alias, 16, 2, out);
 }
 
 template <int MODE, bool DUAL>
