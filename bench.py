@@ -147,7 +147,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--knob", action="append", default=[], help="debug knob k=v passed to l2s_debug_set")
     ap.add_argument("--layers", action="store_true", help="also print a per-launch time table to stderr")
@@ -290,7 +290,8 @@ def main():
         if args.layers:
             for name, t, fl in rows:
                 sys.stderr.write(f"{name:28s} {t * 1e3:9.1f} us  {fl / max(t, 1e-9) / 1e9:8.1f} TFLOP/s\n")
-        kernel = "conv_tc_kernel (tcgen05 tap-offset conv)" if args.precision == "bf16" else "conv_simt_kernel"
+        kernel = {"bf16": "pair_tc_kernel (fused ResBlock step: two tcgen05 tap-offset convs) + conv_tc_kernel (conv_pre, ups)",
+                  "tf32": "conv_tc_kernel (tcgen05 kind::tf32 tap-offset conv)", "fp32": "conv_simt_kernel"}[args.precision]
         line = {
             "metric": "audio-sec generated/sec (16 kHz)",
             "value": world * audio_per_step / step_s,

@@ -45,7 +45,8 @@ enum l2s_status {
 
 enum l2s_precision {
   L2S_PREC_FP32 = 0,  /* fp32 storage and CUDA-core FFMA: the on-device reference mode            */
-  L2S_PREC_BF16 = 1   /* bf16 operands on tcgen05 tensor cores, fp32 accumulate + fp32 residuals  */
+  L2S_PREC_BF16 = 1,  /* bf16 operands on tcgen05 tensor cores, fp32 accumulate + fp32 residuals  */
+  L2S_PREC_TF32 = 2   /* fp32 storage everywhere, tf32 (10-bit mantissa) products on tcgen05       */
 };
 
 enum l2s_variant {

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libl2s_vocoder.so")
 L2S_MAX_UPS, L2S_MAX_RK, L2S_MAX_DIL = 8, 4, 4
 
 OK, ERR_INVALID, ERR_SHAPE, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_INDEX = range(8)
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_TF32 = 0, 1, 2
 VARIANT_MULTI_INPUT, VARIANT_UNIT_ONLY = 0, 1
 F32, F16, BF16 = 0, 1, 2
 

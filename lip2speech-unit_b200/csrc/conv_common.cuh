@@ -38,6 +38,7 @@ struct ConvParams {
   int tap_off[kMaxTaps];
   long long out_shift, out_valid;
   float div, slope;
+  int act_f32;           // tcgen05 kernel only: 1 = operands / activated output are fp32 (tf32 mode), 0 = bf16
 };
 
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }

@@ -33,6 +33,7 @@ constexpr int kTcMaxStagesA = 8;
 constexpr int kTcMaxStagesB = 8;
 
 struct TcGeom {
+  int esz;           // operand element size: 2 (bf16) or 4 (tf32 mode: fp32 words)
   int rb;            // bytes per shared-memory operand row: 32 / 64 / 128 (= swizzle span)
   int kc;            // K chunks per tap (cin_pad * 2 / rb)
   int k16;           // MMAs (K = 16) per chunk (rb / 32)
@@ -88,6 +89,12 @@ __device__ __forceinline__ long long* epi_prof_smem() {
 #else
 #define L2S_PROF_ON false
 #endif
+
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
 
 constexpr int kEpiTileWords = 32 * 32;   // warp-private transpose tile: 32 rows x CW fp32, XOR-swizzled float4 slots
 
@@ -239,9 +246,17 @@ __device__ __forceinline__ void epi_finish(const ConvParams& p, const EpiChunk& 
         *reinterpret_cast<float4*>(raw_p + (long long)i * step) = make_float4(v0, v1, v2, v3);
       if constexpr ((MODE & kEpiAct) != 0) {
         uint2 pk;   // leaky_relu for 0 < slope < 1 is max(v, v * slope)
-        pk.x = lrelu_bf16x2(v0, v1, slope2);
-        pk.y = lrelu_bf16x2(v2, v3, slope2);
-        *reinterpret_cast<uint2*>(act_p + (long long)i * step) = pk;
+        if (p.act_f32) {   // tf32 mode: the activated copy stays fp32
+          // rounded to nearest tf32 here: the tensor core would otherwise TRUNCATE the low 13 mantissa bits
+          const float sl = p.slope;
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out_act) + c.e0 + (long long)i * step) =
+              make_float4(round_tf32(fmaxf(v0, v0 * sl)), round_tf32(fmaxf(v1, v1 * sl)), round_tf32(fmaxf(v2, v2 * sl)),
+                          round_tf32(fmaxf(v3, v3 * sl)));
+        } else {
+          pk.x = lrelu_bf16x2(v0, v1, slope2);
+          pk.y = lrelu_bf16x2(v2, v3, slope2);
+          *reinterpret_cast<uint2*>(act_p + (long long)i * step) = pk;
+        }
       }
     }
   }
@@ -320,12 +335,15 @@ __device__ __forceinline__ void epilogue_item_rows(const ConvParams& p, float* t
 // K16 consecutive K = 16 slices of one (tap, 64-channel chunk): descriptors advance by 32 bytes.
 template <int K16>
 __device__ __forceinline__ void issue_chunk(bool leader, uint32_t d_addr, uint32_t desc_hi, uint32_t a_lo, uint32_t b_lo,
-                                            uint32_t idesc, uint32_t first) {
+                                            uint32_t idesc, uint32_t first, bool tf32 = false) {
 #pragma unroll
   for (int k = 0; k < K16; ++k) {
     const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2u * k);
     const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2u * k);
-    if (leader) umma_bf16(d_addr, da, db, idesc, (first | (uint32_t)k) != 0u ? 1u : 0u);
+    if (leader) {
+      if (tf32) umma_tf32(d_addr, da, db, idesc, (first | (uint32_t)k) != 0u ? 1u : 0u);
+      else umma_bf16(d_addr, da, db, idesc, (first | (uint32_t)k) != 0u ? 1u : 0u);
+    }
   }
 }
 
@@ -399,7 +417,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int ni = rem - mi * g.n_ntiles;
       const int row0 = mi * 128 * g.msub + g.min_off;
       for (int kc = 0; kc < g.kc; ++kc) {
-        const int ch0 = kc * (g.rb >> 1);
+        const int ch0 = kc * (g.rb / g.esz);
         if (!g.per_tap) {
           if (kc == 0) L2S_TRACE(0, it_no, 0);
           mbar_wait(&a_empty[ia], pa ^ 1u);
@@ -480,13 +498,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t d_addr = d_base;
             if (g.k16 == 4) {
               for (int sub = 0; sub < g.msub; ++sub, a_sub += sub_step, d_addr += (uint32_t)g.nt)
-                issue_chunk<4>(leader, d_addr, desc_hi, a_sub, b_lo, g.idesc, first);
+                issue_chunk<4>(leader, d_addr, desc_hi, a_sub, b_lo, g.idesc, first, g.esz == 4);
             } else if (g.k16 == 2) {
               for (int sub = 0; sub < g.msub; ++sub, a_sub += sub_step, d_addr += (uint32_t)g.nt)
-                issue_chunk<2>(leader, d_addr, desc_hi, a_sub, b_lo, g.idesc, first);
+                issue_chunk<2>(leader, d_addr, desc_hi, a_sub, b_lo, g.idesc, first, g.esz == 4);
             } else {
               for (int sub = 0; sub < g.msub; ++sub, a_sub += sub_step, d_addr += (uint32_t)g.nt)
-                issue_chunk<1>(leader, d_addr, desc_hi, a_sub, b_lo, g.idesc, first);
+                issue_chunk<1>(leader, d_addr, desc_hi, a_sub, b_lo, g.idesc, first, g.esz == 4);
             }
           }
           if (leader) umma_commit(&b_empty[ib]);   // W stage free once these MMAs retire
@@ -566,23 +584,27 @@ inline PFN_tmapEncodeTiled tmap_encoder() {
   return fn;
 }
 
-// bf16 tensor [d2][d1][d0] (d0 contiguous), box [b2=1 or tb][b1][b0], swizzle span = b0 * 2 bytes.
-inline bool make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0,
-                              uint32_t b1, uint32_t b2) {
+// tensor [d2][d1][d0] (d0 contiguous) of bf16 (esz 2) or fp32 (esz 4), box [b2][b1][b0], swizzle span = b0 * esz bytes.
+inline bool make_tmap_3d(CUtensorMap* out, const void* base, int esz, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0,
+                         uint32_t b1, uint32_t b2) {
   PFN_tmapEncodeTiled enc = tmap_encoder();
   if (!enc) return false;
   const cuuint64_t dims[3] = {d0, d1, d2};
-  const cuuint64_t strides[2] = {d0 * 2ull, d0 * d1 * 2ull};
+  const cuuint64_t strides[2] = {d0 * (uint64_t)esz, d0 * d1 * (uint64_t)esz};
   const cuuint32_t box[3] = {b0, b1, b2};
   const cuuint32_t estr[3] = {1, 1, 1};
-  const uint32_t rb = b0 * 2;
+  const uint32_t rb = b0 * (uint32_t)esz;
   const CUtensorMapSwizzle sw = rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                 : rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                            : CU_TENSOR_MAP_SWIZZLE_32B;
-  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+  const CUresult r = enc(out, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
+}
+inline bool make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0,
+                              uint32_t b1, uint32_t b2) {
+  return make_tmap_3d(out, base, 2, d0, d1, d2, b0, b1, b2);
 }
 
 struct TcTune {
@@ -601,10 +623,12 @@ inline bool tc_plan_with(const ConvParams& c, int batch, const TcTune& tune, int
                          TcGeom* out) {
   TcGeom g{};
   if (c.cin_pad % 16 != 0 || c.ntot % 16 != 0 || c.ntaps < 1 || c.ntaps > kMaxTaps) return false;
-  g.rb = (c.cin_pad >= 64 ? 64 : c.cin_pad) * 2;
+  g.esz = c.act_f32 ? 4 : 2;
+  const int row_elems = 128 / g.esz;                      // channels per 128-byte operand row
+  g.rb = (c.cin_pad >= row_elems ? row_elems : c.cin_pad) * g.esz;
   if (g.rb != 32 && g.rb != 64 && g.rb != 128) return false;
-  if ((c.cin_pad * 2) % g.rb != 0) return false;
-  g.kc = c.cin_pad * 2 / g.rb;
+  if ((c.cin_pad * g.esz) % g.rb != 0) return false;
+  g.kc = c.cin_pad * g.esz / g.rb;
   g.k16 = g.rb / 32;
   g.nt = c.ntot <= 256 ? c.ntot : 256;
   while (c.ntot % g.nt != 0) g.nt -= 16;
@@ -655,7 +679,7 @@ inline bool tc_plan_with(const ConvParams& c, int batch, const TcTune& tune, int
   if (cols > 512) return false;
   g.tmem_cols = cols;
   g.total_items = batch * g.m_items * g.n_ntiles;
-  g.idesc = umma_idesc_bf16(128u, (uint32_t)g.nt);
+  g.idesc = g.esz == 4 ? umma_idesc_tf32(128u, (uint32_t)g.nt) : umma_idesc_bf16(128u, (uint32_t)g.nt);
   g.cw = g.nt % 32 == 0 ? 32 : 16;
   g.ctas_per_sm = 1;
   *out = g;
@@ -666,7 +690,7 @@ inline bool tc_plan_with(const ConvParams& c, int batch, const TcTune& tune, int
 // registers) hide the epilogue's latency chains on the layers where they fit (C <= 64);
 // everything else gets the whole SM.
 inline bool tc_plan(const ConvParams& c, int batch, const TcTune& tune, TcGeom* out) {
-  if (tune.dual) {
+  if (tune.dual && !c.act_f32) {
     TcTune t = tune;
     for (; t.max_msub >= 1; t.max_msub >>= 1) {   // shrink the item until two CTAs' shared memory fits
       if (tc_plan_with(c, batch, t, 128, 110 * 1024, out) && out->tmem_cols <= 256) {

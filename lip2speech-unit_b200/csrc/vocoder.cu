@@ -54,6 +54,15 @@ inline uint16_t f2bf(float f) {  // round to nearest even
   return (uint16_t)(u >> 16);
 }
 
+inline float f2tf32(float f) {  // round to nearest (ties away), 10-bit mantissa, like cvt.rna.tf32.f32
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return f;
+  u = (u + 0x1000u) & 0xffffe000u;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct ConvLayer {
@@ -110,6 +119,7 @@ int fail(l2s_vocoder* v, int code, const std::string& msg) {
 }
 
 bool is_bf16(const l2s_vocoder* v) { return v->cfg.precision == L2S_PREC_BF16; }
+bool is_tf32(const l2s_vocoder* v) { return v->cfg.precision == L2S_PREC_TF32; }
 size_t act_size(const l2s_vocoder* v) { return is_bf16(v) ? 2 : 4; }
 
 int hop_of(const l2s_config& c) {
@@ -147,7 +157,8 @@ int build_layers(l2s_vocoder* v) {
   const l2s_config& c = v->cfg;
   if (c.n_ups < 1 || c.n_ups > L2S_MAX_UPS || c.n_rk < 1 || c.n_rk > L2S_MAX_RK || c.n_dil < 1 || c.n_dil > L2S_MAX_DIL)
     return fail(v, L2S_ERR_INVALID, "bad layer counts");
-  if (c.precision != L2S_PREC_FP32 && c.precision != L2S_PREC_BF16) return fail(v, L2S_ERR_INVALID, "bad precision");
+  if (c.precision != L2S_PREC_FP32 && c.precision != L2S_PREC_BF16 && c.precision != L2S_PREC_TF32)
+    return fail(v, L2S_ERR_INVALID, "bad precision");
   if (c.embedding_dim != kCondE) return fail(v, L2S_ERR_UNSUPPORTED, "embedding_dim must be 128");
   if (c.num_embeddings < 1) return fail(v, L2S_ERR_INVALID, "num_embeddings");
   const int E = c.embedding_dim;
@@ -321,7 +332,8 @@ int run_conv(l2s_vocoder* v, ConvLayer& L, cudaStream_t st, int batch, int lin, 
   p.slope = slope;
   cudaError_t e;
   timed_begin(v, st, L.name, 2.0 * L.cin * L.cout * L.k * (double)batch * lin);
-  if (!is_bf16(v)) {
+  p.act_f32 = is_tf32(v) ? 1 : 0;
+  if (v->cfg.precision == L2S_PREC_FP32 || (is_tf32(v) && g_knobs.force_simt)) {
     e = launch_conv_simt<float>(p, st);
   } else if (g_knobs.force_simt) {
     e = launch_conv_simt<__nv_bfloat16>(p, st);
@@ -330,16 +342,16 @@ int run_conv(l2s_vocoder* v, ConvLayer& L, cudaStream_t st, int batch, int lin, 
     TcGeom g;
     if (!tc_plan(p, batch, tune, &g)) return fail(v, L2S_ERR_UNSUPPORTED, "no tcgen05 plan for " + L.name);
     if (!L.has_tmW || L.tm_nt != g.nt || L.tm_tb != g.tb) {
-      if (!make_tmap_bf16_3d(&L.tmW, L.w_dev, (uint64_t)L.cin_pad, (uint64_t)L.ntot, (uint64_t)L.ntaps, (uint32_t)(g.rb / 2),
-                             (uint32_t)g.nt, (uint32_t)g.tb))
+      if (!make_tmap_3d(&L.tmW, L.w_dev, g.esz, (uint64_t)L.cin_pad, (uint64_t)L.ntot, (uint64_t)L.ntaps,
+                        (uint32_t)(g.rb / g.esz), (uint32_t)g.nt, (uint32_t)g.tb))
         return fail(v, L2S_ERR_CUDA, "cuTensorMapEncodeTiled failed for the weights of " + L.name);
       L.has_tmW = true;
       L.tm_nt = g.nt;
       L.tm_tb = g.tb;
     }
     CUtensorMap tmA;
-    if (!make_tmap_bf16_3d(&tmA, in, (uint64_t)L.cin_pad, (uint64_t)lin, (uint64_t)batch, (uint32_t)(g.rb / 2),
-                           (uint32_t)g.box_rows, 1u))
+    if (!make_tmap_3d(&tmA, in, g.esz, (uint64_t)L.cin_pad, (uint64_t)lin, (uint64_t)batch, (uint32_t)(g.rb / g.esz),
+                      (uint32_t)g.box_rows, 1u))
       return fail(v, L2S_ERR_CUDA, "cuTensorMapEncodeTiled failed for the input of " + L.name);
     e = launch_conv_tc(p, g, tmA, L.tmW, tune.max_ctas, st);
   }
@@ -701,6 +713,8 @@ int l2s_finalize(l2s_vocoder* v, int device) {
       for (size_t i = 0; i < pw.size(); ++i) hw[i] = f2bf(pw[i]);
       L.w_dev = dev_upload<uint16_t>(v, hw.data(), hw.size(), &e);
     } else {
+      if (is_tf32(v))
+        for (float& x : pw) x = f2tf32(x);   // the tensor core would truncate; round to nearest instead
       L.w_dev = dev_upload<float>(v, pw.data(), pw.size(), &e);
     }
     if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, std::string("upload ") + L.name + ": " + cudaGetErrorString(e));
@@ -847,7 +861,7 @@ int l2s_debug_conv(const l2s_conv_desc* d, int32_t impl, int32_t device, void* s
   if (impl == 0) {
     e = d->act_bf16 ? launch_conv_simt<__nv_bfloat16>(p, st) : launch_conv_simt<float>(p, st);
   } else {
-    if (!d->act_bf16) { say("the tcgen05 kernel takes bf16 operands"); return L2S_ERR_UNSUPPORTED; }
+    p.act_f32 = d->act_bf16 ? 0 : 1;   // fp32 operands run as kind::tf32
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     TcTune tune = current_tune(nullptr);
@@ -857,10 +871,10 @@ int l2s_debug_conv(const l2s_conv_desc* d, int32_t impl, int32_t device, void* s
     TcGeom g;
     if (!tc_plan(p, d->batch, tune, &g)) { say("no tcgen05 plan"); return L2S_ERR_UNSUPPORTED; }
     CUtensorMap tmA, tmW;
-    if (!make_tmap_bf16_3d(&tmW, d->w, (uint64_t)d->cin_pad, (uint64_t)d->ntot, (uint64_t)d->ntaps, (uint32_t)(g.rb / 2),
-                           (uint32_t)g.nt, (uint32_t)g.tb) ||
-        !make_tmap_bf16_3d(&tmA, d->in, (uint64_t)d->cin_pad, (uint64_t)d->lin, (uint64_t)d->batch, (uint32_t)(g.rb / 2),
-                           (uint32_t)g.box_rows, 1u)) {
+    if (!make_tmap_3d(&tmW, d->w, g.esz, (uint64_t)d->cin_pad, (uint64_t)d->ntot, (uint64_t)d->ntaps,
+                      (uint32_t)(g.rb / g.esz), (uint32_t)g.nt, (uint32_t)g.tb) ||
+        !make_tmap_3d(&tmA, d->in, g.esz, (uint64_t)d->cin_pad, (uint64_t)d->lin, (uint64_t)d->batch,
+                      (uint32_t)(g.rb / g.esz), (uint32_t)g.box_rows, 1u)) {
       say("cuTensorMapEncodeTiled failed");
       return L2S_ERR_CUDA;
     }

@@ -121,7 +121,7 @@ class _Engine:
             pass
 
 
-_PRECISIONS = {"fp32": _cabi.PREC_FP32, "bf16": _cabi.PREC_BF16}
+_PRECISIONS = {"fp32": _cabi.PREC_FP32, "bf16": _cabi.PREC_BF16, "tf32": _cabi.PREC_TF32}
 
 
 class _GeneratorBase(nn.Module):

@@ -34,6 +34,15 @@ def test_simt_conv(pkg, shape, act_bf16):
     assert r["ok"], r
 
 
+def test_tcgen05_conv_tf32(pkg):
+    """fp32 operands through the same tcgen05 kernel as kind::tf32 (10-bit mantissa products)."""
+    for shape in (SHAPES[0], SHAPES[3], SHAPES[4], SHAPES[7]):
+        r = run_case(pkg, impl=1, act_bf16=False, **shape)
+        # operands are truncated to tf32 inside the tensor core: ~2^-10 relative per product
+        assert r["max_err_raw"] <= 2e-2 * max(1.0, r["ref_max"]), r
+        assert r["max_err_act"] <= 2e-2 * max(1.0, r["ref_max"]), r
+
+
 @pytest.fixture(scope="module")
 def tc_results():
     # own process: a faulting kernel would poison this process's CUDA context
