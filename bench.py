@@ -91,6 +91,17 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic():
+    """dram read+write bytes per launch of the dominant kernel, from the committed ncu metrics pass (or None)."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["traffic_bytes_per_launch_avg"]), d["source"]
+    except Exception:
+        return None, None
+
+
 def cpu_reference(seconds_budget=12.0):
     """The reference's CPU path (oracle port: the same ATen ops as the reference's
     torch modules, fp32, all host threads) on a bounded sample of the workload:
@@ -292,6 +303,7 @@ def main():
                 sys.stderr.write(f"{name:28s} {t * 1e3:9.1f} us  {fl / max(t, 1e-9) / 1e9:8.1f} TFLOP/s\n")
         kernel = {"bf16": "pair_tc_kernel (fused ResBlock step: two tcgen05 tap-offset convs) + conv_tc_kernel (conv_pre, ups)",
                   "tf32": "conv_tc_kernel (tcgen05 kind::tf32 tap-offset conv)", "fp32": "conv_simt_kernel"}[args.precision]
+        traffic, traffic_src = ncu_traffic() if args.precision == "bf16" else (None, None)
         line = {
             "metric": "audio-sec generated/sec (16 kHz)",
             "value": world * audio_per_step / step_s,
@@ -312,7 +324,8 @@ def main():
                        "l2": f"no flush: per-step activation working set {ws_bytes / 2**20:.0f} MiB > {L2_MB} MB L2"},
             "tensor_frac_whole_step": flops_per_step / step_s / 1e12 / pk["tflops"],
             "roofline": {"bound": "tensor", "kernel": kernel, "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["tflops"], "traffic": None, "peak_source": pk["src"],
+                         "frac": achieved / pk["tflops"], "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": pk["src"],
                          "launches": len(conv_rows), "sum_launch_ms": round(conv_ms, 4), "all_launch_ms": round(all_ms, 4),
                          "algorithmic_gflop_per_step": conv_flops / 1e9, "per_stage": stage_tbl},
             "e2e": {"value": world * audio_per_step / (ms_e2e / 1e3 / args.steps), "unit": "audio-s/s",
