@@ -13,7 +13,8 @@
  *
  * Conventions: plain C types only; every function returns an int status
  * (L2S_OK == 0) and never throws, exits or synchronises the device unless it
- * says so; all kernels are launched on the caller's stream; inputs are borrowed
+ * says so; all kernels are launched on the caller's stream (from the second forward of a shape on, the conv
+ * chain is replayed there as one CUDA graph that was captured on an internal stream); inputs are borrowed
  * for the duration of the call; the output and workspace buffers are owned by
  * the caller; repacked weights are owned by the handle.
  * There is no CPU fallback: without a CUDA device every compute call fails.
@@ -175,7 +176,7 @@ int l2s_debug_layer_time(l2s_vocoder* v, int32_t idx, float* ms, double* flops, 
 int l2s_debug_epi_prof(long long* out8);
 
 /* Override a tuning / descriptor knob (tests and probes only): force_simt,
- * stop_after_stage, stop_after_pre, per_tap, sa_min, dual, cluster, alias_at, fuse_pairs, trace_launch, plan_report, trace_ptr, max_msub, slab_cap, max_ctas,
+ * stop_after_stage, stop_after_pre, per_tap, sa_min, dual, cluster, alias_at, epi_tma, pdl, use_graph, fuse_pairs, trace_launch, span_ptr, plan_report, trace_ptr, max_msub, slab_cap, max_ctas,
  * embed_tap, layer_events. */
 int l2s_debug_set(const char* key, int64_t value);
 

@@ -28,6 +28,8 @@
 namespace l2s {
 
 constexpr int kTcThreads = 320;
+// host-side switch: launch the tcgen05 kernels with programmatic stream serialization (knob `pdl`)
+inline int g_tc_pdl = 0;   // measured neutral on B200 (secondary CTAs cannot start before primaries free their shared memory)
 constexpr int kTcEpiWarps = 8;
 constexpr int kTcMaxStagesA = 8;
 constexpr int kTcMaxStagesB = 8;
@@ -62,6 +64,7 @@ struct TcGeom {
 struct TcParams {
   ConvParams c;
   TcGeom g;
+  unsigned long long* span;   // debug: [0] min CTA start, [1] max CTA end (globaltimer), null in production
   long long* trace;   // debug: [3 roles][64 items][4] globaltimer stamps of CTA 0, then [512 CTAs][smid, t0, t1] (null in production)
 };
 
@@ -377,6 +380,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #ifdef L2S_EPI_PROF
   if (g_epi_prof_on && threadIdx.x < 8) epi_prof_smem()[threadIdx.x] = 0;
 #endif
+  if (P.span && threadIdx.x == 0) atomicMin(&P.span[0], (unsigned long long)gtime());
   if (P.trace && threadIdx.x == 0 && blockIdx.x < 512) {   // debug: which SM ran this CTA, and when
     uint32_t smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -397,6 +401,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: the prologue above may overlap the previous kernel's tail; its data is touched only after this wait
+  pdl_launch_dependents();
+  pdl_wait_prior_grid();
 
   const int items_per_b = g.m_items * g.n_ntiles;
   const int acc_cols = g.msub * g.nt;
@@ -562,6 +569,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #ifdef L2S_EPI_PROF
   if (g_epi_prof_on && blockIdx.x == 0 && threadIdx.x < 8) atomicAdd(reinterpret_cast<unsigned long long*>(&g_epi_prof[threadIdx.x]), (unsigned long long)epi_prof_smem()[threadIdx.x]);
 #endif
+  if (P.span && threadIdx.x == 0) atomicMax(&P.span[1], (unsigned long long)gtime());
   if (P.trace && threadIdx.x == 0 && blockIdx.x < 512) P.trace[768 + blockIdx.x * 3 + 2] = gtime();
   if (warp == 1) tmem_dealloc_dyn(tmem_base, (uint32_t)g.tmem_cols);
 }
@@ -717,16 +725,27 @@ inline cudaError_t launch_conv_tc_mode(const TcParams& P, const CUtensorMap& tmA
     if (e != cudaSuccess) return e;
     configured[dev] = true;
   }
-  conv_tc_kernel<MODE><<<grid, kTcThreads, P.g.smem_bytes, stream>>>(tmA, tmW, P);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = (size_t)P.g.smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_tc_pdl ? 1u : 0u;
+  return cudaLaunchKernelEx(&cfg, conv_tc_kernel<MODE>, tmA, tmW, P);
 }
 
 inline cudaError_t launch_conv_tc(const ConvParams& c, const TcGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmW,
-                                  int num_ctas, cudaStream_t stream, long long* trace = nullptr) {
+                                  int num_ctas, cudaStream_t stream, long long* trace = nullptr,
+                                  unsigned long long* span = nullptr) {
   TcParams P;
   P.c = c;
   P.g = g;
   P.trace = trace;
+  P.span = span;
   const int cap = num_ctas * (g.ctas_per_sm > 1 ? g.ctas_per_sm : 1);
   int grid = g.total_items < cap ? g.total_items : cap;
   if (grid < 1) grid = 1;

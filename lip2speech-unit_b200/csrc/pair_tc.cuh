@@ -45,7 +45,8 @@ struct PairGeom {
   int region_bytes;      // shared memory of the A ring + T slab (max of the two when aliased)
   int cluster;           // 1, or 2: CTA pairs fetch each weight stage from L2 once (TMA multicast)
   int dual;              // planned so that two CTAs share one SM (<= 110 KB smem, <= 256 TMEM columns, 80 registers)
-  int tile_words;        // fp32 words of one warp's transpose tile (32 rows x cw)
+  int tile_words;        // fp32 words of one warp's transpose tile (32 rows x cw), or of its TMA staging (epi_tma)
+  int epi_tma;           // 1: phase 2 streams the residual in and the results out with TMA through per-warp staging
   uint32_t idesc;
   int smem_bytes;
 };
@@ -54,6 +55,7 @@ struct PairParams {
   ConvParams c;          // epilogue of c2: bias = b2, res = x, acc_in, out_raw, out_act, div, slope; lin = mrows = L, ntot = C
   const float* bias1;
   PairGeom g;
+  unsigned long long* span;   // debug: [0] min CTA start, [1] max CTA end (globaltimer), null in production
   long long* trace;      // debug timestamps of CTA 0 (see conv_tc.cuh), null in production
 };
 
@@ -100,10 +102,139 @@ __device__ __forceinline__ void pair_phase1_chunk(const PairParams& P, uint8_t* 
   }
 }
 
-template <int MODE, bool DUAL>
+// ---------------------------------------------------------------------------------------------------
+// Asynchronous phase 2 (DUAL plans, modes residual + raw [+ act]).  Per warp and 16-column chunk:
+//   residual chunk  [32 rows x 64 B]  global -> staging   by TMA, one chunk ahead (mbarrier res_full[buf])
+//   each lane owns one ROW: TMEM row + bias + residual (LDS.128, swizzle-64B slots) -> written back in place,
+//   activated bf16 copy into a [32 x 32 B] buffer (swizzle-32B slots)
+//   fence.proxy.async, then ONE lane issues the TMA stores (raw fp32, act bf16) as a bulk group.
+// No transpose round trip, no LSU global traffic, rows >= r_out of the item are cut by a shorter "tail" box,
+// rows >= L by the tensor bounds.
+constexpr int kTmaStageBytes = 2 * 2048 + 1024;   // per warp: 2 residual/raw buffers + 1 act buffer
+
+// chunk i of this warp -> (accumulator s, 16-column block cc); cps = 16-column chunks per accumulator (1, 2 or 4)
+struct TmaWalk {
+  int cps_sh, n_valid, row_q, half;
+  __device__ __forceinline__ void at(int i, int& s, int& cc) const {
+    const int lin = half + 2 * i;
+    s = lin >> cps_sh;
+    cc = lin - (s << cps_sh);
+  }
+};
+
+__device__ __forceinline__ TmaWalk tma_walk(const PairGeom& g, int q0, int row_lim, int quad, int half) {
+  TmaWalk w;
+  const int cps = g.c >> 4;
+  w.cps_sh = cps == 4 ? 2 : (cps == 2 ? 1 : 0);
+  w.half = half;
+  w.row_q = q0 + quad * 32;
+  const int n_all = (g.msub * cps - half + 1) >> 1;          // my chunks: linear index half, half + 2, ...
+  w.n_valid = 0;                                             // chunks whose first row is inside the item (a prefix)
+  for (int i = 0; i < n_all; ++i) w.n_valid += (w.row_q + (((half + 2 * i) >> w.cps_sh) << 7)) < row_lim ? 1 : 0;
+  return w;
+}
+
+// Residual prefetch of an item, issued BEFORE phase 1: both staging buffers are filled while c1's epilogue and
+// c2's MMAs run, so phase 2 never waits for DRAM.  (With one chunk of look-ahead every warp ate a full loaded
+// DRAM latency per chunk: 16 warps x 2 KB in flight per SM = ~2.5 TB/s chip-wide, which is what ncu showed.)
+__device__ __forceinline__ void tma_prefetch_res(const TmaWalk& w, const CUtensorMap* tmRes, uint8_t* stage,
+                                                 uint64_t* res_full, int b, int lane) {
+  if (lane != 0 || w.n_valid == 0) return;
+  bulk_wait_read<0>();                                       // the previous item's stores have left the staging buffers
+  const int n = w.n_valid < 2 ? w.n_valid : 2;
+  for (int i = 0; i < n; ++i) {
+    int s, cc;
+    w.at(i, s, cc);
+    mbar_expect_tx(&res_full[i], 2048u);
+    tma_load_3d(stage + i * 2048, tmRes, &res_full[i], cc * 16, w.row_q + s * 128, b);
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void epilogue_item_tma(const ConvParams& p, const PairGeom& g, const TmaWalk& w,
+                                                  const CUtensorMap* tmRes, const CUtensorMap* tmRaw,
+                                                  const CUtensorMap* tmRawT, const CUtensorMap* tmAct,
+                                                  const CUtensorMap* tmActT, uint8_t* stage, uint64_t* res_full,
+                                                  uint32_t (&ph)[2], uint32_t t2, int b, int quad, int lane,
+                                                  uint64_t* bar, uint32_t parity, long long* tr = nullptr) {
+  // tr (debug, warp 2 of CTA 0): [0] enter, [1] D2 ready, then per chunk i (<2): [2+3i] tmem ld done, [3+3i] residual
+  // landed, [4+3i] stores issued
+  constexpr bool kAct = (MODE & kEpiAct) != 0;
+  if (tr && lane == 0) tr[0] = gtime();
+  uint8_t* resb0 = stage;
+  uint8_t* resb1 = stage + 2048;
+  uint4* actb = reinterpret_cast<uint4*>(stage + 4096);
+  mbar_wait(bar, parity);                                    // D2 complete
+  tc_fence_after();
+  if (tr && lane == 0) tr[1] = gtime();
+  const int sw64 = (lane >> 1) & 3, sw32 = (lane >> 2) & 1;
+  const __nv_bfloat162 slope2 = __float2bfloat162_rn(p.slope);
+  for (int i = 0; i < w.n_valid; ++i) {
+    int s, cc;
+    w.at(i, s, cc);
+    const int buf = i & 1;
+    float4 bias[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bias[j] = __ldg(reinterpret_cast<const float4*>(p.bias + cc * 16) + j);
+    uint32_t r[16];
+    tmem_ld16(t2 + (uint32_t)(s * g.c + cc * 16), r);
+    tmem_ld_wait();
+    if (tr && lane == 0 && i < 2) tr[2 + 3 * i] = gtime();
+    mbar_wait(&res_full[buf], ph[buf]);
+    ph[buf] ^= 1u;
+    if (tr && lane == 0 && i < 2) tr[3 + 3 * i] = gtime();
+    float4* rb4 = reinterpret_cast<float4*>(buf ? resb1 : resb0);
+    uint32_t pk[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int slot = lane * 4 + (j ^ sw64);
+      const float4 rs = rb4[slot];
+      float4 v;
+      v.x = __uint_as_float(r[4 * j + 0]) + bias[j].x + rs.x;
+      v.y = __uint_as_float(r[4 * j + 1]) + bias[j].y + rs.y;
+      v.z = __uint_as_float(r[4 * j + 2]) + bias[j].z + rs.z;
+      v.w = __uint_as_float(r[4 * j + 3]) + bias[j].w + rs.w;
+      rb4[slot] = v;                                         // raw result, in place
+      if constexpr (kAct) {
+        pk[2 * j] = lrelu_bf16x2(v.x, v.y, slope2);
+        pk[2 * j + 1] = lrelu_bf16x2(v.z, v.w, slope2);
+      }
+    }
+    // the act buffer is single: the previous chunk's act store must have finished READING it
+    if (i > 0) {
+      if (lane == 0) {
+        bulk_wait_read<0>();
+        if (i + 1 < w.n_valid && i + 1 >= 2) {               // geometries with more than two chunks per warp: one ahead
+          int s2, cc2;
+          w.at(i + 1, s2, cc2);
+          mbar_expect_tx(&res_full[(i + 1) & 1], 2048u);
+          tma_load_3d(((i + 1) & 1) ? resb1 : resb0, tmRes, &res_full[(i + 1) & 1], cc2 * 16, w.row_q + s2 * 128, b);
+        }
+      }
+      __syncwarp();
+    }
+    if constexpr (kAct) {
+      actb[lane * 2 + (0 ^ sw32)] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      actb[lane * 2 + (1 ^ sw32)] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    }
+    fence_proxy_async_smem();                                // generic-proxy writes -> visible to the TMA unit
+    __syncwarp();
+    if (lane == 0) {
+      const bool tail = s == g.msub - 1 && quad == 3;        // the item's last (k-1) rows are not computable here
+      tma_store_3d(tail ? tmRawT : tmRaw, buf ? resb1 : resb0, cc * 16, w.row_q + s * 128, b);
+      if constexpr (kAct) tma_store_3d(tail ? tmActT : tmAct, actb, cc * 16, w.row_q + s * 128, b);
+      bulk_commit();
+      if (tr && i < 2) tr[4 + 3 * i] = gtime();
+    }
+  }
+}
+
+template <int MODE, bool DUAL, bool EPI_TMA>
 __global__ void __maxnreg__(DUAL ? 80 : 168)
 pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
-               const __grid_constant__ CUtensorMap tmW2, const PairParams P) {
+               const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmRes,
+               const __grid_constant__ CUtensorMap tmRaw, const __grid_constant__ CUtensorMap tmRawT,
+               const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtensorMap tmActT, const PairParams P) {
   extern __shared__ uint8_t smem_raw[];
   const ConvParams& p = P.c;
   const PairGeom& g = P.g;
@@ -124,10 +255,20 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* d2_empty = d2_full + 1;
   uint64_t* t_free = d2_empty + 1;      // c2 has finished reading the T slab (gates the aliased A-slab loads)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_free + 1);
-  float* epi_tiles = reinterpret_cast<float*>(bars + 40);
+  uint64_t* res_full = bars + 40;        // EPI_TMA: 2 residual barriers per epilogue warp
+  uint8_t* epi_base = reinterpret_cast<uint8_t*>(bars + 64);
+  epi_base += (1024u - (smem_u32(epi_base) & 1023u)) & 1023u;   // swizzle patterns of the staging need aligned bases
+  float* epi_tiles = reinterpret_cast<float*>(epi_base);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (P.span && threadIdx.x == 0) atomicMin(&P.span[0], (unsigned long long)gtime());
+  if (P.trace && threadIdx.x == 0 && blockIdx.x < 512) {   // debug: which SM ran this CTA, and when
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    P.trace[768 + blockIdx.x * 3 + 0] = smid;
+    P.trace[768 + blockIdx.x * 3 + 1] = gtime();
+  }
 #ifdef L2S_EPI_PROF
   if (g_epi_prof_on && threadIdx.x < 8) epi_prof_smem()[threadIdx.x] = 0;
 #endif
@@ -143,6 +284,11 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_init(d2_full, 1);
     mbar_init(d2_empty, kTcEpiWarps);
     mbar_init(t_free, 1);
+    if (EPI_TMA) {
+      for (int i = 0; i < 2 * kTcEpiWarps; ++i) mbar_init(&res_full[i], 1);
+      tma_prefetch_desc(&tmRes); tma_prefetch_desc(&tmRaw); tma_prefetch_desc(&tmRawT);
+      tma_prefetch_desc(&tmAct); tma_prefetch_desc(&tmActT);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_dyn(tmem_slot, (uint32_t)g.tmem_cols);
@@ -160,6 +306,10 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   if (g.cluster > 1) cluster_sync_all();      // the partner's barriers exist before anything is multicast to them
   tc_fence_after();
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the previous kernel's
+  // tail; nothing below may read or write its data before it has completed.
+  pdl_launch_dependents();
+  pdl_wait_prior_grid();
   const uint32_t tmem_base = *tmem_slot;
   const int acc_cols = g.msub * g.c;          // D1 at [0, acc_cols), D2 at [acc_cols, 2 acc_cols)
   // item walk: a CTA pair advances in lockstep (pair p handles items 2j + rank, j = p, p + pairs, ...)
@@ -319,6 +469,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int half = (warp - 2) >> 2;
     float* tile = epi_tiles + (size_t)(warp - 2) * g.tile_words;
     uint32_t pd1 = 0, pd2 = 0;
+    uint32_t ph_res[2] = {0u, 0u};
     int it_no = 0;
     for (int w = walk0; w < walk_n; w += walkers, ++it_no) {
       const int item = g.cluster > 1 ? 2 * w + crank : w;
@@ -326,6 +477,12 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int b = item / g.m_items;
       const int mi = item - b * g.m_items;
       const int q0 = mi * g.r_out;
+      TmaWalk tw{};
+      if constexpr (EPI_TMA) {   // residual of this item: in flight before phase 1 even starts
+        tw = tma_walk(g, q0, dummy ? 0 : min(p.lin, q0 + g.r_out), quad, half);
+        tma_prefetch_res(tw, &tmRes, reinterpret_cast<uint8_t*>(epi_tiles) + (size_t)(warp - 2) * kTmaStageBytes,
+                         res_full + 2 * (warp - 2), b, lane);
+      }
       // ---- phase 1: D1 -> T slab
       mbar_wait(d1_full, pd1);
       if (warp == 2) L2S_TRACE(2, it_no, 0);
@@ -355,7 +512,12 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       {
         const uint32_t t2 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc_cols;
         const int row_lim = dummy ? 0 : min(p.lin, q0 + g.r_out);   // rows >= r_out of a tile are not computable here
-        if constexpr (DUAL) {   // 80-register budget: 16-column chunks, no residual double buffer
+        if constexpr (EPI_TMA) {
+          epilogue_item_tma<MODE>(p, g, tw, &tmRes, &tmRaw, &tmRawT, &tmAct, &tmActT,
+                                  reinterpret_cast<uint8_t*>(epi_tiles) + (size_t)(warp - 2) * kTmaStageBytes,
+                                  res_full + 2 * (warp - 2), ph_res, t2, b, quad, lane, d2_full, pd2,
+                                  (P.trace && blockIdx.x == 0 && warp == 2 && it_no < 32) ? P.trace + 2304 + it_no * 8 : nullptr);
+        } else if constexpr (DUAL) {   // 80-register budget: 16-column chunks, no residual double buffer
           epilogue_item_rows<16, MODE, false>(p, tile, t2, b, q0, row_lim, g.msub, g.c, quad, half, lane, 0, d2_full, pd2);
         } else {
           if (g.cw == 32) epilogue_item_rows<32, MODE, true>(p, tile, t2, b, q0, row_lim, g.msub, g.c, quad, half, lane, 0, d2_full, pd2);
@@ -369,6 +531,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) mbar_arrive(d2_empty);
       if (warp == 2) L2S_TRACE(2, it_no, 3);
     }
+    if (EPI_TMA && lane == 0) bulk_wait_all();   // every TMA store has landed before the CTA exits
   }
 
   __syncwarp();
@@ -377,6 +540,8 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #ifdef L2S_EPI_PROF
   if (g_epi_prof_on && blockIdx.x == 0 && threadIdx.x < 8) atomicAdd(reinterpret_cast<unsigned long long*>(&g_epi_prof[threadIdx.x]), (unsigned long long)epi_prof_smem()[threadIdx.x]);
 #endif
+  if (P.span && threadIdx.x == 0) atomicMax(&P.span[1], (unsigned long long)gtime());
+  if (P.trace && threadIdx.x == 0 && blockIdx.x < 512) P.trace[768 + blockIdx.x * 3 + 2] = gtime();
   if (g.cluster > 1) cluster_sync_all();      // no CTA leaves while its partner may still multicast into it
   if (warp == 1) tmem_dealloc_dyn(tmem_base, (uint32_t)g.tmem_cols);
 }
@@ -384,7 +549,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------ host side
 
 inline bool pair_plan_with(int c, int k, int dil, int lin, int batch, int smem_budget, bool dual, bool cluster_ok,
-                           bool alias_ok, int cw_pref, int min_sb, PairGeom* out) {
+                           bool alias_ok, int cw_pref, int min_sb, bool epi_tma, bool force_alias, PairGeom* out) {
   PairGeom g{};
   if (c % 16 != 0 || c > 256 || k < 1 || k > kMaxTaps || (k & 1) == 0) return false;
   g.c = c; g.k = k; g.dil = dil;
@@ -397,13 +562,15 @@ inline bool pair_plan_with(int c, int k, int dil, int lin, int batch, int smem_b
   g.cw = (!dual && c % 32 == 0 && cw_pref == 32) ? 32 : 16;
   g.dual = dual ? 1 : 0;
   g.tile_words = 32 * g.cw;
+  g.epi_tma = (epi_tma && dual && c <= 64) ? 1 : 0;
+  if (g.epi_tma) g.tile_words = kTmaStageBytes / 4;
   int tb = 1;
   while (tb < k && tb < 16 && (tb * 2) * c * g.rb <= 16384) tb *= 2;
   if (tb > k) tb = k;
   g.tb = tb;
   g.n_tstages = (k + tb - 1) / tb;
   g.bstage_bytes = tb * c * g.rb;
-  const int bar_bytes = 1024 + 320 + kTcEpiWarps * g.tile_words * 4;
+  const int bar_bytes = 1024 + 512 + 1024 + kTcEpiWarps * g.tile_words * 4;   // alignment slack, barriers, staging alignment, tiles
   int msub = (dual ? 128 : 256) / c;
   if (msub < 1) msub = 1;
   if (msub > 8) msub = 8;
@@ -423,7 +590,7 @@ inline bool pair_plan_with(int c, int k, int dil, int lin, int batch, int smem_b
     g.t_chunk_bytes = g.t_rows * g.rb;
     // C >= 128 is bound by how many weight bytes are in flight (ring depth x stage size / L2 latency):
     // give the ring the room by letting the A-slab ring share the T-slab region.
-    g.alias_at = (alias_ok && c >= 128) ? 1 : 0;
+    g.alias_at = (alias_ok && (c >= 128 || force_alias)) ? 1 : 0;
     const int t_bytes = g.kc * g.t_chunk_bytes;
     int sa = g.kc + 1 < 4 ? g.kc + 1 : 4, sb = 4;
     auto region = [&](int sa_) {
@@ -461,56 +628,72 @@ inline bool pair_plan_with(int c, int k, int dil, int lin, int batch, int smem_b
 // MMA / phase 1 overlaps the other's load/store-heavy phase 2.  (Measured: with half the CTAs every
 // stage takes ~1.7x longer, i.e. the kernels are per-SM latency bound, not chip-memory bound.)
 inline bool pair_plan(int c, int k, int dil, int lin, int batch, int smem_budget, bool allow_dual, bool allow_cluster,
-                      bool allow_alias, PairGeom* out) {
-  if (allow_dual && pair_plan_with(c, k, dil, lin, batch, 110 * 1024, true, false, allow_alias, 16, 2, out)) return true;
+                      bool allow_alias, bool want_tma, bool want_tma_alias, PairGeom* out) {
+  // TMA-streamed phase 2: only where its staging fits WITHOUT aliasing the A ring into the T slab (aliasing
+  // exposes the ~1.5 us A-slab load latency in every item, which cancels the faster phase 2; measured)
+  if (allow_dual && want_tma &&
+      pair_plan_with(c, k, dil, lin, batch, 112 * 1024, true, false, allow_alias, 16, 2, true, want_tma_alias, out) && out->epi_tma)
+    return true;
+  if (allow_dual && pair_plan_with(c, k, dil, lin, batch, 112 * 1024, true, false, allow_alias, 16, 2, false, false, out)) return true;
   // single CTA per SM: 32-column epilogue chunks (full 128-byte lines) as long as >= 3 weight stages still fit,
   // else 16-column chunks (smaller transpose tiles) so the room goes to the weight ring
-  if (pair_plan_with(c, k, dil, lin, batch, smem_budget, false, allow_cluster, allow_alias, 32, c >= 128 ? 3 : 2, out)) return true;
-  return pair_plan_with(c, k, dil, lin, batch, smem_budget, false, allow_cluster, allow_alias, 16, 2, out);
+  if (pair_plan_with(c, k, dil, lin, batch, smem_budget, false, allow_cluster, allow_alias, 32, c >= 128 ? 3 : 2, false, false, out)) return true;
+  return pair_plan_with(c, k, dil, lin, batch, smem_budget, false, allow_cluster, allow_alias, 16, 2, false, false, out);
 }
 
-template <int MODE, bool DUAL>
+struct PairEpiMaps {
+  CUtensorMap res, raw, raw_tail, act, act_tail;   // only read by the EPI_TMA kernels
+};
+
+template <int MODE, bool DUAL, bool EPI_TMA>
 inline cudaError_t launch_pair_mode(const PairParams& P, const CUtensorMap& tmA, const CUtensorMap& tmW1,
-                                    const CUtensorMap& tmW2, int grid, cudaStream_t stream) {
+                                    const CUtensorMap& tmW2, const PairEpiMaps& em, int grid, cudaStream_t stream) {
   static bool configured[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(pair_tc_kernel<MODE, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(pair_tc_kernel<MODE, DUAL, EPI_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(pair_tc_kernel<MODE, DUAL>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(pair_tc_kernel<MODE, DUAL, EPI_TMA>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     configured[dev] = true;
   }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = (size_t)P.g.smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
   if (P.g.cluster > 1) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(kTcThreads);
-    cfg.dynamicSmemBytes = (size_t)P.g.smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)P.g.cluster;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, pair_tc_kernel<MODE, DUAL>, tmA, tmW1, tmW2, P);
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = (unsigned)P.g.cluster;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
   }
-  pair_tc_kernel<MODE, DUAL><<<grid, kTcThreads, P.g.smem_bytes, stream>>>(tmA, tmW1, tmW2, P);
-  return cudaGetLastError();
+  if (g_tc_pdl) {   // programmatic dependent launch: this grid may start while the previous one drains
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = (unsigned)na;
+  return cudaLaunchKernelEx(&cfg, pair_tc_kernel<MODE, DUAL, EPI_TMA>, tmA, tmW1, tmW2, em.res, em.raw, em.raw_tail, em.act,
+                            em.act_tail, P);
 }
 
 // c: the c2 epilogue description (bias = b2, res, acc_in, outputs, div, slope, lin = mrows = L, ntot = C, out_valid = L * C).
 inline cudaError_t launch_pair_tc(const ConvParams& c, const float* bias1, const PairGeom& g, const CUtensorMap& tmA,
-                                  const CUtensorMap& tmW1, const CUtensorMap& tmW2, int num_ctas, cudaStream_t stream,
-                                  long long* trace = nullptr) {
+                                  const CUtensorMap& tmW1, const CUtensorMap& tmW2, const PairEpiMaps& em, int num_ctas,
+                                  cudaStream_t stream, long long* trace = nullptr, unsigned long long* span = nullptr) {
   PairParams P;
   P.c = c;
   P.bias1 = bias1;
   P.g = g;
   P.trace = trace;
+  P.span = span;
   const int cap = num_ctas * (g.dual ? 2 : 1);
   int grid = g.total_items < cap ? g.total_items : cap;
   if (grid < 1) grid = 1;
@@ -522,11 +705,16 @@ inline cudaError_t launch_pair_tc(const ConvParams& c, const float* bias1, const
   }
   const int mode = (c.res ? kEpiRes : 0) | ((c.acc_in || c.div != 1.0f) ? kEpiAcc : 0) | (c.out_raw ? kEpiRaw : 0) |
                    (c.out_act ? kEpiAct : 0);
+  if (g.epi_tma) {   // asynchronous phase 2: dual plans, residual + raw (+ act)
+    if (mode == 5) return launch_pair_mode<5, true, true>(P, tmA, tmW1, tmW2, em, grid, stream);
+    if (mode == 13) return launch_pair_mode<13, true, true>(P, tmA, tmW1, tmW2, em, grid, stream);
+    return cudaErrorInvalidValue;
+  }
   switch (mode) {
 #define L2S_PMODE(m)                                                                          \
   case m:                                                                                     \
-    return g.dual ? launch_pair_mode<m, true>(P, tmA, tmW1, tmW2, grid, stream)               \
-                  : launch_pair_mode<m, false>(P, tmA, tmW1, tmW2, grid, stream);
+    return g.dual ? launch_pair_mode<m, true, false>(P, tmA, tmW1, tmW2, em, grid, stream)    \
+                  : launch_pair_mode<m, false, false>(P, tmA, tmW1, tmW2, em, grid, stream);
     L2S_PMODE(5) L2S_PMODE(7) L2S_PMODE(11) L2S_PMODE(13) L2S_PMODE(15)
 #undef L2S_PMODE
     default: return cudaErrorInvalidValue;   // a ResBlock step always has the residual and an output

@@ -31,10 +31,16 @@ struct Knobs {
   long long per_tap = 0;
   long long sa_min = 0;
   long long dual = 1;
+  long long span_ptr = 0;          // device array [launch][2]: min CTA start / max CTA end of every tcgen05 launch
   long long trace_launch = -1;     // index of the fused-step launch of a forward that gets trace_ptr
   long long cluster = 0;           // fused steps with C >= 128: CTA pairs share weight loads (TMA multicast); measured
                                    // neutral on B200 (the weight ring depth, not L2 read volume, bounds those layers)
   long long alias_at = 1;          // fused steps with C >= 128: A-slab ring shares the T-slab shared memory
+  long long epi_tma = 0;           // dual fused steps (C <= 64, residual + raw [+ act]): TMA-streamed phase 2 (1: where it fits
+                                   // without aliasing, 2: also aliased).  Bit-exact, measured neutral: TMA-store completion
+                                   // latency replaces the LSU cost, so it is off by default.
+  long long use_graph = 1;         // replay the conv chain (conv_pre .. last MRF stage) as a CUDA graph per (B, T, workspace)
+  long long epoch = 0;             // bumped by every l2s_debug_set: cached graphs of older epochs are not reused
   long long fuse_pairs = 1;        // bf16 mode: one kernel per ResBlock (c1, c2) step
   long long plan_report = 0;       // l2s_debug_conv: write the chosen plan + occupancy into the err buffer
   long long trace_ptr = 0;         // device pointer for the kernel trace of l2s_debug_conv (0: off)
@@ -109,6 +115,11 @@ struct l2s_vocoder {
   std::vector<Timed> timed;
   size_t timed_used = 0;
   long long pair_launches = 0;     // fused-step launches issued by the current forward
+  long long tc_launches = 0;       // all tcgen05 launches of the current forward (span_ptr slots)
+  // CUDA-graph replay of the conv chain
+  struct ChainGraph { int batch, frames; void* workspace; long long epoch; int seen; cudaGraphExec_t exec; };
+  std::vector<ChainGraph> graphs;
+  cudaStream_t capture_stream = nullptr;
 };
 
 namespace {
@@ -353,7 +364,9 @@ int run_conv(l2s_vocoder* v, ConvLayer& L, cudaStream_t st, int batch, int lin, 
     if (!make_tmap_3d(&tmA, in, g.esz, (uint64_t)L.cin_pad, (uint64_t)lin, (uint64_t)batch, (uint32_t)(g.rb / g.esz),
                       (uint32_t)g.box_rows, 1u))
       return fail(v, L2S_ERR_CUDA, "cuTensorMapEncodeTiled failed for the input of " + L.name);
-    e = launch_conv_tc(p, g, tmA, L.tmW, tune.max_ctas, st);
+    unsigned long long* span = g_knobs.span_ptr ? reinterpret_cast<unsigned long long*>(g_knobs.span_ptr) + 2 * v->tc_launches : nullptr;
+    ++v->tc_launches;
+    e = launch_conv_tc(p, g, tmA, L.tmW, tune.max_ctas, st, nullptr, span);
   }
   timed_end(v, st);
   if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, std::string("launch ") + L.name + ": " + cudaGetErrorString(e));
@@ -380,7 +393,11 @@ int run_pair(l2s_vocoder* v, ConvLayer& c1, ConvLayer& c2, cudaStream_t st, int 
   if (c1.cin != c1.cout || c2.cin != c2.cout || c1.cin != c2.cin || c1.cin_pad != c1.cin || c1.k != c2.k || c2.dil != 1)
     return L2S_ERR_UNSUPPORTED;
   PairGeom g;
-  if (!pair_plan(c1.cin, c1.k, c1.dil, lin, batch, 220 * 1024, g_knobs.dual != 0, g_knobs.cluster != 0, g_knobs.alias_at != 0, &g)) return L2S_ERR_UNSUPPORTED;
+  const int emode = (res ? kEpiRes : 0) | ((acc_in || div != 1.0f) ? kEpiAcc : 0) | (out_raw ? kEpiRaw : 0) | (out_act ? kEpiAct : 0);
+  const bool want_tma = g_knobs.epi_tma != 0 && (emode == 5 || emode == 13);
+  if (!pair_plan(c1.cin, c1.k, c1.dil, lin, batch, 220 * 1024, g_knobs.dual != 0, g_knobs.cluster != 0, g_knobs.alias_at != 0,
+                 want_tma, g_knobs.epi_tma == 2, &g))
+    return L2S_ERR_UNSUPPORTED;
   // with CTA-pair multicast each CTA fetches half of the output-channel rows of a weight stage
   if (!ensure_w_map(c1, g.rb, g.c / g.cluster, g.tb) || !ensure_w_map(c2, g.rb, g.c / g.cluster, g.tb))
     return fail(v, L2S_ERR_CUDA, "cuTensorMapEncodeTiled failed for the weights of " + c1.name);
@@ -408,9 +425,25 @@ int run_pair(l2s_vocoder* v, ConvLayer& c1, ConvLayer& c2, cudaStream_t st, int 
   p.slope = slope;
   timed_begin(v, st, c1.name + "+c2", 4.0 * c1.cin * c1.cout * c1.k * (double)batch * lin);
   const int ctas = g_knobs.max_ctas > 0 ? (int)g_knobs.max_ctas : v->num_sms;
+  PairEpiMaps em{};
+  if (g.epi_tma) {
+    const int tail_rows = 32 - 2 * g.h2 > 0 ? 32 - 2 * g.h2 : 32;
+    const uint64_t C = (uint64_t)c2.cout, L = (uint64_t)lin, B = (uint64_t)batch;
+    bool ok = make_tmap_3d(&em.res, res, 4, C, L, B, 16u, 32u, 1u) && make_tmap_3d(&em.raw, out_raw, 4, C, L, B, 16u, 32u, 1u) &&
+              make_tmap_3d(&em.raw_tail, out_raw, 4, C, L, B, 16u, (uint32_t)tail_rows, 1u);
+    if (out_act)
+      ok = ok && make_tmap_3d(&em.act, out_act, 2, C, L, B, 16u, 32u, 1u) &&
+           make_tmap_3d(&em.act_tail, out_act, 2, C, L, B, 16u, (uint32_t)tail_rows, 1u);
+    else { em.act = em.raw; em.act_tail = em.raw_tail; }
+    if (!ok) return fail(v, L2S_ERR_CUDA, "cuTensorMapEncodeTiled failed for the epilogue tensors of " + c1.name);
+  } else {
+    em.res = tmA; em.raw = tmA; em.raw_tail = tmA; em.act = tmA; em.act_tail = tmA;   // never read
+  }
   long long* trace = (g_knobs.trace_ptr && g_knobs.trace_launch == v->pair_launches) ? reinterpret_cast<long long*>(g_knobs.trace_ptr) : nullptr;
   ++v->pair_launches;
-  cudaError_t e = launch_pair_tc(p, c1.bias_dev, g, tmA, c1.tmW, c2.tmW, ctas, st, trace);
+  unsigned long long* span = g_knobs.span_ptr ? reinterpret_cast<unsigned long long*>(g_knobs.span_ptr) + 2 * v->tc_launches : nullptr;
+  ++v->tc_launches;
+  cudaError_t e = launch_pair_tc(p, c1.bias_dev, g, tmA, c1.tmW, c2.tmW, em, ctas, st, trace, span);
   timed_end(v, st);
   if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, std::string("launch pair ") + c1.name + ": " + cudaGetErrorString(e));
   return L2S_OK;
@@ -461,6 +494,89 @@ Workspace carve(const l2s_vocoder* v, int batch, int frames, uint8_t* base) {
   return w;
 }
 
+// conv_pre, the upsample stages and the MRF stacks: every launch of a forward between the conditioning front end
+// and the waveform head.  All buffers live in the workspace, so the sequence can be captured once per
+// (batch, frames, workspace) and replayed as a CUDA graph.  *stopped: a debug knob ended the forward early.
+int run_chain(l2s_vocoder* v, cudaStream_t st, const Workspace& ws, int batch, int frames, bool* stopped) {
+  const l2s_config& c = v->cfg;
+  ConvLayer& pre = v->convs[v->conv_pre];
+  *stopped = true;
+  // ---- conv_pre (its consumer applies leaky_relu(0.1): emit the activated copy only)
+  int rc = run_conv(v, pre, st, batch, frames, ws.cond, nullptr, ws.ma[0], nullptr, nullptr, 1.f, 0.1f);
+  if (rc) return rc;
+  v->taps["conv_pre_act"] = {ws.ma[0], (long long)batch * frames * c.up_init_ch, true};
+  if (g_knobs.stop_after_pre) return L2S_OK;
+
+  // ---- upsample stages + MRF
+  int cur = 0;
+  long long len = frames;
+  for (int i = 0; i < c.n_ups; ++i) {
+    ConvLayer& up = v->convs[v->ups[i]];
+    rc = run_conv(v, up, st, batch, (int)len, ws.ma[cur], ws.x, ws.xa, nullptr, nullptr, 1.f, 0.1f);
+    if (rc) return rc;
+    len *= c.up_rates[i];
+    const int ch = v->stage_ch[i];
+    const long long numel = (long long)batch * len * ch;
+    const bool last_stage = i == c.n_ups - 1;
+    const bool want_raw = last_stage || g_knobs.stop_after_stage == i;
+    // A fused step reads its activated input WITH HALO while other CTAs already write the activated
+    // output, so fused stages ping-pong the activated buffers (xa -> ya -> ta -> ...); the fp32
+    // residual is updated in place (each element is read and written by the same thread).
+    bool stage_fused = pairs_fused(v);
+    for (int j = 0; stage_fused && j < c.n_rk; ++j)
+      for (int m = 0; m < c.n_dil; ++m) {
+        const ConvLayer& a1 = v->convs[v->rb_c1[i][j][m]];
+        const ConvLayer& a2 = v->convs[v->rb_c2[i][j][m]];
+        PairGeom pg;
+        if (a1.cin != a1.cout || a1.cin_pad != a1.cin || a1.k != a2.k || a2.dil != 1 ||
+            !pair_plan(a1.cin, a1.k, a1.dil, (int)len, batch, 220 * 1024, g_knobs.dual != 0, g_knobs.cluster != 0, g_knobs.alias_at != 0, false, false, &pg))
+          stage_fused = false;
+      }
+    for (int j = 0; j < c.n_rk; ++j) {
+      for (int m = 0; m < c.n_dil; ++m) {
+        ConvLayer& c1 = v->convs[v->rb_c1[i][j][m]];
+        ConvLayer& c2 = v->convs[v->rb_c2[i][j][m]];
+        void* act_pp[2] = {ws.ya, ws.ta};
+        const void* in1 = m == 0 ? ws.xa : (stage_fused ? act_pp[(m - 1) & 1] : ws.ya);
+        void* mid_act = stage_fused ? act_pp[m & 1] : ws.ya;     // activated output of a non-final step
+        const float* res = m == 0 ? ws.x : ws.y;
+        // per (j, m): which outputs the step produces
+        float* o_raw;
+        void* o_act;
+        const float* a_in = nullptr;
+        float dv = 1.f;
+        if (m < c.n_dil - 1) { o_raw = ws.y; o_act = mid_act; }
+        else if (j < c.n_rk - 1) { o_raw = ws.acc; o_act = nullptr; a_in = j == 0 ? nullptr : ws.acc; }
+        else {
+          // last branch: mean over branches (true division by num_kernels, models.py:109)
+          o_raw = want_raw ? ws.acc : nullptr;
+          o_act = last_stage ? nullptr : ws.ma[cur ^ 1];
+          a_in = c.n_rk == 1 ? nullptr : ws.acc;
+          dv = (float)c.n_rk;
+        }
+        if (stage_fused) {
+          rc = run_pair(v, c1, c2, st, batch, (int)len, in1, res, o_raw, o_act, a_in, dv, 0.1f);
+          if (rc == L2S_ERR_UNSUPPORTED) return fail(v, L2S_ERR_STATE, "fused plan vanished for " + c1.name);
+        } else {
+          rc = run_conv(v, c1, st, batch, (int)len, in1, nullptr, ws.ta, nullptr, nullptr, 1.f, 0.1f);
+          if (rc) return rc;
+          rc = run_conv(v, c2, st, batch, (int)len, ws.ta, o_raw, o_act, res, a_in, dv, 0.1f);
+        }
+        if (rc) return rc;
+      }
+    }
+    cur ^= 1;
+    if (g_knobs.stop_after_stage == i) {
+      v->taps["ups"] = {ws.x, numel, false};
+      v->taps["mrf"] = {ws.acc, numel, false};
+      return L2S_OK;
+    }
+  }
+
+  *stopped = false;
+  return L2S_OK;
+}
+
 int forward_impl(l2s_vocoder* v, void* stream, const int64_t* code, const void* mel, int32_t mel_dtype, const void* spkr,
                  int32_t batch, int32_t units, int32_t frames, float* out, int16_t* out_i16, void* workspace,
                  int64_t workspace_bytes) {
@@ -496,6 +612,7 @@ int forward_impl(l2s_vocoder* v, void* stream, const int64_t* code, const void* 
   v->taps.clear();
   v->timed_used = 0;
   v->pair_launches = 0;
+  v->tc_launches = 0;
   cudaError_t e;
   ConvLayer& pre = v->convs[v->conv_pre];
 
@@ -545,77 +662,54 @@ int forward_impl(l2s_vocoder* v, void* stream, const int64_t* code, const void* 
   v->taps["cond"] = {ws.cond, (long long)batch * frames * pre.cin_pad, true};
   if (embed_tap) v->taps["embed"] = {ws.embed, (long long)batch * units * E, false};
 
-  // ---- conv_pre (its consumer applies leaky_relu(0.1): emit the activated copy only)
-  int rc = run_conv(v, pre, st, batch, frames, ws.cond, nullptr, ws.ma[0], nullptr, nullptr, 1.f, 0.1f);
-  if (rc) return rc;
-  v->taps["conv_pre_act"] = {ws.ma[0], (long long)batch * frames * c.up_init_ch, true};
-  if (g_knobs.stop_after_pre) return L2S_OK;
-
-  // ---- upsample stages + MRF
-  int cur = 0;
-  long long len = frames;
-  for (int i = 0; i < c.n_ups; ++i) {
-    ConvLayer& up = v->convs[v->ups[i]];
-    rc = run_conv(v, up, st, batch, (int)len, ws.ma[cur], ws.x, ws.xa, nullptr, nullptr, 1.f, 0.1f);
-    if (rc) return rc;
-    len *= c.up_rates[i];
-    const int ch = v->stage_ch[i];
-    const long long numel = (long long)batch * len * ch;
-    const bool last_stage = i == c.n_ups - 1;
-    const bool want_raw = last_stage || g_knobs.stop_after_stage == i;
-    // A fused step reads its activated input WITH HALO while other CTAs already write the activated
-    // output, so fused stages ping-pong the activated buffers (xa -> ya -> ta -> ...); the fp32
-    // residual is updated in place (each element is read and written by the same thread).
-    bool stage_fused = pairs_fused(v);
-    for (int j = 0; stage_fused && j < c.n_rk; ++j)
-      for (int m = 0; m < c.n_dil; ++m) {
-        const ConvLayer& a1 = v->convs[v->rb_c1[i][j][m]];
-        const ConvLayer& a2 = v->convs[v->rb_c2[i][j][m]];
-        PairGeom pg;
-        if (a1.cin != a1.cout || a1.cin_pad != a1.cin || a1.k != a2.k || a2.dil != 1 ||
-            !pair_plan(a1.cin, a1.k, a1.dil, (int)len, batch, 220 * 1024, g_knobs.dual != 0, g_knobs.cluster != 0, g_knobs.alias_at != 0, &pg))
-          stage_fused = false;
-      }
-    for (int j = 0; j < c.n_rk; ++j) {
-      for (int m = 0; m < c.n_dil; ++m) {
-        ConvLayer& c1 = v->convs[v->rb_c1[i][j][m]];
-        ConvLayer& c2 = v->convs[v->rb_c2[i][j][m]];
-        void* act_pp[2] = {ws.ya, ws.ta};
-        const void* in1 = m == 0 ? ws.xa : (stage_fused ? act_pp[(m - 1) & 1] : ws.ya);
-        void* mid_act = stage_fused ? act_pp[m & 1] : ws.ya;     // activated output of a non-final step
-        const float* res = m == 0 ? ws.x : ws.y;
-        // per (j, m): which outputs the step produces
-        float* o_raw;
-        void* o_act;
-        const float* a_in = nullptr;
-        float dv = 1.f;
-        if (m < c.n_dil - 1) { o_raw = ws.y; o_act = mid_act; }
-        else if (j < c.n_rk - 1) { o_raw = ws.acc; o_act = nullptr; a_in = j == 0 ? nullptr : ws.acc; }
-        else {
-          // last branch: mean over branches (true division by num_kernels, models.py:109)
-          o_raw = want_raw ? ws.acc : nullptr;
-          o_act = last_stage ? nullptr : ws.ma[cur ^ 1];
-          a_in = c.n_rk == 1 ? nullptr : ws.acc;
-          dv = (float)c.n_rk;
+  // ---- conv_pre, upsample stages, MRF stacks: eager, or replayed from a captured CUDA graph
+  {
+    const bool debug_run = g_knobs.stop_after_pre || g_knobs.stop_after_stage >= 0 || g_knobs.layer_events || g_knobs.span_ptr ||
+                           g_knobs.trace_ptr;
+    const bool graph_ok = g_knobs.use_graph && !debug_run && v->cfg.precision != L2S_PREC_FP32;
+    bool stopped = false;
+    int rc = L2S_OK;
+    l2s_vocoder::ChainGraph* slot = nullptr;
+    if (graph_ok) {
+      for (auto& gph : v->graphs)
+        if (gph.batch == batch && gph.frames == frames && gph.workspace == workspace && gph.epoch == g_knobs.epoch) slot = &gph;
+      if (!slot) {
+        if (v->graphs.size() >= 16) {   // keep the cache small: drop everything (shapes rarely vary that much)
+          for (auto& gph : v->graphs) if (gph.exec) cudaGraphExecDestroy(gph.exec);
+          v->graphs.clear();
         }
-        if (stage_fused) {
-          rc = run_pair(v, c1, c2, st, batch, (int)len, in1, res, o_raw, o_act, a_in, dv, 0.1f);
-          if (rc == L2S_ERR_UNSUPPORTED) return fail(v, L2S_ERR_STATE, "fused plan vanished for " + c1.name);
-        } else {
-          rc = run_conv(v, c1, st, batch, (int)len, in1, nullptr, ws.ta, nullptr, nullptr, 1.f, 0.1f);
-          if (rc) return rc;
-          rc = run_conv(v, c2, st, batch, (int)len, ws.ta, o_raw, o_act, res, a_in, dv, 0.1f);
-        }
-        if (rc) return rc;
+        v->graphs.push_back({batch, frames, workspace, g_knobs.epoch, 0, nullptr});
+        slot = &v->graphs.back();
       }
     }
-    cur ^= 1;
-    if (g_knobs.stop_after_stage == i) {
-      v->taps["ups"] = {ws.x, numel, false};
-      v->taps["mrf"] = {ws.acc, numel, false};
-      return L2S_OK;
+    if (slot && slot->exec) {
+      if ((e = cudaGraphLaunch(slot->exec, st)) != cudaSuccess)
+        return fail(v, L2S_ERR_CUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(e));
+    } else if (slot && slot->seen >= 1) {
+      // second forward with this shape: capture on the internal stream (the caller's may be the legacy default
+      // stream, which cannot be captured), then replay on the caller's stream
+      if (!v->capture_stream && (e = cudaStreamCreateWithFlags(&v->capture_stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return fail(v, L2S_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+      cudaGraph_t graph = nullptr;
+      if ((e = cudaStreamBeginCapture(v->capture_stream, cudaStreamCaptureModeThreadLocal)) != cudaSuccess)
+        return fail(v, L2S_ERR_CUDA, std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(e));
+      rc = run_chain(v, v->capture_stream, ws, batch, frames, &stopped);
+      e = cudaStreamEndCapture(v->capture_stream, &graph);
+      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+      if (e != cudaSuccess || !graph) return fail(v, L2S_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+      e = cudaGraphInstantiate(&slot->exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) { slot->exec = nullptr; return fail(v, L2S_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+      if ((e = cudaGraphLaunch(slot->exec, st)) != cudaSuccess)
+        return fail(v, L2S_ERR_CUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(e));
+    } else {
+      rc = run_chain(v, st, ws, batch, frames, &stopped);   // eager (first use of a shape, debug runs, fp32 mode)
+      if (rc) return rc;
+      if (slot) ++slot->seen;
+      if (stopped) return L2S_OK;
     }
   }
+  long long len = (long long)frames * hop_of(c);
 
   // ---- waveform head
   PostParams pp{};
@@ -657,6 +751,8 @@ void l2s_destroy(l2s_vocoder* v) {
     int dev = -1;
     cudaGetDevice(&dev);
     if (dev != v->device) cudaSetDevice(v->device);
+    for (auto& gph : v->graphs) if (gph.exec) cudaGraphExecDestroy(gph.exec);
+    if (v->capture_stream) cudaStreamDestroy(v->capture_stream);
     for (void* p : v->dev_allocs) cudaFree(p);
     if (v->err_host) cudaFreeHost(v->err_host);
     if (dev >= 0 && dev != v->device) cudaSetDevice(dev);
@@ -919,6 +1015,8 @@ int l2s_debug_epi_prof(long long* out8) {
 int l2s_debug_set(const char* key, int64_t value) {
   if (!key) return L2S_ERR_INVALID;
   const std::string k(key);
+  ++g_knobs.epoch;
+  if (k == "use_graph") { g_knobs.use_graph = value; return L2S_OK; }
   if (k == "force_simt") g_knobs.force_simt = value;
   else if (k == "stop_after_stage") g_knobs.stop_after_stage = value;
   else if (k == "stop_after_pre") g_knobs.stop_after_pre = value;
@@ -928,8 +1026,11 @@ int l2s_debug_set(const char* key, int64_t value) {
   else if (k == "fuse_pairs") g_knobs.fuse_pairs = value;
   else if (k == "cluster") g_knobs.cluster = value;
   else if (k == "alias_at") g_knobs.alias_at = value;
+  else if (k == "epi_tma") g_knobs.epi_tma = value;
+  else if (k == "pdl") g_tc_pdl = (int)value;
   else if (k == "epi_prof") { int on = (int)value; cudaMemcpyToSymbol(g_epi_prof_on, &on, sizeof on); }
   else if (k == "trace_launch") g_knobs.trace_launch = value;
+  else if (k == "span_ptr") g_knobs.span_ptr = value;
   else if (k == "plan_report") g_knobs.plan_report = value;
   else if (k == "trace_ptr") g_knobs.trace_ptr = value;
   else if (k == "max_msub") g_knobs.max_msub = value;

@@ -239,7 +239,7 @@ def test_fused_resblock_steps_equal_unfused(pkg, weights, frames):
     assert torch.equal(a, b), float((a - b).abs().max())
 
 
-@pytest.mark.parametrize("knob", ["dual", "cluster", "alias_at"])
+@pytest.mark.parametrize("knob", ["dual", "cluster", "alias_at", "epi_tma", "pdl"])
 def test_fused_kernel_variants_agree(pkg, weights, knob):
     """Two-CTAs-per-SM plans (dual) and CTA-pair weight multicast (cluster) change scheduling only:
     the waveform must not change by a bit."""
@@ -256,8 +256,33 @@ def test_fused_kernel_variants_agree(pkg, weights, knob):
         lib.l2s_debug_set(b"dual", 1)
         lib.l2s_debug_set(b"cluster", 0)
         lib.l2s_debug_set(b"alias_at", 1)
+        lib.l2s_debug_set(b"epi_tma", 0)
+        lib.l2s_debug_set(b"pdl", 1)
     assert torch.isfinite(outs[0]).all()
     assert torch.equal(outs[0], outs[1]), float((outs[0] - outs[1]).abs().max())
+
+
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+def test_graph_replay_equals_eager(pkg, weights, precision):
+    """The conv chain is run eagerly on the first forward of a shape, captured into a CUDA graph on the second and
+    replayed afterwards: all three must give the same bits, also for new inputs of the same shape."""
+    h, sds = weights
+    g = make_gen(pkg, h, sds["trained"], precision)
+    lib = pkg._cabi.load()
+    code, mel, spkr = vo.synthetic_inputs(2, 90, seed=41)
+    code2, mel2, spkr2 = vo.synthetic_inputs(2, 90, seed=42)
+    try:
+        lib.l2s_debug_set(b"use_graph", 0)
+        ref1 = g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV)).clone()
+        ref2 = g(code=code2.to(DEV), mel=mel2.to(DEV), spkr=spkr2.to(DEV)).clone()
+        lib.l2s_debug_set(b"use_graph", 1)
+        outs = [g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV)).clone() for _ in range(3)]
+        other = g(code=code2.to(DEV), mel=mel2.to(DEV), spkr=spkr2.to(DEV)).clone()
+    finally:
+        lib.l2s_debug_set(b"use_graph", 1)
+    for o in outs:
+        assert torch.equal(o, ref1)
+    assert torch.equal(other, ref2)
 
 
 def test_cfg2_shape_bf16_vs_fp32_device_reference(pkg, weights):
