@@ -28,6 +28,8 @@
 
 namespace l2s {
 
+inline int g_pair_pref = 0;   // planning experiment switch (knob pair_pref)
+
 struct PairGeom {
   int c;             // channels (= cin = cout = MMA N)
   int k, dil;        // kernel size, dilation of c1 (c2 has dilation 1)
@@ -637,6 +639,9 @@ inline bool pair_plan(int c, int k, int dil, int lin, int batch, int smem_budget
   if (allow_dual && pair_plan_with(c, k, dil, lin, batch, 112 * 1024, true, false, allow_alias, 16, 2, false, false, out)) return true;
   // single CTA per SM: 32-column epilogue chunks (full 128-byte lines) as long as >= 3 weight stages still fit,
   // else 16-column chunks (smaller transpose tiles) so the room goes to the weight ring
+  if (g_pair_pref == 1 && c >= 256 &&
+      pair_plan_with(c, k, dil, lin, batch, smem_budget, false, allow_cluster, allow_alias, 16, 4, false, false, out))
+    return true;   // experiment: 16-column tiles, >= 4 weight stages
   if (pair_plan_with(c, k, dil, lin, batch, smem_budget, false, allow_cluster, allow_alias, 32, c >= 128 ? 3 : 2, false, false, out)) return true;
   return pair_plan_with(c, k, dil, lin, batch, smem_budget, false, allow_cluster, allow_alias, 16, 2, false, false, out);
 }

@@ -41,6 +41,7 @@ struct Knobs {
                                    // latency replaces the LSU cost, so it is off by default.
   long long use_graph = 1;         // replay the conv chain (conv_pre .. last MRF stage) as a CUDA graph per (B, T, workspace)
   long long epoch = 0;             // bumped by every l2s_debug_set: cached graphs of older epochs are not reused
+  long long pair_smem = 220 * 1024; // shared-memory budget of the single-CTA fused plans
   long long fuse_pairs = 1;        // bf16 mode: one kernel per ResBlock (c1, c2) step
   long long plan_report = 0;       // l2s_debug_conv: write the chosen plan + occupancy into the err buffer
   long long trace_ptr = 0;         // device pointer for the kernel trace of l2s_debug_conv (0: off)
@@ -395,7 +396,7 @@ int run_pair(l2s_vocoder* v, ConvLayer& c1, ConvLayer& c2, cudaStream_t st, int 
   PairGeom g;
   const int emode = (res ? kEpiRes : 0) | ((acc_in || div != 1.0f) ? kEpiAcc : 0) | (out_raw ? kEpiRaw : 0) | (out_act ? kEpiAct : 0);
   const bool want_tma = g_knobs.epi_tma != 0 && (emode == 5 || emode == 13);
-  if (!pair_plan(c1.cin, c1.k, c1.dil, lin, batch, 220 * 1024, g_knobs.dual != 0, g_knobs.cluster != 0, g_knobs.alias_at != 0,
+  if (!pair_plan(c1.cin, c1.k, c1.dil, lin, batch, (int)g_knobs.pair_smem, g_knobs.dual != 0, g_knobs.cluster != 0, g_knobs.alias_at != 0,
                  want_tma, g_knobs.epi_tma == 2, &g))
     return L2S_ERR_UNSUPPORTED;
   // with CTA-pair multicast each CTA fetches half of the output-channel rows of a weight stage
@@ -529,7 +530,7 @@ int run_chain(l2s_vocoder* v, cudaStream_t st, const Workspace& ws, int batch, i
         const ConvLayer& a2 = v->convs[v->rb_c2[i][j][m]];
         PairGeom pg;
         if (a1.cin != a1.cout || a1.cin_pad != a1.cin || a1.k != a2.k || a2.dil != 1 ||
-            !pair_plan(a1.cin, a1.k, a1.dil, (int)len, batch, 220 * 1024, g_knobs.dual != 0, g_knobs.cluster != 0, g_knobs.alias_at != 0, false, false, &pg))
+            !pair_plan(a1.cin, a1.k, a1.dil, (int)len, batch, (int)g_knobs.pair_smem, g_knobs.dual != 0, g_knobs.cluster != 0, g_knobs.alias_at != 0, false, false, &pg))
           stage_fused = false;
       }
     for (int j = 0; j < c.n_rk; ++j) {
@@ -1028,6 +1029,8 @@ int l2s_debug_set(const char* key, int64_t value) {
   else if (k == "alias_at") g_knobs.alias_at = value;
   else if (k == "epi_tma") g_knobs.epi_tma = value;
   else if (k == "pdl") g_tc_pdl = (int)value;
+  else if (k == "pair_pref") g_pair_pref = (int)value;
+  else if (k == "pair_smem") g_knobs.pair_smem = value;
   else if (k == "epi_prof") { int on = (int)value; cudaMemcpyToSymbol(g_epi_prof_on, &on, sizeof on); }
   else if (k == "trace_launch") g_knobs.trace_launch = value;
   else if (k == "span_ptr") g_knobs.span_ptr = value;
