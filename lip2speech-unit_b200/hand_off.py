@@ -1,0 +1,144 @@
+"""The on-disk hand-off around the generator: what stage 1 and
+``create_dataset.vocoder()`` leave for the vocoder service, and what the service writes back.
+
+    <root>/label/<split>.tsv    first line = dataset root, then  id \\t video \\t audio \\t n_video_frames \\t n_audio_samples
+    <root>/label/<split>.unt    one line of space-separated unit tokens per row (an optional ``name|`` prefix is dropped)
+    <root>/label/dict.unt.txt   ``token count`` per line; a token's id is its line number
+    <root>/mel/<id>.npy         (T', 80) float32 / float16 log-mel, 100 Hz
+    <root>/spk_emb/<id>.npy     (256,) float32 speaker embedding
+    <out>/pred_wav/<split>/<name>.wav   int16, 16 kHz mono
+
+Mirrors ``multi_input_vocoder/dataset_multi_input.py`` (parse_manifest :40-110, load_code_dict :118-125,
+code_to_sequence :128-141, the trimming rule of __getitem__ :219-241, speaker file mapping :174) and the writer
+of ``inference.py:152-165`` / ``inference_server.py:133-146`` -- minus what the vocoder never needed at
+inference (the ground-truth wav read, the discarded STFT mel, random interval sampling).
+
+``vocode_manifest`` is the batched caller: the reference runs one utterance per forward; here utterances of
+equal length are stacked into one forward (the generator has no length masks), and the int16
+conversion happens on the device.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+CODE_HOP, MEL_HOP, SAMPLE_RATE = 320, 160, 16000
+
+
+@dataclass
+class ManifestRow:
+    uid: str            # "test/UmvOgW6iV2s/00007"
+    audio_rel: str      # "audio/test/UmvOgW6iV2s/00007.wav" (relative to the dataset root)
+    n_video: int        # video frames (25 fps): the manifest's size column (items[-2])
+    n_audio: int        # audio samples at 16 kHz (items[-1])
+    units: str          # unit tokens, space separated
+
+
+def parse_manifest(manifest_path: str, max_keep: Optional[int] = None, min_keep: Optional[int] = None):
+    """Returns (root_line, rows).  Same filtering and the same alignment check (|len(units) - 2 * n_video| <= 2)
+    as dataset_multi_input.py:59-77; a misaligned row raises instead of dropping into pdb."""
+    code_path = os.path.splitext(manifest_path)[0] + ".unt"
+    rows: List[ManifestRow] = []
+    with open(manifest_path) as f, open(code_path) as fc:
+        root = f.readline().strip()
+        for line, line_code in zip(f, fc):
+            items = line.strip().split("\t")
+            code = line_code.strip().split("|")[-1]
+            sz = int(items[-2])
+            diff = len(code.split()) - sz * 2
+            if not -2 <= diff <= 2:
+                raise ValueError(f"{items[0]}: code length {len(code.split())} != video length * 2 ({sz * 2})")
+            if min_keep is not None and sz < min_keep:
+                continue
+            if max_keep is not None and sz > max_keep:
+                continue
+            rows.append(ManifestRow(items[0], items[2], sz, int(items[-1]), code))
+    return root, rows
+
+
+def load_code_dict(path: str) -> Dict[str, int]:
+    with open(path) as f:
+        codes = [line.rstrip().rsplit(" ", 1)[0] for line in f]
+    d = {c: i for i, c in enumerate(codes)}
+    if set(d.values()) != set(range(len(d))):
+        raise ValueError("duplicate tokens in the unit dictionary")
+    return d
+
+
+def code_to_sequence(tokens: Sequence[str], code_dict: Dict[str, int]) -> List[int]:
+    """collapse_code=False branch of dataset_multi_input.py:128-141 (unknown tokens are dropped; the reference warns
+    when more than 5 % are)."""
+    return [code_dict[c] for c in tokens if c in code_dict]
+
+
+def trim_lengths(n_audio: int, n_units: int, n_mel: int):
+    """The trimming rule of __getitem__ (:219-241): U = min(n // 320, units), T = min(n // 160, mel frames),
+    cut = min(160 T, 320 U)  ->  (units kept, mel frames kept, samples)."""
+    u = min(n_audio // CODE_HOP, n_units)
+    t = min(n_audio // MEL_HOP, n_mel)
+    cut = min(t * MEL_HOP, u * CODE_HOP)
+    return cut // CODE_HOP, cut // MEL_HOP, cut
+
+
+def load_item(root: str, row: ManifestRow, code_dict: Dict[str, int], n_audio: Optional[int] = None):
+    """code int64 (U,), mel (80, T) in the file's dtype, spkr float32 (256,), and the sample count of the output.
+    n_audio defaults to the manifest's sample count (the reference reads the wav for it; they agree)."""
+    audio_path = os.path.join(root, row.audio_rel)
+    mel = np.load(audio_path.replace("/audio/", "/mel/")[:-4] + ".npy")
+    spk = np.load(audio_path.replace("/audio/", "/spk_emb/")[:-4] + ".npy")
+    if spk.shape != (256,) or spk.dtype != np.float32:      # helpers.py:194 / create_dataset.py:229
+        raise ValueError(f"{row.uid}: speaker embedding must be (256,) float32, got {spk.shape} {spk.dtype}")
+    code = np.asarray(code_to_sequence(row.units.split(), code_dict), dtype=np.int64)
+    u, t, cut = trim_lengths(row.n_audio if n_audio is None else n_audio, code.shape[0], mel.shape[0])
+    return {"code": code[:u], "mel": np.ascontiguousarray(mel[:t].T), "spkr": spk}, cut
+
+
+def output_name(row: ManifestRow) -> str:
+    """pred_wav/<speaker dir>/<file> without extension, as inference.py:156 builds it from the audio path."""
+    return os.path.join("pred_wav", *row.audio_rel.split("/")[-2:])[:-4]
+
+
+def write_wav_int16(path: str, samples: np.ndarray, rate: int = SAMPLE_RATE) -> None:
+    """16-bit PCM mono RIFF, what scipy.io.wavfile.write produces for an int16 array (inference.py:164)."""
+    samples = np.ascontiguousarray(samples, dtype="<i2")
+    n = samples.size * 2
+    header = (b"RIFF" + (36 + n).to_bytes(4, "little") + b"WAVEfmt " + (16).to_bytes(4, "little") +
+              (1).to_bytes(2, "little") + (1).to_bytes(2, "little") + rate.to_bytes(4, "little") +
+              (rate * 2).to_bytes(4, "little") + (2).to_bytes(2, "little") + (16).to_bytes(2, "little") +
+              b"data" + n.to_bytes(4, "little"))
+    os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+    with open(path, "wb") as f:
+        f.write(header)
+        f.write(samples.tobytes())
+
+
+@torch.no_grad()
+def vocode_manifest(generator, manifest_path: str, out_dir: str, root: Optional[str] = None, device="cuda",
+                    max_batch: int = 64, code_dict_path: Optional[str] = None) -> List[str]:
+    """Vocode every row of a manifest and write <out_dir>/pred_wav/.../<name>.wav (int16, 16 kHz).
+    Rows with the same number of mel frames share one forward; the waveform is quantised on the device."""
+    tsv_root, rows = parse_manifest(manifest_path)
+    root = root or tsv_root
+    code_dict = load_code_dict(code_dict_path or os.path.join(os.path.dirname(manifest_path), "dict.unt.txt"))
+    items = [load_item(root, r, code_dict) for r in rows]
+    by_len: Dict[int, List[int]] = {}
+    for i, (feats, _) in enumerate(items):
+        by_len.setdefault(feats["mel"].shape[1], []).append(i)
+    written = [""] * len(rows)
+    for _, idxs in sorted(by_len.items()):
+        for s in range(0, len(idxs), max_batch):
+            grp = idxs[s:s + max_batch]
+            code = torch.from_numpy(np.stack([items[i][0]["code"] for i in grp])).to(device)
+            mel = torch.from_numpy(np.stack([items[i][0]["mel"] for i in grp])).to(device)
+            spk = torch.from_numpy(np.stack([items[i][0]["spkr"] for i in grp])).to(device)
+            _, wav16 = generator.forward_int16(code=code, mel=mel, spkr=spk)
+            wav16 = wav16.cpu().numpy()
+            for j, i in enumerate(grp):
+                path = os.path.join(out_dir, output_name(rows[i]) + ".wav")
+                write_wav_int16(path, wav16[j, :items[i][1]])
+                written[i] = path
+    return written

@@ -285,6 +285,27 @@ def test_graph_replay_equals_eager(pkg, weights, precision):
     assert torch.equal(other, ref2)
 
 
+def test_vocode_manifest_batched_equals_per_utterance(pkg, weights, tmp_path):
+    """the batched manifest caller (device-side int16) against the reference's per-utterance flow
+    (forward, * 32768, astype int16 on the host, inference.py:79-81) on the shipped sample rows."""
+    from scipy.io import wavfile
+    h, sds = weights
+    g = make_gen(pkg, h, sds["trained"], "fp32")
+    fix = os.path.join(GOLDEN, "lrs3_handoff")
+    ho = pkg.hand_off
+    paths = ho.vocode_manifest(g, os.path.join(fix, "label", "test.tsv"), str(tmp_path), root=fix, device=DEV)
+    _, rows = ho.parse_manifest(os.path.join(fix, "label", "test.tsv"))
+    code_dict = ho.load_code_dict(os.path.join(fix, "label", "dict.unt.txt"))
+    assert len(paths) == 5
+    for r, pth in zip(rows, paths):
+        assert pth.endswith(ho.output_name(r) + ".wav")
+        feats, n = ho.load_item(fix, r, code_dict)
+        y = g(**{k: torch.from_numpy(v).to(DEV).unsqueeze(0) for k, v in feats.items()})
+        expect = (y.squeeze() * 32768.0).clamp(-32768, 32767).cpu().numpy().astype("int16")
+        rate, got = wavfile.read(pth)
+        assert rate == 16000 and got.shape == (n,) and np.array_equal(got, expect)
+
+
 def test_cfg2_shape_bf16_vs_fp32_device_reference(pkg, weights):
     """configs[1] at full size (16 x 4 s): bf16 tensor-core path against the fp32
     CUDA-core mode of the same library, plus finiteness and range."""
