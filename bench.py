@@ -288,7 +288,7 @@ def main():
         stages = {}
         for name, t, fl in rows:
             if name.startswith("resblocks."):
-                key = "mrf%d" % (int(name.split(".")[1]) // len(h["resblock_kernel_sizes"]))
+                key = "mrf%d" % (int(name.split(".")[1].split()[0]) // len(h["resblock_kernel_sizes"]))
             elif name.startswith("ups."):
                 key = "ups"
             else:

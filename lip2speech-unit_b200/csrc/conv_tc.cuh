@@ -126,7 +126,7 @@ struct EpiChunk {
 
 template <int CW>
 __device__ __forceinline__ EpiChunk epi_locate(const ConvParams& p, uint32_t taddr, int b, int q_base, int n_base,
-                                               int crow, int c4, int mrows_eff) {
+                                               int crow, int c4, int mrows_eff, int row_lo = 0) {
   constexpr int LPR = CW / 4, RPI = 32 / LPR, ITERS = 32 / RPI;
   EpiChunk c;
   c.n = n_base + c4 * 4;
@@ -142,6 +142,12 @@ __device__ __forceinline__ EpiChunk epi_locate(const ConvParams& p, uint32_t tad
     const int left = mrows_eff - q0;                          // valid rows from q0 on
     const int n_ok = left <= 0 ? 0 : (left + RPI - 1) / RPI;
     c.okmask = n_ok >= ITERS ? (1u << ITERS) - 1u : (1u << n_ok) - 1u;
+    // rows below row_lo (the halo rows of a fused ResBlock tile) are not stored either
+    const int below = row_lo - q0;
+    if (below > 0) {
+      const int n_lo = (below + RPI - 1) / RPI;
+      c.okmask &= n_lo >= ITERS ? 0u : ~((1u << n_lo) - 1u);
+    }
     return c;
   }
   const long long idx0 = (long long)q0 * p.ntot + c.n + p.out_shift;
@@ -276,7 +282,7 @@ __device__ __forceinline__ void epi_finish(const ConvParams& p, const EpiChunk& 
 template <int CW, int MODE, bool PIPE>
 __device__ __forceinline__ void epilogue_item_rows(const ConvParams& p, float* tile, uint32_t t_base, int b, int q0,
                                                    int row_lim, int msub, int nt, int quad, int half, int lane,
-                                                   int n_tile_base, uint64_t* bar, uint32_t parity) {
+                                                   int n_tile_base, uint64_t* bar, uint32_t parity, int row_lo = 0) {
   constexpr int LPR = CW / 4;
   constexpr uint32_t kAll = (1u << (CW / 4)) - 1u;
   // PIPE: double-buffer the residual registers (needs the 168-register budget of the fused kernel)
@@ -287,7 +293,7 @@ __device__ __forceinline__ void epilogue_item_rows(const ConvParams& p, float* t
   const int cps = nt / CW;                    // chunks per 128-row accumulator
   auto locate = [&](int s_, int cc_) {
     return epi_locate<CW>(p, t_base + (uint32_t)(s_ * nt + cc_ * CW), b, q0 + s_ * 128 + quad * 32, n_tile_base + cc_ * CW,
-                          crow, c4, row_lim);
+                          crow, c4, row_lim, row_lo);
   };
   auto finish = [&](const EpiChunk& c, const float4 (&rv)[CW / 4], const float4 (&av)[CW / 4]) {
     const bool prof = L2S_PROF_ON;

@@ -18,6 +18,7 @@
 #include "conv_tc.cuh"
 #include "pair_tc.cuh"
 #include "frontend.cuh"
+#include "res_tc.cuh"
 
 using namespace l2s;
 
@@ -43,6 +44,9 @@ struct Knobs {
   long long epoch = 0;             // bumped by every l2s_debug_set: cached graphs of older epochs are not reused
   long long pair_smem = 220 * 1024; // shared-memory budget of the single-CTA fused plans
   long long fuse_pairs = 1;        // bf16 mode: one kernel per ResBlock (c1, c2) step
+  long long fuse_branch = 1;       // bf16 mode, C <= 64: one kernel per ResBlock (all its steps), residual stream kept in TMEM
+  long long res_mode = 0;          // whole-ResBlock plans: 0 auto, 1 two CTAs per SM, 2 one CTA per SM
+  long long res_msub = 8;          // whole-ResBlock plans: largest tile, in 128-row accumulators
   long long plan_report = 0;       // l2s_debug_conv: write the chosen plan + occupancy into the err buffer
   long long trace_ptr = 0;         // device pointer for the kernel trace of l2s_debug_conv (0: off)
   long long max_msub = 8;
@@ -97,6 +101,7 @@ struct l2s_vocoder {
   std::vector<int> ups;                        // index into convs
   std::vector<std::vector<std::vector<int>>> rb_c1, rb_c2;  // [stage][branch][dil]
   std::vector<int> stage_ch;
+  float* d_zero_bias = nullptr;                // 256 zeros: output epilogue of the whole-ResBlock kernel
   bool finalized = false;
   int device = -1, num_sms = 0;
   // device-side small weights
@@ -116,6 +121,7 @@ struct l2s_vocoder {
   std::vector<Timed> timed;
   size_t timed_used = 0;
   long long pair_launches = 0;     // fused-step launches issued by the current forward
+  long long res_launches = 0;      // whole-ResBlock launches issued by the current forward
   long long tc_launches = 0;       // all tcgen05 launches of the current forward (span_ptr slots)
   // CUDA-graph replay of the conv chain
   struct ChainGraph { int batch, frames; void* workspace; long long epoch; int seen; cudaGraphExec_t exec; };
@@ -450,6 +456,80 @@ int run_pair(l2s_vocoder* v, ConvLayer& c1, ConvLayer& c2, cudaStream_t st, int 
   return L2S_OK;
 }
 
+bool branch_geom(const l2s_vocoder* v, int i, int j, int lin, int batch, ResGeom* g) {
+  const l2s_config& c = v->cfg;
+  const ConvLayer& a = v->convs[v->rb_c1[i][j][0]];
+  int dil[kResMaxDil];
+  if (c.n_dil > kResMaxDil || a.cin != a.cout || a.cin_pad != a.cin) return false;
+  for (int m = 0; m < c.n_dil; ++m) {
+    const ConvLayer& a1 = v->convs[v->rb_c1[i][j][m]];
+    const ConvLayer& a2 = v->convs[v->rb_c2[i][j][m]];
+    if (a1.k != a.k || a2.k != a.k || a2.dil != 1) return false;
+    dil[m] = a1.dil;
+  }
+  return res_plan(a.cin, a.k, c.n_dil, dil, lin, batch, (int)g_knobs.res_mode, (int)g_knobs.res_msub, g);
+}
+
+// Every ResBlock of stage i runs as one whole-ResBlock kernel (bf16 mode, C <= 64, a plan exists for each branch).
+bool stage_branch_fused(const l2s_vocoder* v, int i, int lin, int batch) {
+  if (!pairs_fused(v) || !g_knobs.fuse_branch || v->stage_ch[i] > 64) return false;
+  for (int j = 0; j < v->cfg.n_rk; ++j) {
+    ResGeom g;
+    if (!branch_geom(v, i, j, lin, batch, &g)) return false;
+  }
+  return true;
+}
+
+// One whole ResBlock: x -> x + sum of its steps, then the branch sum / mean epilogue.
+int run_res(l2s_vocoder* v, int i, int j, cudaStream_t st, int batch, int lin, const float* x, float* out_raw, void* out_act,
+            const float* acc_in, float div, float slope) {
+  const l2s_config& c = v->cfg;
+  ResParams P{};
+  if (!branch_geom(v, i, j, lin, batch, &P.g)) return L2S_ERR_UNSUPPORTED;
+  const ResGeom& g = P.g;
+  ResMaps maps;
+  double flops = 0.0;
+  for (int m = 0; m < c.n_dil; ++m) {
+    ConvLayer& c1 = v->convs[v->rb_c1[i][j][m]];
+    ConvLayer& c2 = v->convs[v->rb_c2[i][j][m]];
+    if (!ensure_w_map(c1, g.rb, g.c, g.tb) || !ensure_w_map(c2, g.rb, g.c, g.tb))
+      return fail(v, L2S_ERR_CUDA, "cuTensorMapEncodeTiled failed for the weights of " + c1.name);
+    maps.w[2 * m] = c1.tmW;
+    maps.w[2 * m + 1] = c2.tmW;
+    P.bias1[m] = c1.bias_dev;
+    P.bias2[m] = c2.bias_dev;
+    flops += 4.0 * c1.cin * c1.cout * c1.k * (double)batch * lin;
+  }
+  for (int m = 2 * c.n_dil; m < 2 * kResMaxDil; ++m) maps.w[m] = maps.w[0];
+  ConvParams& p = P.c;
+  p.bias = v->d_zero_bias;   // the kernel folds every bias into its TMEM-resident stream
+  p.out_raw = out_raw;
+  p.out_act = out_act;
+  p.acc_in = acc_in;
+  p.batch = batch;
+  p.lin = lin;
+  p.cin_pad = g.c;
+  p.ntaps = g.k;
+  p.ntot = g.c;
+  p.mrows = lin;
+  p.out_shift = 0;
+  p.out_valid = (long long)lin * g.c;
+  p.div = div;
+  p.slope = slope;
+  P.x = x;
+  P.span = g_knobs.span_ptr ? reinterpret_cast<unsigned long long*>(g_knobs.span_ptr) + 2 * v->tc_launches : nullptr;
+  ++v->tc_launches;
+  P.trace = (g_knobs.trace_ptr && g_knobs.trace_launch == v->res_launches) ? reinterpret_cast<long long*>(g_knobs.trace_ptr) : nullptr;
+  ++v->res_launches;
+  const std::string nm = v->convs[v->rb_c1[i][j][0]].name;
+  timed_begin(v, st, nm.substr(0, nm.find(".convs1")) + " (whole)", flops);
+  const int ctas = g_knobs.max_ctas > 0 ? (int)g_knobs.max_ctas : v->num_sms;
+  cudaError_t e = launch_res_tc(P, maps, ctas, st);
+  timed_end(v, st);
+  if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, std::string("launch ResBlock ") + nm + ": " + cudaGetErrorString(e));
+  return L2S_OK;
+}
+
 struct Workspace {
   void* cond;
   void* ma[2];
@@ -513,7 +593,9 @@ int run_chain(l2s_vocoder* v, cudaStream_t st, const Workspace& ws, int batch, i
   long long len = frames;
   for (int i = 0; i < c.n_ups; ++i) {
     ConvLayer& up = v->convs[v->ups[i]];
-    rc = run_conv(v, up, st, batch, (int)len, ws.ma[cur], ws.x, ws.xa, nullptr, nullptr, 1.f, 0.1f);
+    // whole-ResBlock kernels activate the fp32 stream themselves: the upsampler then skips the bf16 copy
+    const bool whole = stage_branch_fused(v, i, (int)(len * c.up_rates[i]), batch);
+    rc = run_conv(v, up, st, batch, (int)len, ws.ma[cur], ws.x, whole ? nullptr : ws.xa, nullptr, nullptr, 1.f, 0.1f);
     if (rc) return rc;
     len *= c.up_rates[i];
     const int ch = v->stage_ch[i];
@@ -523,6 +605,24 @@ int run_chain(l2s_vocoder* v, cudaStream_t st, const Workspace& ws, int batch, i
     // A fused step reads its activated input WITH HALO while other CTAs already write the activated
     // output, so fused stages ping-pong the activated buffers (xa -> ya -> ta -> ...); the fp32
     // residual is updated in place (each element is read and written by the same thread).
+    if (whole) {
+      for (int j = 0; j < c.n_rk; ++j) {
+        float* o_raw;
+        void* o_act = nullptr;
+        const float* a_in = nullptr;
+        float dv = 1.f;
+        if (j < c.n_rk - 1) { o_raw = ws.acc; a_in = j == 0 ? nullptr : ws.acc; }
+        else {
+          o_raw = want_raw ? ws.acc : nullptr;
+          o_act = last_stage ? nullptr : ws.ma[cur ^ 1];
+          a_in = c.n_rk == 1 ? nullptr : ws.acc;
+          dv = (float)c.n_rk;
+        }
+        rc = run_res(v, i, j, st, batch, (int)len, ws.x, o_raw, o_act, a_in, dv, 0.1f);
+        if (rc == L2S_ERR_UNSUPPORTED) return fail(v, L2S_ERR_STATE, "whole-ResBlock plan vanished");
+        if (rc) return rc;
+      }
+    }
     bool stage_fused = pairs_fused(v);
     for (int j = 0; stage_fused && j < c.n_rk; ++j)
       for (int m = 0; m < c.n_dil; ++m) {
@@ -533,7 +633,7 @@ int run_chain(l2s_vocoder* v, cudaStream_t st, const Workspace& ws, int batch, i
             !pair_plan(a1.cin, a1.k, a1.dil, (int)len, batch, (int)g_knobs.pair_smem, g_knobs.dual != 0, g_knobs.cluster != 0, g_knobs.alias_at != 0, false, false, &pg))
           stage_fused = false;
       }
-    for (int j = 0; j < c.n_rk; ++j) {
+    for (int j = 0; !whole && j < c.n_rk; ++j) {
       for (int m = 0; m < c.n_dil; ++m) {
         ConvLayer& c1 = v->convs[v->rb_c1[i][j][m]];
         ConvLayer& c2 = v->convs[v->rb_c2[i][j][m]];
@@ -613,6 +713,7 @@ int forward_impl(l2s_vocoder* v, void* stream, const int64_t* code, const void* 
   v->taps.clear();
   v->timed_used = 0;
   v->pair_launches = 0;
+  v->res_launches = 0;
   v->tc_launches = 0;
   cudaError_t e;
   ConvLayer& pre = v->convs[v->conv_pre];
@@ -819,6 +920,11 @@ int l2s_finalize(l2s_vocoder* v, int device) {
     if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, cudaGetErrorString(e));
   }
   {
+    const std::vector<float> zeros(256, 0.f);
+    v->d_zero_bias = dev_upload<float>(v, zeros.data(), zeros.size(), &e);
+    if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, cudaGetErrorString(e));
+  }
+  {
     const std::vector<float>& d = v->weights["dict.weight"];
     v->d_dict = dev_upload<float>(v, d.data(), d.size(), &e);
     if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, cudaGetErrorString(e));
@@ -901,10 +1007,14 @@ int l2s_poll_index_error(l2s_vocoder* v) {
 
 int32_t l2s_launch_count(l2s_vocoder* v, int32_t batch, int32_t frames) {
   if (!v) return -1;
-  (void)batch; (void)frames;
   const l2s_config& c = v->cfg;
   int n = (int)v->convs.size() + 1 /* post */ + 1 /* cond */;
   if (pairs_fused(v)) n -= c.n_ups * c.n_rk * c.n_dil;   // one launch per (c1, c2) step
+  long long len = frames;
+  for (int i = 0; i < c.n_ups; ++i) {
+    len *= c.up_rates[i];
+    if (batch > 0 && frames > 0 && stage_branch_fused(v, i, (int)len, batch)) n -= c.n_rk * (c.n_dil - 1);   // one per ResBlock
+  }
   if (c.variant == L2S_VARIANT_MULTI_INPUT && c.multispkr) n += 1;
   return n;
 }
@@ -1025,6 +1135,9 @@ int l2s_debug_set(const char* key, int64_t value) {
   else if (k == "sa_min") g_knobs.sa_min = value;
   else if (k == "dual") g_knobs.dual = value;
   else if (k == "fuse_pairs") g_knobs.fuse_pairs = value;
+  else if (k == "fuse_branch") g_knobs.fuse_branch = value;
+  else if (k == "res_mode") g_knobs.res_mode = value;
+  else if (k == "res_msub") g_knobs.res_msub = value;
   else if (k == "cluster") g_knobs.cluster = value;
   else if (k == "alias_at") g_knobs.alias_at = value;
   else if (k == "epi_tma") g_knobs.epi_tma = value;

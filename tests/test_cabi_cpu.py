@@ -37,8 +37,12 @@ def test_create_validates_without_cuda(pkg):
     hnd = C.c_void_p()
     assert lib.l2s_create(C.byref(cfg), C.byref(hnd)) == pkg._cabi.OK
     assert lib.l2s_hop(hnd) == 160
-    # bf16 mode: 1 speaker projection + 1 conditioning + conv_pre + 5 ups + 45 fused ResBlock steps + conv_post
-    assert lib.l2s_launch_count(hnd, 16, 400) == 54
+    # bf16 mode: 1 speaker projection + 1 conditioning + conv_pre + 5 ups + conv_post + 18 fused ResBlock steps
+    # (C = 256, 128: one launch per step) + 9 whole-ResBlock kernels (C <= 64: one launch per ResBlock)
+    assert lib.l2s_launch_count(hnd, 16, 400) == 36
+    assert lib.l2s_debug_set(b"fuse_branch", 0) == pkg._cabi.OK
+    assert lib.l2s_launch_count(hnd, 16, 400) == 54     # every ResBlock step its own launch
+    assert lib.l2s_debug_set(b"fuse_branch", 1) == pkg._cabi.OK
     cfg32 = _cfg(pkg)
     cfg32.precision = pkg._cabi.PREC_FP32
     h32 = C.c_void_p()
