@@ -39,6 +39,7 @@ struct ConvParams {
   long long out_shift, out_valid;
   float div, slope;
   int act_f32;           // tcgen05 kernel only: 1 = operands / activated output are fp32 (tf32 mode), 0 = bf16
+  int pf;               // prefetch experiment bits: 1 = L2 bulk prefetch of residual tiles, 2 = L1 prefetch of the next chunk
 };
 
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }

@@ -201,6 +201,27 @@ __device__ __forceinline__ void epi_load_acc(const ConvParams& p, const EpiChunk
   }
 }
 
+// The same lines pulled into L1 ahead of time, holding no registers (80-register kernels cannot double-buffer the
+// loads above; without this every chunk pays a full memory latency).  One lane per row segment issues.
+template <int CW, int MODE>
+__device__ __forceinline__ void epi_prefetch(const ConvParams& p, const EpiChunk& c, int c4) {
+  constexpr int LPR = CW / 4, RPI = 32 / LPR, ITERS = 32 / RPI;
+  if (c4 != 0) return;
+  const int step = RPI * p.ntot;
+  if constexpr ((MODE & kEpiRes) != 0) {
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i)
+      if ((c.okmask >> i) & 1u) prefetch_l1(p.res + c.e0 + (long long)i * step);
+  }
+  if constexpr ((MODE & kEpiAcc) != 0) {
+    if (p.acc_in) {
+#pragma unroll
+      for (int i = 0; i < ITERS; ++i)
+        if ((c.okmask >> i) & 1u) prefetch_l1(p.acc_in + c.e0 + (long long)i * step);
+    }
+  }
+}
+
 // Stage 2: accumulator rows -> transpose tile (one row per lane, swizzled float4 slots).
 template <int CW>
 __device__ __forceinline__ void epi_stage(float4* tile4, uint32_t taddr, int lane) {
@@ -322,6 +343,7 @@ __device__ __forceinline__ void epilogue_item_rows(const ConvParams& p, float* t
     while (cc >= cps) { cc -= cps; ++s; }
     bool more = s < msub;
     epi_load_acc<CW, MODE>(p, ca, av);
+    if (!kPipe && more && (p.pf & 2)) epi_prefetch<CW, MODE>(p, locate(s, cc), c4);   // experiment: next chunk's lines -> L1
     epi_stage<CW>(tile4, ca.taddr, lane);
     if (kPipe && more) { cb = locate(s, cc); epi_load_res<CW, MODE>(p, cb, rvb); }
     __syncwarp();
@@ -629,6 +651,7 @@ struct TcTune {
   int sa_min = 0;              // force at least this many slab ring slots when they fit
   int dual = 1;                // try the two-CTAs-per-SM plan first
   int max_ctas = 0;            // 0: number of SMs
+  int max_nt = 256;            // widest column tile (MMA N)
 };
 
 // Shape-only planning (no device pointers): valid for any batch with the same (lin, mrows).
@@ -645,6 +668,7 @@ inline bool tc_plan_with(const ConvParams& c, int batch, const TcTune& tune, int
   g.kc = c.cin_pad * g.esz / g.rb;
   g.k16 = g.rb / 32;
   g.nt = c.ntot <= 256 ? c.ntot : 256;
+  if (g.nt > tune.max_nt && tune.max_nt >= 16) g.nt = tune.max_nt;
   while (c.ntot % g.nt != 0) g.nt -= 16;
   if (g.nt > acc_cols_cap) return false;
   g.n_ntiles = c.ntot / g.nt;

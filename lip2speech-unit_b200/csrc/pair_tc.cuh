@@ -231,6 +231,30 @@ __device__ __forceinline__ void epilogue_item_tma(const ConvParams& p, const Pai
   }
 }
 
+// MMAs of one weight stage for all msub accumulators with every stride and the instruction descriptor as
+// immediates (C >= 64: 128-byte operand rows, four K = 16 slices per 64-channel chunk).
+template <int C>
+__device__ __forceinline__ void pair_issue_stage(bool leader, int msub, uint32_t desc_hi, uint32_t a_lo, uint32_t tap_step,
+                                                 uint32_t b_lo, int tap0, int t_end, uint32_t first_or, uint32_t d_base) {
+  constexpr uint32_t kSubStep = (128u * 128u) >> 4;
+  constexpr uint32_t kTapW = ((uint32_t)C * 128u) >> 4;
+  constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)C >> 3) << 17) | ((128u >> 4) << 24);
+  uint32_t a_tap = a_lo + (uint32_t)tap0 * tap_step;
+  for (int t = 0; t < t_end; ++t, b_lo += kTapW, a_tap += tap_step) {
+    const uint32_t first = first_or | (uint32_t)(tap0 + t);
+    uint32_t a_sub = a_tap;
+    uint32_t d_addr = d_base;
+    for (int s = 0; s < msub; ++s, a_sub += kSubStep, d_addr += (uint32_t)C) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(a_sub + 2u * k);
+        const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2u * k);
+        if (leader) umma_bf16(d_addr, da, db, kIdesc, (first | (uint32_t)k) != 0u ? 1u : 0u);
+      }
+    }
+  }
+}
+
 template <int MODE, bool DUAL, bool EPI_TMA>
 __global__ void __maxnreg__(DUAL ? 80 : 168)
 pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
@@ -405,7 +429,9 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           uint32_t b_lo = desc_lo_fixed | ((smem_u32(stageB + (size_t)ib * g.bstage_bytes) & 0x3FFFFu) >> 4);
           const int t_end = min(g.tb, g.k - ts * g.tb);
-          for (int t = 0; t < t_end; ++t, b_lo += tapw_step) {
+          if (g.c == 256) { pair_issue_stage<256>(leader, g.msub, desc_hi, a_lo, (uint32_t)g.dil * row_step, b_lo, ts * g.tb, t_end, (uint32_t)kc, tmem_base); }
+          else if (g.c == 128) { pair_issue_stage<128>(leader, g.msub, desc_hi, a_lo, (uint32_t)g.dil * row_step, b_lo, ts * g.tb, t_end, (uint32_t)kc, tmem_base); }
+          else for (int t = 0; t < t_end; ++t, b_lo += tapw_step) {
             const int tap = ts * g.tb + t;
             uint32_t a_sub = a_lo + (uint32_t)(tap * g.dil) * row_step;
             const uint32_t first = (uint32_t)(kc | tap);
@@ -443,7 +469,9 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           uint32_t b_lo = desc_lo_fixed | ((smem_u32(stageB + (size_t)ib * g.bstage_bytes) & 0x3FFFFu) >> 4);
           const int t_end = min(g.tb, g.k - ts * g.tb);
-          for (int t = 0; t < t_end; ++t, b_lo += tapw_step) {
+          if (g.c == 256) { pair_issue_stage<256>(leader, g.msub, desc_hi, t_lo, row_step, b_lo, ts * g.tb, t_end, (uint32_t)kc, tmem_base + (uint32_t)acc_cols); }
+          else if (g.c == 128) { pair_issue_stage<128>(leader, g.msub, desc_hi, t_lo, row_step, b_lo, ts * g.tb, t_end, (uint32_t)kc, tmem_base + (uint32_t)acc_cols); }
+          else for (int t = 0; t < t_end; ++t, b_lo += tapw_step) {
             const int tap = ts * g.tb + t;
             uint32_t a_sub = t_lo + (uint32_t)tap * row_step;
             const uint32_t first = (uint32_t)(kc | tap);

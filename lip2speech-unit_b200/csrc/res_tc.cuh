@@ -291,20 +291,30 @@ __device__ __forceinline__ void res_output(const ConvParams& p, float* tile, uin
   }
 }
 
-// MMAs of one weight stage (taps tap0 .. tap0 + t_end) for all msub accumulators.
-template <int K16>
-__device__ __forceinline__ void res_issue_stage(bool leader, const ResGeom& g, uint32_t desc_hi, uint32_t a_tap0_lo,
-                                                uint32_t tap_step, uint32_t b_lo, int tap0, int t_end, uint32_t d_base,
-                                                uint32_t accumulate_all) {
-  const uint32_t sub_step = (uint32_t)(128 * g.rb) >> 4;
-  const uint32_t tapw_step = (uint32_t)(g.c * g.rb) >> 4;
-  for (int t = 0; t < t_end; ++t, b_lo += tapw_step) {
-    const int tap = tap0 + t;
-    uint32_t a_sub = a_tap0_lo + (uint32_t)tap * tap_step;
-    const uint32_t first = accumulate_all | (uint32_t)tap;
+// MMAs of one weight stage (taps tap0 .. tap0 + t_end) for all msub accumulators.  Templated on C so that the
+// instruction descriptor and every descriptor stride are immediates: with run-time values the compiler re-loaded
+// them from the constant bank next to every UTCHMMA, and those dependent loads (not the tensor core) set the pace
+// of these small N = C MMAs.
+template <int C>
+__device__ __forceinline__ void res_issue_stage(bool leader, int msub, uint32_t desc_hi, uint32_t a_tap0_lo, uint32_t tap_step,
+                                                uint32_t b_lo, int tap0, int t_end, uint32_t d_base) {
+  constexpr int K16 = C / 16;
+  constexpr uint32_t kRb = 2 * C;
+  constexpr uint32_t kSubStep = (128u * kRb) >> 4;
+  constexpr uint32_t kTapW = ((uint32_t)C * kRb) >> 4;
+  constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)C >> 3) << 17) | ((128u >> 4) << 24);
+  uint32_t a_tap = a_tap0_lo + (uint32_t)tap0 * tap_step;
+  for (int t = 0; t < t_end; ++t, b_lo += kTapW, a_tap += tap_step) {
+    uint32_t a_sub = a_tap;
     uint32_t d_addr = d_base;
-    for (int s = 0; s < g.msub; ++s, a_sub += sub_step, d_addr += (uint32_t)g.c)
-      issue_chunk<K16>(leader, d_addr, desc_hi, a_sub, b_lo, g.idesc, first);
+    for (int s = 0; s < msub; ++s, a_sub += kSubStep, d_addr += (uint32_t)C) {
+#pragma unroll
+      for (int k = 0; k < K16; ++k) {
+        const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(a_sub + 2u * k);
+        const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2u * k);
+        if (leader) umma_bf16(d_addr, da, db, kIdesc, 1u);    // both convs accumulate: D1 starts as the bias, X as x
+      }
+    }
   }
 }
 
@@ -426,9 +436,9 @@ res_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
           tc_fence_after();
           const uint32_t b_lo = desc_lo_fixed | ((smem_u32(stageB + (size_t)ib * g.bstage_bytes) & 0x3FFFFu) >> 4);
           const int t_end = min(g.tb, g.k - ts * g.tb);
-          if (g.k16 == 4) res_issue_stage<4>(leader, g, desc_hi, a_tap0, (uint32_t)dil * row_step, b_lo, ts * g.tb, t_end, d_base, 1u);
-          else if (g.k16 == 2) res_issue_stage<2>(leader, g, desc_hi, a_tap0, (uint32_t)dil * row_step, b_lo, ts * g.tb, t_end, d_base, 1u);
-          else res_issue_stage<1>(leader, g, desc_hi, a_tap0, (uint32_t)dil * row_step, b_lo, ts * g.tb, t_end, d_base, 1u);
+          if (g.c == 64) res_issue_stage<64>(leader, g.msub, desc_hi, a_tap0, (uint32_t)dil * row_step, b_lo, ts * g.tb, t_end, d_base);
+          else if (g.c == 32) res_issue_stage<32>(leader, g.msub, desc_hi, a_tap0, (uint32_t)dil * row_step, b_lo, ts * g.tb, t_end, d_base);
+          else res_issue_stage<16>(leader, g.msub, desc_hi, a_tap0, (uint32_t)dil * row_step, b_lo, ts * g.tb, t_end, d_base);
           if (leader) umma_commit(&b_empty[ib]);
           if (++ib == g.sb) { ib = 0; pb ^= 1u; }
         }

@@ -50,6 +50,8 @@ struct Knobs {
   long long plan_report = 0;       // l2s_debug_conv: write the chosen plan + occupancy into the err buffer
   long long trace_ptr = 0;         // device pointer for the kernel trace of l2s_debug_conv (0: off)
   long long max_msub = 8;
+  long long max_nt = 256;
+  long long epi_pf = 0;            // fused-step kernels: 1 = L2 prefetch of the residual tile, 2 = L1 prefetch of the next chunk
   long long slab_cap = 40960;
   long long max_ctas = 0;
   long long embed_tap = 0;
@@ -299,6 +301,7 @@ void pack_conv(const ConvLayer& L, const std::vector<float>& w, const std::vecto
 TcTune current_tune(const l2s_vocoder* v) {
   TcTune t;
   t.max_msub = (int)g_knobs.max_msub;
+  t.max_nt = (int)g_knobs.max_nt;
   t.slab_cap = (int)g_knobs.slab_cap;
   t.per_tap = (int)g_knobs.per_tap;
   t.sa_min = (int)g_knobs.sa_min;
@@ -430,6 +433,7 @@ int run_pair(l2s_vocoder* v, ConvLayer& c1, ConvLayer& c2, cudaStream_t st, int 
   p.out_valid = (long long)lin * c2.cout;
   p.div = div;
   p.slope = slope;
+  p.pf = (int)g_knobs.epi_pf;
   timed_begin(v, st, c1.name + "+c2", 4.0 * c1.cin * c1.cout * c1.k * (double)batch * lin);
   const int ctas = g_knobs.max_ctas > 0 ? (int)g_knobs.max_ctas : v->num_sms;
   PairEpiMaps em{};
@@ -1150,6 +1154,8 @@ int l2s_debug_set(const char* key, int64_t value) {
   else if (k == "plan_report") g_knobs.plan_report = value;
   else if (k == "trace_ptr") g_knobs.trace_ptr = value;
   else if (k == "max_msub") g_knobs.max_msub = value;
+  else if (k == "max_nt") g_knobs.max_nt = value;
+  else if (k == "epi_pf") g_knobs.epi_pf = value;
   else if (k == "slab_cap") g_knobs.slab_cap = value;
   else if (k == "max_ctas") g_knobs.max_ctas = value;
   else if (k == "embed_tap") g_knobs.embed_tap = value;
