@@ -301,7 +301,7 @@ def main():
         if args.layers:
             for name, t, fl in rows:
                 sys.stderr.write(f"{name:28s} {t * 1e3:9.1f} us  {fl / max(t, 1e-9) / 1e9:8.1f} TFLOP/s\n")
-        kernel = {"bf16": "pair_tc_kernel (fused ResBlock step: two tcgen05 tap-offset convs) + conv_tc_kernel (conv_pre, ups)",
+        kernel = {"bf16": "pair_tc_kernel (fused ResBlock step, C >= 128) + res_tc_kernel (whole ResBlock, C <= 64) + conv_tc_kernel (conv_pre, ups): tcgen05 tap-offset convolutions",
                   "tf32": "conv_tc_kernel (tcgen05 kind::tf32 tap-offset conv)", "fp32": "conv_simt_kernel"}[args.precision]
         traffic, traffic_src = ncu_traffic() if args.precision == "bf16" else (None, None)
         line = {
