@@ -29,18 +29,22 @@ __device__ __forceinline__ float load_mel(const void* mel, int dtype, long long 
   return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(mel)[i]);
 }
 
-// out[b][c] = bias[c] + sum_k spkr[b][k] * W[c][k].  One block per utterance.
+// out[b][c] = bias[c] + sum_k spkr[b][k] * W[c][k].  One block per utterance, one warp per output channel at a
+// time: the lanes read a weight row contiguously and the partial sums are combined with shuffles (fixed order).
 __global__ void spk_project_kernel(const float* __restrict__ spkr, const float* __restrict__ w,
                                    const float* __restrict__ bias, float* __restrict__ out, int spk_dim, int e) {
   extern __shared__ float s_in[];
   const int b = blockIdx.x;
   for (int k = threadIdx.x; k < spk_dim; k += blockDim.x) s_in[k] = spkr[(long long)b * spk_dim + k];
   __syncthreads();
-  for (int c = threadIdx.x; c < e; c += blockDim.x) {
-    float acc = bias[c];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+  for (int c = warp; c < e; c += n_warps) {
     const float* wr = w + (long long)c * spk_dim;
-    for (int k = 0; k < spk_dim; ++k) acc = fmaf(s_in[k], wr[k], acc);
-    out[(long long)b * e + c] = acc;
+    float acc = 0.f;
+    for (int k = lane; k < spk_dim; k += 32) acc = fmaf(s_in[k], wr[k], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[(long long)b * e + c] = acc + bias[c];
   }
 }
 
@@ -60,23 +64,30 @@ struct CondParams {
   int batch, units, frames, e, num_mels, num_embeddings, cin_pad, has_spk;
 };
 
-constexpr int kCondFrames = 8;   // frames per block (even start).  Measured on cfg2: 8 -> 82 us, 16 -> 114 us, 32 -> 158 us:
-                                 // the kernel is parallelism bound (few warps per SM), not bound by re-reading the weights from L2.
+constexpr int kCondFrames = 8;   // frames per block (even start)
 constexpr int kCondE = 128;      // embedding_dim this kernel is specialised for
+constexpr int kCondSplit = 4;    // K (input channel) split: 4 thread groups of 128 each own a quarter of the reduction
+constexpr int kCondThreads = kCondE * kCondSplit;
 
+// One block = 8 frames x 128 output channels x 4 K-quarters.  With one thread per output channel (the first
+// version) a forward put only ~20 warps on an SM and every warp walked 640 dependent weight loads: 82 us for cfg2,
+// latency bound.  Splitting the reductions over four thread groups quadruples the warps for the same loads.
 template <typename Ta>
-__global__ void __launch_bounds__(kCondE) cond_multi_kernel(const CondParams p) {
+__global__ void __launch_bounds__(kCondThreads) cond_multi_kernel(const CondParams p) {
   __shared__ float s_emb[kCondFrames / 2 + 2][kCondE];   // units i0-1 .. i0+4
   __shared__ float s_act[kCondFrames][kCondE];
+  __shared__ float s_part[kCondSplit][kCondFrames][kCondE];
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * kCondFrames;
   const int i0 = t0 >> 1;
-  const int c = threadIdx.x;
+  const int c = threadIdx.x & (kCondE - 1);
+  const int g = threadIdx.x >> 7;
+  constexpr int KQ = kCondE / kCondSplit;                 // input channels per group
+  constexpr int FPG = kCondFrames / kCondSplit;           // frames each group finishes
   Ta* cond = reinterpret_cast<Ta*>(p.cond) + ((long long)b * p.frames) * p.cin_pad;
 
   // (1) gather: an exact row copy of the unit table
-#pragma unroll
-  for (int r = 0; r < kCondFrames / 2 + 2; ++r) {
+  for (int r = g; r < kCondFrames / 2 + 2; r += kCondSplit) {
     const int i = i0 - 1 + r;
     float v = 0.f;
     if (i >= 0 && i < p.units) {
@@ -94,11 +105,10 @@ __global__ void __launch_bounds__(kCondE) cond_multi_kernel(const CondParams p) 
 
   // (2) ConvTranspose1d(E,E,4,stride 2,pad 1): out[2i] = W1 x[i] + W3 x[i-1], out[2i+1] = W2 x[i] + W0 x[i+1]
   float acc[kCondFrames];
-  const float bias = p.wt_bias[c];
 #pragma unroll
-  for (int f = 0; f < kCondFrames; ++f) acc[f] = bias;
+  for (int f = 0; f < kCondFrames; ++f) acc[f] = 0.f;
 #pragma unroll 4
-  for (int ci = 0; ci < kCondE; ++ci) {
+  for (int ci = g * KQ; ci < (g + 1) * KQ; ++ci) {
     const float w0 = p.wt[(0 * kCondE + ci) * kCondE + c];
     const float w1 = p.wt[(1 * kCondE + ci) * kCondE + c];
     const float w2 = p.wt[(2 * kCondE + ci) * kCondE + c];
@@ -110,40 +120,52 @@ __global__ void __launch_bounds__(kCondE) cond_multi_kernel(const CondParams p) 
       acc[2 * h + 1] = fmaf(x0, w2, fmaf(xp, w0, acc[2 * h + 1]));
     }
   }
-  // (3) exact (erf) GELU
 #pragma unroll
-  for (int f = 0; f < kCondFrames; ++f) {
-    const float y = acc[f];
-    s_act[f][c] = 0.5f * y * (1.0f + erff(y * 0.70710678118654752440f));
+  for (int f = 0; f < kCondFrames; ++f) s_part[g][f][c] = acc[f];
+  __syncthreads();
+  // (3) reduce the four partial sums (fixed order), bias, exact (erf) GELU
+  {
+    const float bias = p.wt_bias[c];
+#pragma unroll
+    for (int j = 0; j < FPG; ++j) {
+      const int f = g * FPG + j;
+      const float y = bias + ((s_part[0][f][c] + s_part[1][f][c]) + (s_part[2][f][c] + s_part[3][f][c]));
+      s_act[f][c] = 0.5f * y * (1.0f + erff(y * 0.70710678118654752440f));
+    }
   }
   __syncthreads();
-  // (4) fc
-  const float fb = p.fc_bias[c];
+  // (4) fc, same split
 #pragma unroll
-  for (int f = 0; f < kCondFrames; ++f) acc[f] = fb;
+  for (int f = 0; f < kCondFrames; ++f) acc[f] = 0.f;
 #pragma unroll 8
-  for (int k = 0; k < kCondE; ++k) {
+  for (int k = g * KQ; k < (g + 1) * KQ; ++k) {
     const float w = p.fc_t[k * kCondE + c];
 #pragma unroll
     for (int f = 0; f < kCondFrames; ++f) acc[f] = fmaf(s_act[f][k], w, acc[f]);
   }
-  // (5) concat: [mel | code feats | speaker | zero pad]
+#pragma unroll
+  for (int f = 0; f < kCondFrames; ++f) s_part[g][f][c] = acc[f];
+  __syncthreads();
+  // (5) reduce + concat: [mel | code feats | speaker | zero pad]
+  const float fb = p.fc_bias[c];
   const float sv = p.has_spk ? p.spk_vec[(long long)b * kCondE + c] : 0.f;
   const int spk_base = p.num_mels + kCondE;
 #pragma unroll
-  for (int f = 0; f < kCondFrames; ++f) {
+  for (int j = 0; j < FPG; ++j) {
+    const int f = g * FPG + j;
     const int t = t0 + f;
     if (t >= p.frames) break;
+    const float y = fb + ((s_part[0][f][c] + s_part[1][f][c]) + (s_part[2][f][c] + s_part[3][f][c]));
     Ta* row = cond + (long long)t * p.cin_pad;
-    row[p.num_mels + c] = to_act<Ta>(acc[f]);
+    row[p.num_mels + c] = to_act<Ta>(y);
     if (p.has_spk) row[spk_base + c] = to_act<Ta>(sv);
   }
   const int tail0 = spk_base + (p.has_spk ? kCondE : 0);
-  for (int idx = c; idx < kCondFrames * (p.cin_pad - tail0); idx += kCondE) {
+  for (int idx = threadIdx.x; idx < kCondFrames * (p.cin_pad - tail0); idx += kCondThreads) {
     const int f = idx / (p.cin_pad - tail0), ch = tail0 + idx % (p.cin_pad - tail0);
     if (t0 + f < p.frames) cond[(long long)(t0 + f) * p.cin_pad + ch] = to_act<Ta>(0.f);
   }
-  for (int idx = c; idx < kCondFrames * p.num_mels; idx += kCondE) {
+  for (int idx = threadIdx.x; idx < kCondFrames * p.num_mels; idx += kCondThreads) {
     const int m = idx / kCondFrames, f = idx % kCondFrames;
     const int t = t0 + f;
     if (t < p.frames)

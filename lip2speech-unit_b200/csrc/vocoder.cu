@@ -727,7 +727,7 @@ int forward_impl(l2s_vocoder* v, void* stream, const int64_t* code, const void* 
   float* embed_tap = g_knobs.embed_tap ? ws.embed : nullptr;
   if (multi) {
     if (c.multispkr) {
-      spk_project_kernel<<<batch, 128, c.spk_dim * sizeof(float), st>>>((const float*)spkr, v->d_spk_w, v->d_spk_b, ws.spk_vec,
+      spk_project_kernel<<<batch, 512, c.spk_dim * sizeof(float), st>>>((const float*)spkr, v->d_spk_w, v->d_spk_b, ws.spk_vec,
                                                                         c.spk_dim, E);
     }
     CondParams cp{};
@@ -746,8 +746,8 @@ int forward_impl(l2s_vocoder* v, void* stream, const int64_t* code, const void* 
     cp.batch = batch; cp.units = units; cp.frames = frames; cp.e = E; cp.num_mels = c.num_mels;
     cp.num_embeddings = c.num_embeddings; cp.cin_pad = pre.cin_pad; cp.has_spk = c.multispkr ? 1 : 0;
     dim3 grid((frames + kCondFrames - 1) / kCondFrames, batch);
-    if (bf) cond_multi_kernel<__nv_bfloat16><<<grid, kCondE, 0, st>>>(cp);
-    else cond_multi_kernel<float><<<grid, kCondE, 0, st>>>(cp);
+    if (bf) cond_multi_kernel<__nv_bfloat16><<<grid, kCondThreads, 0, st>>>(cp);
+    else cond_multi_kernel<float><<<grid, kCondThreads, 0, st>>>(cp);
   } else {
     CondUnitParams cp{};
     cp.code = (const long long*)code;
