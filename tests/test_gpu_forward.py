@@ -367,6 +367,58 @@ def test_vocode_manifest_batched_equals_per_utterance(pkg, weights, tmp_path):
         assert rate == 16000 and got.shape == (n,) and np.array_equal(got, expect)
 
 
+@pytest.mark.parametrize("precision", ["bf16", "tf32", "fp32"])
+@pytest.mark.parametrize("batch,frames", [(1, 2), (3, 34), (2, 514)])
+def test_guard_bands_stay_intact(pkg, weights, precision, batch, frames):
+    """No sanitizer on this pool: call the C ABI with the workspace and the output embedded in larger buffers filled
+    with a canary pattern.  Every kernel (TMA zero-fill boxes, halo rows, tile tails, polyphase edges) must leave the
+    bytes before and after both buffers untouched, and the result must equal the host class's forward."""
+    h, sds = weights
+    g = make_gen(pkg, h, sds["trained"], precision)
+    code, mel, spkr = vo.synthetic_inputs(batch, frames, seed=61)
+    cd, md, sp = code.to(DEV), mel.to(DEV), spkr.to(DEV)
+    want = g(code=cd, mel=md, spkr=sp)
+    eng = g._engine(torch.device(DEV))
+    lib = eng.lib
+    need = int(lib.l2s_workspace_bytes(eng.handle, batch, frames))
+    guard = 1 << 20
+    big = torch.full((need + 2 * guard,), 0xA5, dtype=torch.uint8, device=DEV)
+    n_out = batch * eng.hop * frames
+    out_big = torch.full((n_out + 2 * 4096,), -1234.5, dtype=torch.float32, device=DEV)
+    ws_ptr = big.data_ptr() + guard            # torch allocations are 512-byte aligned, the guard keeps that
+    out_ptr = out_big.data_ptr() + 4096 * 4
+    st = lib.l2s_forward(eng.handle, torch.cuda.current_stream().cuda_stream, cd.data_ptr(), md.data_ptr(), pkg._cabi.F32,
+                         sp.data_ptr(), batch, frames // 2, frames, out_ptr, ws_ptr, need)
+    pkg._cabi.raise_for(lib, eng.handle, st)
+    torch.cuda.synchronize()
+    assert bool((big[:guard] == 0xA5).all()) and bool((big[guard + need:] == 0xA5).all()), "workspace guard band overwritten"
+    assert bool((out_big[:4096] == -1234.5).all()) and bool((out_big[4096 + n_out:] == -1234.5).all()), "output guard band overwritten"
+    got = out_big[4096:4096 + n_out].view(batch, 1, -1)
+    assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("batch,frames", [(1, 2), (1, 10), (3, 34), (5, 66), (2, 514), (1, 1300)])
+def test_odd_shapes_whole_resblock_vs_steps(pkg, weights, batch, frames):
+    """Tile tails, utterances shorter than a tile, several tiles per utterance, batch sizes that do not divide the
+    grid: the whole-ResBlock kernels and the step kernels must agree to bf16-noise level and both match the oracle."""
+    h, sds = weights
+    g = make_gen(pkg, h, sds["trained"], "bf16")
+    code, mel, spkr = vo.synthetic_inputs(batch, frames, seed=71)
+    lib = pkg._cabi.load()
+    outs = []
+    try:
+        for fb in (0, 1):
+            lib.l2s_debug_set(b"fuse_branch", fb)
+            outs.append(g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV)).cpu())
+    finally:
+        lib.l2s_debug_set(b"fuse_branch", 1)
+    assert torch.isfinite(outs[1]).all()
+    assert vo.snr_db(outs[0], outs[1]) >= 40.0, vo.snr_db(outs[0], outs[1])
+    if frames <= 600:
+        ref = vo.mel_code_generator_forward(vo.fold_weight_norm(sds["trained"]), h, code, mel, spkr)
+        check(ref, outs[1], "bf16", f"odd shape {batch}x{frames}")
+
+
 def test_cfg2_shape_bf16_vs_fp32_device_reference(pkg, weights):
     """configs[1] at full size (16 x 4 s): bf16 tensor-core path against the fp32
     CUDA-core mode of the same library, plus finiteness and range."""
