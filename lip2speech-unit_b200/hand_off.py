@@ -117,6 +117,38 @@ def write_wav_int16(path: str, samples: np.ndarray, rate: int = SAMPLE_RATE) -> 
 
 
 @torch.no_grad()
+def vocode_batched(generator, feats: Sequence[dict], device="cuda", max_batch: int = 64) -> List[torch.Tensor]:
+    """The batched caller.  feats[i] = {"code": (U,) int64, "mel": (80, T = 2U), "spkr": (256,)} as numpy
+    arrays or torch tensors (host or device).  The generator has no length masks, so utterances of equal
+    length are stacked into one forward (at most max_batch each); host arrays go through one pinned staging buffer per
+    batch.  Returns the int16 waveforms (device tensors, 160 T samples each) in input order."""
+    def as_tensor(v):
+        return v if isinstance(v, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(v))
+
+    def stack(vals):
+        ts = [as_tensor(v) for v in vals]
+        if ts[0].is_cuda:
+            return torch.stack([t.to(device) for t in ts])
+        pinned = torch.empty((len(ts),) + tuple(ts[0].shape), dtype=ts[0].dtype).pin_memory()
+        torch.stack(ts, out=pinned)
+        return pinned.to(device, non_blocking=True)
+
+    by_len: Dict[int, List[int]] = {}
+    for i, f in enumerate(feats):
+        by_len.setdefault(int(f["mel"].shape[1]), []).append(i)
+    out: List[Optional[torch.Tensor]] = [None] * len(feats)
+    for _, idxs in sorted(by_len.items()):
+        for s in range(0, len(idxs), max_batch):
+            grp = idxs[s:s + max_batch]
+            _, wav16 = generator.forward_int16(code=stack([feats[i]["code"] for i in grp]),
+                                               mel=stack([feats[i]["mel"] for i in grp]),
+                                               spkr=stack([feats[i]["spkr"] for i in grp]))
+            for j, i in enumerate(grp):
+                out[i] = wav16[j]
+    return out
+
+
+@torch.no_grad()
 def vocode_manifest(generator, manifest_path: str, out_dir: str, root: Optional[str] = None, device="cuda",
                     max_batch: int = 64, code_dict_path: Optional[str] = None) -> List[str]:
     """Vocode every row of a manifest and write <out_dir>/pred_wav/.../<name>.wav (int16, 16 kHz).
@@ -125,20 +157,34 @@ def vocode_manifest(generator, manifest_path: str, out_dir: str, root: Optional[
     root = root or tsv_root
     code_dict = load_code_dict(code_dict_path or os.path.join(os.path.dirname(manifest_path), "dict.unt.txt"))
     items = [load_item(root, r, code_dict) for r in rows]
-    by_len: Dict[int, List[int]] = {}
-    for i, (feats, _) in enumerate(items):
-        by_len.setdefault(feats["mel"].shape[1], []).append(i)
-    written = [""] * len(rows)
-    for _, idxs in sorted(by_len.items()):
-        for s in range(0, len(idxs), max_batch):
-            grp = idxs[s:s + max_batch]
-            code = torch.from_numpy(np.stack([items[i][0]["code"] for i in grp])).to(device)
-            mel = torch.from_numpy(np.stack([items[i][0]["mel"] for i in grp])).to(device)
-            spk = torch.from_numpy(np.stack([items[i][0]["spkr"] for i in grp])).to(device)
-            _, wav16 = generator.forward_int16(code=code, mel=mel, spkr=spk)
-            wav16 = wav16.cpu().numpy()
-            for j, i in enumerate(grp):
-                path = os.path.join(out_dir, output_name(rows[i]) + ".wav")
-                write_wav_int16(path, wav16[j, :items[i][1]])
-                written[i] = path
+    wavs = vocode_batched(generator, [f for f, _ in items], device=device, max_batch=max_batch)
+    written = []
+    for row, (_, n), w in zip(rows, items, wavs):
+        path = os.path.join(out_dir, output_name(row) + ".wav")
+        write_wav_int16(path, w[:n].cpu().numpy())
+        written.append(path)
     return written
+
+
+def stage1_mel_to_frames(encoder_out_mel: torch.Tensor) -> torch.Tensor:
+    """The mel head of the stage-1 model emits two 80-bin frames per 50 Hz step as (B, T1, 160); the reference
+    de-interleaves them to (B, 2 T1, 80) with reshape(B,T,D//2,2).transpose(-1,-2).reshape(B,2T,D//2)
+    (multi_target_lip2speech/model.py:209-212).  Same expression, any device."""
+    b, t, d = encoder_out_mel.shape
+    return encoder_out_mel.reshape(b, t, d // 2, 2).transpose(-1, -2).reshape(b, t * 2, d // 2)
+
+
+@torch.no_grad()
+def vocode_stage1_outputs(generator, mels: Sequence[torch.Tensor], units: Sequence[torch.Tensor],
+                          spk_embs: Sequence[torch.Tensor], device="cuda", max_batch: int = 64) -> List[torch.Tensor]:
+    """stage-1 outputs straight into the vocoder, no .npy / .unt / HTTP round trip.
+    mels[i]: (T_i', 80) time-major frames as the stage-1 generator keeps them (sequence_generator.py:136-139 cuts them
+    to 2 * target_length), units[i]: (U_i,) int64 unit ids already mapped through dict.unt.txt, spk_embs[i]: (256,).
+    Lengths are reconciled as the dataset does without an audio file: U = min(U_i, T_i' // 2), T = 2 U
+    (dataset_multi_input.py:219-241 with n_audio = 320 U).  Tensors may live on the device already."""
+    feats = []
+    for mel, code, spk in zip(mels, units, spk_embs):
+        u = min(int(code.shape[0]), int(mel.shape[0]) // 2)
+        feats.append({"code": code[:u].to(torch.int64), "mel": mel[:2 * u].transpose(0, 1).contiguous().float(),
+                      "spkr": spk.float()})
+    return vocode_batched(generator, feats, device=device, max_batch=max_batch)

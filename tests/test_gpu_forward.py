@@ -367,6 +367,28 @@ def test_vocode_manifest_batched_equals_per_utterance(pkg, weights, tmp_path):
         assert rate == 16000 and got.shape == (n,) and np.array_equal(got, expect)
 
 
+def test_stage1_outputs_straight_into_the_vocoder(pkg, weights):
+    """device-resident stage-1 outputs (time-major mel frames, unit ids, speaker embeddings of several
+    utterances with different lengths, one mel a frame longer than 2U as the mel head produces) through the batched
+    caller must equal the per-utterance forward -> *32768 -> int16 flow bit for bit."""
+    h, sds = weights
+    g = make_gen(pkg, h, sds["trained"], "fp32")
+    ho = pkg.hand_off
+    mels, units, spks, expect = [], [], [], []
+    for i, (frames, extra) in enumerate([(40, 0), (40, 1), (64, 0), (40, 0), (22, 3)]):
+        code, mel, spkr = vo.synthetic_inputs(1, frames, seed=80 + i)
+        tm = mel[0].transpose(0, 1).contiguous()                        # (T, 80) as stage 1 keeps it
+        if extra:
+            tm = torch.cat([tm, tm[-extra:]], dim=0)
+        mels.append(tm.to(DEV)); units.append(code[0].to(DEV)); spks.append(spkr[0].to(DEV))
+        y = g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV))
+        expect.append((y.squeeze() * 32768.0).clamp(-32768, 32767).to(torch.int16))
+    got = ho.vocode_stage1_outputs(g, mels, units, spks, device=DEV)
+    assert len(got) == 5
+    for a, b in zip(got, expect):
+        assert a.dtype == torch.int16 and torch.equal(a, b)
+
+
 @pytest.mark.parametrize("precision", ["bf16", "tf32", "fp32"])
 @pytest.mark.parametrize("batch,frames", [(1, 2), (3, 34), (2, 514)])
 def test_guard_bands_stay_intact(pkg, weights, precision, batch, frames):

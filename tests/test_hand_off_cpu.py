@@ -60,3 +60,12 @@ def test_wav_writer_matches_scipy(pkg, tmp_path):
     assert p.read_bytes() == buf.getvalue()
     rate, y = wavfile.read(str(p))
     assert rate == 16000 and np.array_equal(x, y)
+
+
+def test_stage1_mel_deinterleave_matches_reference_expression(pkg):
+    """model.py:209-212 of the stage-1 model: (B, T, 160) -> (B, 2T, 80); frame 2t is the even-indexed bins."""
+    import torch
+    x = torch.arange(2 * 3 * 160, dtype=torch.float32).reshape(2, 3, 160)
+    y = pkg.hand_off.stage1_mel_to_frames(x)
+    assert y.shape == (2, 6, 80)
+    assert torch.equal(y[:, 0::2], x[:, :, 0::2]) and torch.equal(y[:, 1::2], x[:, :, 1::2])

@@ -1,0 +1,74 @@
+"""Service-style throughput of the manifest caller: a synthetic dataset in the reference's on-disk
+layout (label/test.tsv + .unt + dict, mel/*.npy, spk_emb/*.npy) is vocoded to pred_wav/*.wav
+
+  (a) the way inference.py does it: one utterance per forward, host-side * 32768 -> int16, one wav per item;
+  (b) hand_off.vocode_manifest: equal-length rows stacked into one forward, int16 on the device.
+
+Both include reading the .npy files and writing the wav files.  Prints JSON.   python tools/manifest_bench.py [n_utts]
+"""
+import json
+import os
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+from oracle import vocoder_oracle as vo  # noqa: E402  (weights + synthetic inputs)
+
+n_utts = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+pkg = ge.load_package()
+ho = pkg.hand_off
+dev = torch.device("cuda:0")
+h = vo.shipped_config()
+g = pkg.MelCodeGenerator(pkg.AttrDict(h))
+g.load_state_dict(vo.init_state_dict(h, seed=1234, style="ref"), strict=True)
+g.eval(); g.remove_weight_norm(); g = g.to(dev)
+
+with tempfile.TemporaryDirectory() as root:
+    os.makedirs(os.path.join(root, "label"))
+    with open(os.path.join(root, "label", "dict.unt.txt"), "w") as f:
+        f.writelines(f"{i} 1\n" for i in range(200))
+    lengths = [400, 400, 400, 300, 400, 200, 400, 300]          # mel frames: mostly 4 s, some shorter
+    tsv, unt, total_s = [root + "\n"], [], 0.0
+    for i in range(n_utts):
+        frames = lengths[i % len(lengths)]
+        code, mel, spkr = vo.synthetic_inputs(1, frames, seed=1000 + i)
+        rel = f"audio/test/spk{i % 4}/{i:05d}.wav"
+        for sub, arr in (("mel", mel[0].T.numpy().astype(np.float32)), ("spk_emb", spkr[0].numpy().astype(np.float32))):
+            path = os.path.join(root, rel.replace("audio/", sub + "/")[:-4] + ".npy")
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            np.save(path, arr)
+        tsv.append(f"test/spk{i % 4}/{i:05d}\tvideo/x.mp4\t{rel}\t{frames // 4}\t{frames * 160}\n")
+        unt.append(" ".join(str(int(c)) for c in code[0]) + "\n")
+        total_s += frames / 100.0
+    open(os.path.join(root, "label", "test.tsv"), "w").writelines(tsv)
+    open(os.path.join(root, "label", "test.unt"), "w").writelines(unt)
+    manifest = os.path.join(root, "label", "test.tsv")
+
+    def per_utterance(out_dir):
+        _, rows = ho.parse_manifest(manifest)
+        cd = ho.load_code_dict(os.path.join(root, "label", "dict.unt.txt"))
+        for r in rows:
+            feats, n = ho.load_item(root, r, cd)
+            y = g(**{k: torch.from_numpy(v).to(dev).unsqueeze(0) for k, v in feats.items()})
+            audio = (y.squeeze() * 32768.0).cpu().numpy().astype("int16")      # inference.py:79-81
+            ho.write_wav_int16(os.path.join(out_dir, ho.output_name(r) + ".wav"), audio[:n])
+
+    def batched(out_dir):
+        ho.vocode_manifest(g, manifest, out_dir, root=root, device=dev)
+
+    res = {"utterances": n_utts, "audio_s": total_s}
+    for name, fn in (("per_utterance_like_inference_py", per_utterance), ("batched_vocode_manifest", batched)):
+        with tempfile.TemporaryDirectory() as out:
+            fn(out)                                   # warm-up: plans, graphs, file cache
+        with tempfile.TemporaryDirectory() as out:
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            fn(out)
+            torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        res[name] = {"seconds": round(dt, 4), "audio_s_per_s": round(total_s / dt, 1)}
+    print(json.dumps(res))
