@@ -233,20 +233,26 @@ def main():
     host_ms = (time.perf_counter() - t_h0) * 1e3 / args.steps
     torch.cuda.synchronize()
 
-    # ---- end to end through the public class: pinned host inputs -> device, waveform -> pinned host
-    out_h = torch.empty((BATCH, 1, FRAMES * HOP), dtype=torch.float32).pin_memory()
-    for _ in range(2):
-        y = gen(code=code_h.to(dev, non_blocking=True), mel=mel_h.to(dev, non_blocking=True), spkr=spk_h.to(dev, non_blocking=True))
-        out_h.copy_(y, non_blocking=True)
+    # ---- end to end through the public API: every step copies its inputs from pinned host memory to the device and
+    # its waveform back to pinned host memory.  HostPipeline (dispatch.py) is the call a user with many batches makes:
+    # the copies of neighbouring steps overlap the forward (two copy streams, double-buffered device inputs).
+    out_h = [torch.empty((BATCH, 1, FRAMES * HOP), dtype=torch.float32).pin_memory() for _ in range(2)]
+    pipe = pkg.HostPipeline(gen, dev)
+    for i in range(4):
+        pipe.submit(code_h, mel_h, spk_h, out_h[i & 1])
+    pipe.finish()
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        y = gen(code=code_h.to(dev, non_blocking=True), mel=mel_h.to(dev, non_blocking=True), spkr=spk_h.to(dev, non_blocking=True))
-        out_h.copy_(y, non_blocking=True)
+    for i in range(args.steps):
+        pipe.submit(code_h, mel_h, spk_h, out_h[i & 1])
+    pipe.s_out.synchronize()
     e1.record()
     sync_all()
     ms_e2e = e0.elapsed_time(e1)
+    pipe.finish()
+    if not torch.equal(out_h[(args.steps - 1) & 1], y.cpu()):
+        raise RuntimeError("end-to-end pipeline output differs from the device-resident forward")
     # short steps: keep the GPU under the same load until nvidia-smi has delivered a few samples
     t_end = time.time() + 4.0
     while len(sampler.rows) < 8 and time.time() < t_end:
@@ -255,7 +261,7 @@ def main():
         torch.cuda.synchronize()
     clocks = sampler.stop()
     h2d = code_h.numel() * 8 + mel_h.numel() * 4 + spk_h.numel() * 4
-    d2h = out_h.numel() * 4
+    d2h = out_h[0].numel() * 4
 
     # ---- per-launch times of one more forward (event pair per launch), for the roofline object
     lib.l2s_debug_set(b"layer_events", 1)
@@ -330,7 +336,7 @@ def main():
                          "algorithmic_gflop_per_step": conv_flops / 1e9, "per_stage": stage_tbl},
             "e2e": {"value": world * audio_per_step / (ms_e2e / 1e3 / args.steps), "unit": "audio-s/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
-                    "api": "MelCodeGenerator(**kwargs) with pinned host tensors, fp32 waveform copied back"},
+                    "api": "HostPipeline.submit(code, mel, spkr, out) per step: pinned host inputs -> device, MelCodeGenerator forward, fp32 waveform -> pinned host; copies of neighbouring steps overlap the forward"},
             "gpu_launches": launches_per_step * args.steps,
             "host_issue_ms_per_step": host_ms,
             "clocks": clocks,

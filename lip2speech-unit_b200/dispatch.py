@@ -58,3 +58,61 @@ def vocode_long(generator, code: torch.Tensor, mel: torch.Tensor, spkr: torch.Te
         for i, (lo, hi, klo, khi) in enumerate(chunks):
             out[0, 0, klo * hop:khi * hop] = y[i, 0, (klo - lo) * hop:(khi - lo) * hop]
     return out
+
+
+class HostPipeline:
+    """Back-to-back batches from pinned host memory: while batch i runs, the inputs of batch i+1 are already on
+    their way to the device and the waveform of batch i-1 on its way back (two copy streams, double-buffered device
+    inputs).  A caller that vocodes many batches (a manifest, a service queue) then pays the PCIe time only once.
+
+        pipe = HostPipeline(generator, "cuda:0")
+        for (code_h, mel_h, spk_h), out_h in zip(batches, pinned_outputs):
+            pipe.submit(code_h, mel_h, spk_h, out_h)        # asynchronous; out_h is a pinned float32 (B,1,L) tensor
+        pipe.finish()                                       # every out_h is complete
+
+    The forward itself runs on the stream that is current when submit() is called."""
+
+    def __init__(self, generator, device="cuda"):
+        self.g = generator
+        self.device = torch.device(device)
+        self.s_in = torch.cuda.Stream(self.device)
+        self.s_out = torch.cuda.Stream(self.device)
+        self.slot = 0
+        self.in_free = [None, None]      # event: the forward that read slot s's device inputs has been issued and finished
+        self.bufs = [None, None]
+        self.pending = []
+
+    @torch.no_grad()
+    def submit(self, code_h, mel_h, spk_h, out_h):
+        s = self.slot
+        self.slot ^= 1
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.s_in):
+            if self.in_free[s] is not None:
+                self.s_in.wait_event(self.in_free[s])          # the previous user of this slot is done with the buffers
+            shapes = (tuple(code_h.shape), tuple(mel_h.shape), tuple(spk_h.shape), mel_h.dtype)
+            if self.bufs[s] is None or self.bufs[s][0] != shapes:
+                self.bufs[s] = (shapes, torch.empty_like(code_h, device=self.device), torch.empty_like(mel_h, device=self.device),
+                                torch.empty_like(spk_h, device=self.device))
+            _, code, mel, spk = self.bufs[s]
+            code.copy_(code_h, non_blocking=True)
+            mel.copy_(mel_h, non_blocking=True)
+            spk.copy_(spk_h, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self.s_in)
+        main.wait_event(ready)
+        y = self.g(code=code, mel=mel, spkr=spk)
+        done = torch.cuda.Event()
+        done.record(main)
+        self.in_free[s] = done
+        y.record_stream(self.s_out)                             # y is read on the copy-out stream
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(done)
+            out_h.copy_(y, non_blocking=True)
+        self.pending.append(y)
+        if len(self.pending) > 4:
+            self.pending.pop(0)
+
+    def finish(self):
+        self.s_out.synchronize()
+        self.pending.clear()

@@ -367,6 +367,25 @@ def test_vocode_manifest_batched_equals_per_utterance(pkg, weights, tmp_path):
         assert rate == 16000 and got.shape == (n,) and np.array_equal(got, expect)
 
 
+def test_host_pipeline_equals_direct_forward(pkg, weights):
+    """HostPipeline overlaps the copies of neighbouring batches with the forward; every pinned output must equal the
+    plain forward of the same batch (different batches, two shapes, more batches than buffer slots)."""
+    h, sds = weights
+    g = make_gen(pkg, h, sds["trained"], "bf16")
+    pipe = pkg.HostPipeline(g, DEV)
+    batches, outs, want = [], [], []
+    for i in range(7):
+        frames = 60 if i % 3 else 84
+        code, mel, spkr = vo.synthetic_inputs(2, frames, seed=90 + i)
+        batches.append((code.pin_memory(), mel.pin_memory(), spkr.pin_memory()))
+        outs.append(torch.empty((2, 1, frames * 160), dtype=torch.float32).pin_memory())
+    for (c, m, s), o in zip(batches, outs):
+        pipe.submit(c, m, s, o)
+    pipe.finish()
+    for (c, m, s), o in zip(batches, outs):
+        assert torch.equal(o, g(code=c.to(DEV), mel=m.to(DEV), spkr=s.to(DEV)).cpu())
+
+
 def test_stage1_outputs_straight_into_the_vocoder(pkg, weights):
     """device-resident stage-1 outputs (time-major mel frames, unit ids, speaker embeddings of several
     utterances with different lengths, one mel a frame longer than 2U as the mel head produces) through the batched
