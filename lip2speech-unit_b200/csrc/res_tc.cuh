@@ -6,10 +6,11 @@
 // fp32 residual and re-writes both.  Here the residual stream never leaves the SM between the steps:
 //
 //   X  (TMEM, fp32, msub x C columns)   the residual stream of the tile.  It is written once from global
-//                                       memory (tcgen05.st) and after that only by the c2 MMAs, which
-//                                       ACCUMULATE onto it; the c2 biases are carried as a running sum that
-//                                       is added whenever X is read.
-//   D1 (TMEM, fp32, msub x C columns)   accumulator of c1
+//                                       memory (tcgen05.st, as x + b2 of the first step) and after that only by
+//                                       the c2 MMAs, which ACCUMULATE onto it; the bias of the next c2 is added
+//                                       by the epilogue warps while the next c1 runs.
+//   D1 (TMEM, fp32, msub x C columns)   accumulator of c1, pre-loaded with the bias of the next c1 while c2 runs,
+//                                       so that phases A and B are TMEM load -> leaky-ReLU -> bf16 -> shared store
 //   S  (shared, bf16, (MT + 2 pad) rows in the K-major swizzled operand layout)
 //                                       lrelu(x), then lrelu(c1 + b1), then lrelu(x') ... each overwrites the
 //                                       previous one once the MMAs that read it have retired.
@@ -19,14 +20,16 @@
 // R = MT - 2H rows.  Rows outside [0, L) are forced to zero in S before every conv (the per-layer zero padding
 // of the reference).
 //
-//   warp 0      TMA producer: the weight stages of the 2 n_dil convs, in order, through a ring
+//   warp 0      TMA producer: the weight stages of the 2 n_dil convs, in order, through a ring; L2 prefetch of the
+//               next item's x / branch-sum rows
 //   warp 1      MMA issuer:   wait s_full -> c1 -> commit d_full -> wait s_full -> c2 (onto X) -> commit d_full
-//   warps 2..9  load x (global -> transpose tile -> X, S), phase A (D1 -> S), phase B (X -> S), and after the last
-//               step the same transposed global epilogue as conv_tc.cuh (branch sum / mean / activated copy)
+//   warps 2..9  load x (global, one row per lane -> X, S), phase A (D1 -> S), phase B (X -> S), and after the last
+//               step the transposed global epilogue of conv_tc.cuh (branch sum / mean / activated copy)
 //
 // MMA and epilogue phases of one CTA alternate; two co-resident CTAs per SM overlap them.
-// Rounding: x + sum of products is formed in the tensor core's fp32 accumulator and the biases are added
-// afterwards, so results differ from the step-by-step kernels in the last fp32 bit (tests compare with a tolerance).
+// Rounding: x + sum of products is formed in the tensor core's fp32 accumulator and the biases enter at different
+// points than in the step-by-step kernels, so results differ from those in the last fp32 bits (tests compare the
+// two with a tolerance; tile size and CTAs per SM do not change a bit).
 #pragma once
 #include "pair_tc.cuh"
 
