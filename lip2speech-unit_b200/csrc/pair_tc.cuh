@@ -104,6 +104,32 @@ __device__ __forceinline__ void pair_phase1_chunk(const PairParams& P, uint8_t* 
   }
 }
 
+// Same arithmetic with the per-chunk overheads removed: bias read from shared memory (broadcast LDS instead of a
+// global load per chunk), lane-constant swizzle term, shifts instead of a division, and the zero fill for rows
+// outside [0, L) only compiled into the path taken by tiles that touch an utterance edge.
+template <int CW, bool EDGE>
+__device__ __forceinline__ void pair_phase1_lean(uint8_t* t_slab, int t_chunk_bytes, int rb, int cpc_shift, const float* sbias1,
+                                                 uint32_t taddr, int i_row, int c0, int sw, bool valid) {
+  uint32_t r[CW];
+  if constexpr (CW == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
+  tmem_ld_wait();
+  uint8_t* row_ptr = t_slab + (size_t)(c0 >> cpc_shift) * t_chunk_bytes + (size_t)i_row * rb;
+  const int first16 = (c0 & ((1 << cpc_shift) - 1)) >> 3;
+  const __nv_bfloat162 slope2 = __float2bfloat162_rn(0.1f);                    // LRELU_SLOPE, models.py:13,38
+#pragma unroll
+  for (int s = 0; s < CW / 8; ++s) {
+    const float4 ba = *reinterpret_cast<const float4*>(sbias1 + c0 + 8 * s);
+    const float4 bb = *reinterpret_cast<const float4*>(sbias1 + c0 + 8 * s + 4);
+    uint4 pk;
+    pk.x = lrelu_bf16x2(__uint_as_float(r[8 * s + 0]) + ba.x, __uint_as_float(r[8 * s + 1]) + ba.y, slope2);
+    pk.y = lrelu_bf16x2(__uint_as_float(r[8 * s + 2]) + ba.z, __uint_as_float(r[8 * s + 3]) + ba.w, slope2);
+    pk.z = lrelu_bf16x2(__uint_as_float(r[8 * s + 4]) + bb.x, __uint_as_float(r[8 * s + 5]) + bb.y, slope2);
+    pk.w = lrelu_bf16x2(__uint_as_float(r[8 * s + 6]) + bb.z, __uint_as_float(r[8 * s + 7]) + bb.w, slope2);
+    if (EDGE && !valid) pk = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(row_ptr + (((first16 + s) ^ sw) << 4)) = pk;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Asynchronous phase 2 (DUAL plans, modes residual + raw [+ act]).  Per warp and 16-column chunk:
 //   residual chunk  [32 rows x 64 B]  global -> staging   by TMA, one chunk ahead (mbarrier res_full[buf])
@@ -284,7 +310,8 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* res_full = bars + 40;        // EPI_TMA: 2 residual barriers per epilogue warp
   uint8_t* epi_base = reinterpret_cast<uint8_t*>(bars + 64);
   epi_base += (1024u - (smem_u32(epi_base) & 1023u)) & 1023u;   // swizzle patterns of the staging need aligned bases
-  float* epi_tiles = reinterpret_cast<float*>(epi_base);
+  float* sbias1 = reinterpret_cast<float*>(epi_base);           // c1 bias, read by phase 1
+  float* epi_tiles = reinterpret_cast<float*>(epi_base + 1024);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -326,6 +353,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int o = (threadIdx.x - 64) * 16; o < tail_bytes; o += (kTcThreads - 64) * 16)
         *reinterpret_cast<uint4*>(base + o) = make_uint4(0u, 0u, 0u, 0u);
     }
+    for (int i = threadIdx.x - 64; i < g.c; i += kTcThreads - 64) sbias1[i] = P.bias1[i];
     fence_proxy_async_smem();
   }
   tc_fence_before();
@@ -521,14 +549,24 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       {
         const uint32_t t1 = tmem_base + ((uint32_t)(quad * 32) << 16);
         const int cps = g.c / g.cw;
+        const bool edge = dummy || q0 - g.h2 < 0 || q0 - g.h2 + g.mt > p.lin;   // some T rows lie outside the utterance
+        const int sw = g.rb == 128 ? (lane & 7) : (g.rb == 64 ? ((lane >> 1) & 3) : ((lane >> 2) & 1));
+        const int cpc_shift = g.rb == 128 ? 6 : (g.rb == 64 ? 5 : 4);           // log2(channels per K chunk)
         int s = 0, cc = half;
         while (cc >= cps) { cc -= cps; ++s; }
         while (s < g.msub) {
           const int i_row = s * 128 + quad * 32 + lane;
           const int t = q0 - g.h2 + i_row;
           const bool valid = t >= 0 && t < p.lin && !dummy;
-          if (!DUAL && g.cw == 32) pair_phase1_chunk<32>(P, slabT, t1 + (uint32_t)(s * g.c + cc * 32), i_row, cc * 32, valid);
-          else pair_phase1_chunk<16>(P, slabT, t1 + (uint32_t)(s * g.c + cc * 16), i_row, cc * 16, valid);
+          if (!DUAL && g.cw == 32) {
+            const uint32_t ta = t1 + (uint32_t)(s * g.c + cc * 32);
+            if (edge) pair_phase1_lean<32, true>(slabT, g.t_chunk_bytes, g.rb, cpc_shift, sbias1, ta, i_row, cc * 32, sw, valid);
+            else pair_phase1_lean<32, false>(slabT, g.t_chunk_bytes, g.rb, cpc_shift, sbias1, ta, i_row, cc * 32, sw, true);
+          } else {
+            const uint32_t ta = t1 + (uint32_t)(s * g.c + cc * 16);
+            if (edge) pair_phase1_lean<16, true>(slabT, g.t_chunk_bytes, g.rb, cpc_shift, sbias1, ta, i_row, cc * 16, sw, valid);
+            else pair_phase1_lean<16, false>(slabT, g.t_chunk_bytes, g.rb, cpc_shift, sbias1, ta, i_row, cc * 16, sw, true);
+          }
           cc += 2;
           while (cc >= cps) { cc -= cps; ++s; }
         }
@@ -600,7 +638,7 @@ inline bool pair_plan_with(int c, int k, int dil, int lin, int batch, int smem_b
   g.tb = tb;
   g.n_tstages = (k + tb - 1) / tb;
   g.bstage_bytes = tb * c * g.rb;
-  const int bar_bytes = 1024 + 512 + 1024 + kTcEpiWarps * g.tile_words * 4;   // alignment slack, barriers, staging alignment, tiles
+  const int bar_bytes = 1024 + 512 + 1024 + 1024 + kTcEpiWarps * g.tile_words * 4;   // alignment slack, barriers, staging alignment, bias1, tiles
   int msub = (dual ? 128 : 256) / c;
   if (msub < 1) msub = 1;
   if (msub > 8) msub = 8;
