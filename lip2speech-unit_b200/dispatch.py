@@ -78,41 +78,45 @@ class HostPipeline:
         self.s_in = torch.cuda.Stream(self.device)
         self.s_out = torch.cuda.Stream(self.device)
         self.slot = 0
-        self.in_free = [None, None]      # event: the forward that read slot s's device inputs has been issued and finished
-        self.bufs = [None, None]
-        self.pending = []
+        self.in_free = [None, None]      # event: the forward that read slot s's device inputs has finished
+        self.out_free = [None, None]     # event: the device->host copy of slot s's waveform has finished
+        self.bufs = [None, None]         # per slot: (shapes, code, mel, spk, out) device buffers, allocated once per shape
 
     @torch.no_grad()
     def submit(self, code_h, mel_h, spk_h, out_h):
         s = self.slot
         self.slot ^= 1
         main = torch.cuda.current_stream(self.device)
+        shapes = (tuple(code_h.shape), tuple(mel_h.shape), tuple(spk_h.shape), mel_h.dtype, tuple(out_h.shape))
+        if self.bufs[s] is None or self.bufs[s][0] != shapes:
+            if self.bufs[s] is not None:
+                torch.cuda.synchronize(self.device)               # a new shape: retire the old buffers first
+            self.bufs[s] = (shapes, torch.empty_like(code_h, device=self.device), torch.empty_like(mel_h, device=self.device),
+                            torch.empty_like(spk_h, device=self.device),
+                            torch.empty(out_h.shape, dtype=torch.float32, device=self.device))
+            self.in_free[s] = self.out_free[s] = None
+        _, code, mel, spk, out = self.bufs[s]
         with torch.cuda.stream(self.s_in):
             if self.in_free[s] is not None:
-                self.s_in.wait_event(self.in_free[s])          # the previous user of this slot is done with the buffers
-            shapes = (tuple(code_h.shape), tuple(mel_h.shape), tuple(spk_h.shape), mel_h.dtype)
-            if self.bufs[s] is None or self.bufs[s][0] != shapes:
-                self.bufs[s] = (shapes, torch.empty_like(code_h, device=self.device), torch.empty_like(mel_h, device=self.device),
-                                torch.empty_like(spk_h, device=self.device))
-            _, code, mel, spk = self.bufs[s]
+                self.s_in.wait_event(self.in_free[s])          # the previous user of this slot is done with the inputs
             code.copy_(code_h, non_blocking=True)
             mel.copy_(mel_h, non_blocking=True)
             spk.copy_(spk_h, non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(self.s_in)
         main.wait_event(ready)
-        y = self.g(code=code, mel=mel, spkr=spk)
+        if self.out_free[s] is not None:
+            main.wait_event(self.out_free[s])                  # the slot's previous waveform has left the device
+        self.g.forward_into(out, code=code, mel=mel, spkr=spk)
         done = torch.cuda.Event()
         done.record(main)
         self.in_free[s] = done
-        y.record_stream(self.s_out)                             # y is read on the copy-out stream
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(done)
-            out_h.copy_(y, non_blocking=True)
-        self.pending.append(y)
-        if len(self.pending) > 4:
-            self.pending.pop(0)
+            out_h.copy_(out, non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(self.s_out)
+        self.out_free[s] = copied
 
     def finish(self):
         self.s_out.synchronize()
-        self.pending.clear()

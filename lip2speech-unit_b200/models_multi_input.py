@@ -275,7 +275,7 @@ class _GeneratorBase(nn.Module):
         if not t.is_cuda:
             raise RuntimeError(f"{name} is on {t.device}: this generator runs on a B200 only (no CPU fallback)")
 
-    def _run(self, code, mel, spkr, frames, want_i16=False):
+    def _run(self, code, mel, spkr, frames, want_i16=False, out=None):
         if self.training:
             raise NotImplementedError("the accelerated generator is inference-only: call .eval() first")
         device = code.device
@@ -293,7 +293,11 @@ class _GeneratorBase(nn.Module):
                 eng.workspaces[wkey] = None
                 ws = torch.empty(int(need), dtype=torch.uint8, device=device)
                 eng.workspaces[wkey] = ws
-            out = torch.empty((batch, 1, eng.hop * frames), dtype=torch.float32, device=device)
+            if out is None:
+                out = torch.empty((batch, 1, eng.hop * frames), dtype=torch.float32, device=device)
+            elif (out.dtype != torch.float32 or not out.is_cuda or not out.is_contiguous()
+                  or tuple(out.shape) != (batch, 1, eng.hop * frames)):
+                raise RuntimeError(f"out must be a contiguous float32 CUDA tensor of shape {(batch, 1, eng.hop * frames)}")
             mel_ptr, mel_tag = None, _cabi.F32
             if mel is not None:
                 mel_tag = {torch.float32: _cabi.F32, torch.float16: _cabi.F16, torch.bfloat16: _cabi.BF16}[mel.dtype]
@@ -399,6 +403,13 @@ class MelCodeGenerator(_GeneratorBase):
     def forward(self, **kwargs):
         code, mel, spkr, frames = self._prepare(kwargs)
         return self._run(code, mel, spkr, frames)
+
+    @torch.no_grad()
+    def forward_into(self, out, **kwargs):
+        """Same forward, written into a caller-owned (B,1,L) float32 device tensor (no allocation per call: what a
+        pipelined caller wants, see dispatch.HostPipeline).  Returns out."""
+        code, mel, spkr, frames = self._prepare(kwargs)
+        return self._run(code, mel, spkr, frames, out=out)
 
     @torch.no_grad()
     def forward_int16(self, **kwargs):
