@@ -226,11 +226,16 @@ __device__ __forceinline__ void res_output(const ConvParams& p, float* tile, uin
   const int cps = c / CW;
   const int cps_sh = cps == 4 ? 2 : (cps == 2 ? 1 : 0);
   const int n_chunks = msub << cps_sh;
+  // Ownership follows the 32-column units of res_load_x / res_phase (a warp that finishes early starts writing the
+  // next item's X while its neighbour may still be reading this one): unit u = half, half + 2, ... is chunk u for
+  // 32-column chunks and chunks 2u, 2u + 1 for 16-column chunks.
+  const int first = CW == 32 ? w.half : 2 * w.half;
+  auto next_after = [&](int idx) { return CW == 32 ? idx + 2 : ((idx & 1) ? idx + 3 : idx + 1); };
   auto skip = [&](int idx) {   // first owned chunk at or after idx that holds an output row
     while (idx < n_chunks) {
       const int r0 = t_row0 + (idx >> cps_sh) * 128 + w.quad * 32;
       if (r0 < row_lim && r0 + 32 > row_lo) break;
-      idx += 2;
+      idx = next_after(idx);
     }
     return idx;
   };
@@ -247,7 +252,7 @@ __device__ __forceinline__ void res_output(const ConvParams& p, float* tile, uin
     else epi_finish<CW, MODE, false>(p, ch, tile4, no_res, av, crow, c4);
     __syncwarp();   // the tile is rewritten by the next chunk
   };
-  int idx = skip(w.half);
+  int idx = skip(first);
   if constexpr (PIPE) {
     // 168-register budget: the next chunk's branch-sum values wait in registers
     EpiChunk ca{}, cb{};
@@ -256,7 +261,7 @@ __device__ __forceinline__ void res_output(const ConvParams& p, float* tile, uin
     mbar_wait(bar, parity);
     tc_fence_after();
     while (idx < n_chunks) {
-      const int idx2 = skip(idx + 2);
+      const int idx2 = skip(next_after(idx));
       if (idx2 < n_chunks) { cb = locate(idx2); epi_load_acc<CW, MODE>(p, cb, avb); }
       finish(ca, ava);
       ca = cb;
@@ -287,7 +292,7 @@ __device__ __forceinline__ void res_output(const ConvParams& p, float* tile, uin
       const EpiChunk ca = locate(idx);
       float4 ava[CW / 4];
       epi_load_acc<CW, MODE>(p, ca, ava);
-      idx = skip(idx + 2);
+      idx = skip(next_after(idx));
       prefetch_acc(idx);
       finish(ca, ava);
     }
