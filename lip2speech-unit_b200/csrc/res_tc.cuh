@@ -586,6 +586,8 @@ inline bool res_plan_with(int c, int k, int n_dil, const int* dil, int lin, int 
 
 // Best-scoring tile of each kind; two co-resident CTAs (MMA / epilogue overlap) beat one bigger tile unless the
 // halo eats too much of the smaller tile.  mode: 0 auto, 1 force dual, 2 force single.
+inline int g_res_single_pct = 85;   // planner: score discount (percent) of a one-CTA-per-SM plan (knob res_single_pct)
+
 inline bool res_plan(int c, int k, int n_dil, const int* dil, int lin, int batch, int mode, int max_msub, ResGeom* out) {
   ResGeom best{};
   double best_score = 0.0;
@@ -594,10 +596,10 @@ inline bool res_plan(int c, int k, int n_dil, const int* dil, int lin, int batch
     for (int msub = max_msub < 8 ? max_msub : 8; msub >= 1; --msub) {
       ResGeom g;
       if (!res_plan_with(c, k, n_dil, dil, lin, batch, dual != 0, msub, &g)) continue;
-      // useful rows per computed row, discounted when nothing overlaps the CTA's alternating phases; tiles much
+      // useful rows per computed row, discounted (0.85, from the measured C = 64 / 32 sweeps) when nothing overlaps the CTA's alternating phases; tiles much
       // longer than the utterance waste the rest
       const int covered = g.m_items * g.r_out;
-      double score = (double)g.r_out / g.mt * ((double)lin / covered) * (dual ? 1.0 : 0.75);
+      double score = (double)g.r_out / g.mt * ((double)lin / covered) * (dual ? 1.0 : 0.01 * g_res_single_pct);
       if (score > best_score) { best_score = score; best = g; }
     }
   }
