@@ -46,6 +46,8 @@ struct ResGeom {
   int s_bytes;
   int tb, n_tstages, bstage_bytes, sb;
   int tmem_cols, cw, dual, tile_words;
+  int ne;                   // epilogue warps: 8, or 4 in the four-CTAs-per-SM plans (one warp per TMEM lane quadrant)
+  int ctas_per_sm;          // 1, 2 (dual) or 4 (quad)
   uint32_t idesc;
   int smem_bytes;
 };
@@ -73,6 +75,7 @@ struct ResMaps {
 // lane); for C = 16 it is two neighbouring accumulators (two tile rows per lane, 128 apart).
 struct ResLane {
   int quad, half, lane;
+  int ustep;     // units advance by this much per warp: 2 when two warps share a lane quadrant, 1 when one warp owns it
   int sw;        // this lane's swizzle term of the S slots (rows advance by multiples of 8 between units)
 };
 
@@ -112,7 +115,7 @@ template <bool EDGE>
 __device__ __forceinline__ void res_phase(const ResGeom& g, const ResLane& w, uint8_t* slab, uint32_t t_quad, int t_row0, int lin,
                                           long long* tr = nullptr) {
   const int n_units = (g.msub * g.c) >> 5;
-  for (int u = w.half; u < n_units; u += 2) {
+  for (int u = w.half; u < n_units; u += w.ustep) {
     uint32_t r[32];
     if (tr && w.lane == 0) tr[0] = gtime();
     tmem_ld32(t_quad + (uint32_t)(32 * u), r);
@@ -130,7 +133,7 @@ __device__ __forceinline__ void res_phase(const ResGeom& g, const ResLane& w, ui
 __device__ __forceinline__ void res_prebias_d1(const ResGeom& g, const ResLane& w, uint32_t d1_quad, const float* sbias) {
   const int n_units = (g.msub * g.c) >> 5;
   const int cmask = g.c - 1;
-  for (int u = w.half; u < n_units; u += 2) {
+  for (int u = w.half; u < n_units; u += w.ustep) {
     const int c0 = (32 * u) & cmask;
     uint32_t r[32];
 #pragma unroll
@@ -147,7 +150,7 @@ __device__ __forceinline__ void res_prebias_d1(const ResGeom& g, const ResLane& 
 __device__ __forceinline__ void res_addbias_x(const ResGeom& g, const ResLane& w, uint32_t x_quad, const float* sbias) {
   const int n_units = (g.msub * g.c) >> 5;
   const int cmask = g.c - 1;
-  for (int u = w.half; u < n_units; u += 2) {
+  for (int u = w.half; u < n_units; u += w.ustep) {
     const int c0 = (32 * u) & cmask;
     uint32_t r[32];
     tmem_ld32(x_quad + (uint32_t)(32 * u), r);
@@ -178,14 +181,14 @@ __device__ __forceinline__ void res_load_x(const ResParams& P, const ResLane& w,
   const float* xb = P.x + (long long)b * lin * g.c;
   // all of this lane's rows into L1 first (one prefetch per 128-byte line, no registers held), so that the unit
   // loop below pays the L2 latency once instead of once per unit
-  for (int u = w.half + 2; u < n_units; u += 2) {
+  for (int u = w.half + w.ustep; u < n_units; u += w.ustep) {
     int row, c0;
     res_unit_pos(g, w, u, row, c0);
     const int t = t_row0 + row;
     if (t >= 0 && t < lin) prefetch_l1(xb + (long long)t * g.c + c0);
     if (c16 && t + 128 >= 0 && t + 128 < lin) prefetch_l1(xb + (long long)(t + 128) * g.c);
   }
-  for (int u = w.half; u < n_units; u += 2) {
+  for (int u = w.half; u < n_units; u += w.ustep) {
     int row, c0;
     res_unit_pos(g, w, u, row, c0);
     uint32_t r[32];
@@ -227,10 +230,10 @@ __device__ __forceinline__ void res_output(const ConvParams& p, float* tile, uin
   const int cps_sh = cps == 4 ? 2 : (cps == 2 ? 1 : 0);
   const int n_chunks = msub << cps_sh;
   // Ownership follows the 32-column units of res_load_x / res_phase (a warp that finishes early starts writing the
-  // next item's X while its neighbour may still be reading this one): unit u = half, half + 2, ... is chunk u for
+  // next item's X while its neighbour may still be reading this one): unit u = half, half + ustep, ... is chunk u for
   // 32-column chunks and chunks 2u, 2u + 1 for 16-column chunks.
   const int first = CW == 32 ? w.half : 2 * w.half;
-  auto next_after = [&](int idx) { return CW == 32 ? idx + 2 : ((idx & 1) ? idx + 3 : idx + 1); };
+  auto next_after = [&](int idx) { return CW == 32 ? idx + w.ustep : ((idx & 1) ? idx + 2 * w.ustep - 1 : idx + 1); };
   auto skip = [&](int idx) {   // first owned chunk at or after idx that holds an output row
     while (idx < n_chunks) {
       const int r0 = t_row0 + (idx >> cps_sh) * 128 + w.quad * 32;
@@ -353,7 +356,7 @@ res_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 2 * g.n_dil; ++i) tma_prefetch_desc(&maps.w[i]);
     for (int i = 0; i < g.sb; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    mbar_init(s_full, kTcEpiWarps);
+    mbar_init(s_full, (uint32_t)g.ne);
     mbar_init(d_full, 1);
     fence_barrier_init();
   }
@@ -363,11 +366,11 @@ res_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
     const int pad_bytes = g.pad * g.rb;
     uint8_t* lo = slab;
     uint8_t* hi = slab + (size_t)(g.pad + g.mt) * g.rb;
-    for (int o = (threadIdx.x - 64) * 16; o < pad_bytes; o += (kTcThreads - 64) * 16) {
+    for (int o = (threadIdx.x - 64) * 16; o < pad_bytes; o += ((int)blockDim.x - 64) * 16) {
       *reinterpret_cast<uint4*>(lo + o) = make_uint4(0u, 0u, 0u, 0u);
       *reinterpret_cast<uint4*>(hi + o) = make_uint4(0u, 0u, 0u, 0u);
     }
-    for (int i = threadIdx.x - 64; i < 2 * g.n_dil * g.c; i += kTcThreads - 64) {
+    for (int i = threadIdx.x - 64; i < 2 * g.n_dil * g.c; i += (int)blockDim.x - 64) {
       const int cv = i / g.c, ch = i - cv * g.c;
       sbias[cv * 64 + ch] = (cv & 1) ? P.bias2[cv >> 1][ch] : P.bias1[cv >> 1][ch];
     }
@@ -460,6 +463,7 @@ res_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
     ResLane w;
     w.quad = warp & 3;
     w.half = (warp - 2) >> 2;
+    w.ustep = g.ne >> 2;
     w.lane = lane;
     w.sw = g.rb == 128 ? (lane & 7) : (g.rb == 64 ? ((lane >> 1) & 3) : ((lane >> 2) & 1));
     float* tile = epi_tiles + (size_t)(warp - 2) * g.tile_words;
@@ -533,7 +537,11 @@ res_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
 
 // ------------------------------------------------------------------ host side
 
-inline bool res_plan_with(int c, int k, int n_dil, const int* dil, int lin, int batch, bool dual, int msub, ResGeom* out) {
+// kind: 0 = one CTA per SM (168 registers, 32-column epilogue chunks), 1 = two (80 registers, <= 112 KB, <= 256 TMEM
+// columns), 2 = four CTAs per SM with four epilogue warps each (<= 55 KB, <= 128 TMEM columns): more independent
+// tiles in flight for the MMA-light ResBlocks, whose epilogue warps otherwise idle while their own tile's MMAs run.
+inline bool res_plan_with(int c, int k, int n_dil, const int* dil, int lin, int batch, int kind, int msub, ResGeom* out) {
+  const bool dual = kind != 0;
   ResGeom g{};
   if ((c != 16 && c != 32 && c != 64) || k < 1 || k > kMaxTaps || (k & 1) == 0 || n_dil < 1 || n_dil > kResMaxDil) return false;
   g.c = c; g.k = k; g.n_dil = n_dil;
@@ -558,8 +566,10 @@ inline bool res_plan_with(int c, int k, int n_dil, const int* dil, int lin, int 
   if (g.r_out < 32) return false;
   int cols = 32;
   while (cols < 2 * msub * c) cols <<= 1;
-  if (cols > (dual ? 256 : 512)) return false;
+  if (cols > (kind == 2 ? 128 : (dual ? 256 : 512))) return false;
   g.tmem_cols = cols;
+  g.ne = kind == 2 ? 4 : kTcEpiWarps;
+  g.ctas_per_sm = kind == 2 ? 4 : (dual ? 2 : 1);
   int tb = 1;
   while (tb < k && tb < 16 && (tb * 2) * c * g.rb <= 16384) tb *= 2;
   if (tb > k) tb = k;
@@ -568,8 +578,8 @@ inline bool res_plan_with(int c, int k, int n_dil, const int* dil, int lin, int 
   g.bstage_bytes = tb * c * g.rb;
   g.s_bytes = ((g.mt + 2 * g.pad) * g.rb + 1023) & ~1023;
   if ((msub * c) % 32 != 0) return false;   // the phases walk the TMEM region in 32-column units
-  const int fixed = 1024 + 192 + 2 * kResMaxDil * 64 * 4 + kTcEpiWarps * g.tile_words * 4 + g.s_bytes;   // slack, barriers, biases, tiles, S
-  const int budget = dual ? 112 * 1024 : 220 * 1024;
+  const int fixed = 1024 + 192 + 2 * kResMaxDil * 64 * 4 + g.ne * g.tile_words * 4 + g.s_bytes;   // slack, barriers, biases, tiles, S
+  const int budget = kind == 2 ? 55 * 1024 : (dual ? 112 * 1024 : 220 * 1024);
   int sb = 2;
   if (fixed + sb * g.bstage_bytes > budget) return false;
   while (sb < kTcMaxStagesB && sb < 2 * g.n_tstages && fixed + (sb + 1) * g.bstage_bytes <= budget &&
@@ -585,21 +595,26 @@ inline bool res_plan_with(int c, int k, int n_dil, const int* dil, int lin, int 
 }
 
 // Best-scoring tile of each kind; two co-resident CTAs (MMA / epilogue overlap) beat one bigger tile unless the
-// halo eats too much of the smaller tile.  mode: 0 auto, 1 force dual, 2 force single.
+// halo eats too much of the smaller tile.  mode: 0 auto, 1 force dual, 2 force single, 3 force quad.
 inline int g_res_single_pct = 85;   // planner: score discount (percent) of a one-CTA-per-SM plan (knob res_single_pct)
+
+inline int g_res_quad_pct = 115;    // planner: score weight (percent) of a four-CTAs-per-SM plan, 0 = never (knob res_quad_pct).  Measured on
+                                    // cfg2: C=32 k=3 92 -> 84 us, C=16 k=7 117 -> 107 us; 200 (quad everywhere it fits) is slower.
 
 inline bool res_plan(int c, int k, int n_dil, const int* dil, int lin, int batch, int mode, int max_msub, ResGeom* out) {
   ResGeom best{};
   double best_score = 0.0;
-  for (int dual = 1; dual >= 0; --dual) {
-    if ((mode == 1 && !dual) || (mode == 2 && dual)) continue;
+  for (int kind = 2; kind >= 0; --kind) {
+    if ((mode == 1 && kind != 1) || (mode == 2 && kind != 0) || (mode == 3 && kind != 2)) continue;
+    if (kind == 2 && mode != 3 && g_res_quad_pct <= 0) continue;
     for (int msub = max_msub < 8 ? max_msub : 8; msub >= 1; --msub) {
       ResGeom g;
-      if (!res_plan_with(c, k, n_dil, dil, lin, batch, dual != 0, msub, &g)) continue;
-      // useful rows per computed row, discounted (0.85, from the measured C = 64 / 32 sweeps) when nothing overlaps the CTA's alternating phases; tiles much
-      // longer than the utterance waste the rest
+      if (!res_plan_with(c, k, n_dil, dil, lin, batch, kind, msub, &g)) continue;
+      // useful rows per computed row, weighted by how well the kind overlaps MMA and epilogue phases (from the
+      // measured sweeps); tiles much longer than the utterance waste the rest
       const int covered = g.m_items * g.r_out;
-      double score = (double)g.r_out / g.mt * ((double)lin / covered) * (dual ? 1.0 : 0.01 * g_res_single_pct);
+      const double w = kind == 2 ? 0.01 * (g_res_quad_pct > 0 ? g_res_quad_pct : 100) : (kind == 1 ? 1.0 : 0.01 * g_res_single_pct);
+      const double score = (double)g.r_out / g.mt * ((double)lin / covered) * w;
       if (score > best_score) { best_score = score; best = g; }
     }
   }
@@ -621,14 +636,14 @@ inline cudaError_t launch_res_mode(const ResParams& P, const ResMaps& maps, int 
     if (e != cudaSuccess) return e;
     configured[dev] = true;
   }
-  res_tc_kernel<MODE, DUAL><<<grid, kTcThreads, (size_t)P.g.smem_bytes, stream>>>(maps, P);
+  res_tc_kernel<MODE, DUAL><<<grid, 64 + 32 * P.g.ne, (size_t)P.g.smem_bytes, stream>>>(maps, P);
   return cudaGetLastError();
 }
 
 inline cudaError_t launch_res_tc(const ResParams& P, const ResMaps& maps, int num_ctas, cudaStream_t stream) {
   const ResGeom& g = P.g;
   const ConvParams& c = P.c;
-  const int cap = num_ctas * (g.dual ? 2 : 1);
+  const int cap = num_ctas * g.ctas_per_sm;
   int grid = g.total_items < cap ? g.total_items : cap;
   if (grid < 1) grid = 1;
   const int mode = ((c.acc_in || c.div != 1.0f) ? kEpiAcc : 0) | (c.out_raw ? kEpiRaw : 0) | (c.out_act ? kEpiAct : 0);

@@ -1143,6 +1143,7 @@ int l2s_debug_set(const char* key, int64_t value) {
   else if (k == "res_mode") g_knobs.res_mode = value;
   else if (k == "res_msub") g_knobs.res_msub = value;
   else if (k == "res_single_pct") g_res_single_pct = (int)value;
+  else if (k == "res_quad_pct") g_res_quad_pct = (int)value;
   else if (k == "cluster") g_knobs.cluster = value;
   else if (k == "alias_at") g_knobs.alias_at = value;
   else if (k == "epi_tma") g_knobs.epi_tma = value;

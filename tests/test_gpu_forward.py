@@ -279,10 +279,11 @@ def test_whole_resblock_kernels_match_steps(pkg, weights, frames):
     check(ref, y, "bf16", f"whole-ResBlock kernels, {frames} frames")
 
 
-@pytest.mark.parametrize("knob,value", [("res_mode", 1), ("res_mode", 2), ("res_msub", 2), ("res_msub", 4)])
+@pytest.mark.parametrize("knob,value", [("res_mode", 1), ("res_mode", 2), ("res_quad_pct", 200), ("res_quad_pct", 0), ("res_msub", 2),
+                                        ("res_msub", 4)])
 def test_whole_resblock_tilings_agree(pkg, weights, knob, value):
-    """Tile size and CTAs per SM of the whole-ResBlock kernel change the schedule, not the arithmetic of any
-    output element: the waveform must not change by a bit."""
+    """Tile size, CTAs per SM (1 / 2 / 4) and epilogue warps per CTA (8 / 4) of the whole-ResBlock kernel change the
+    schedule, not the arithmetic of any output element: the waveform must not change by a bit."""
     h, sds = weights
     code, mel, spkr = vo.synthetic_inputs(3, 150, seed=33)
     g = make_gen(pkg, h, sds["trained"], "bf16")
@@ -294,6 +295,7 @@ def test_whole_resblock_tilings_agree(pkg, weights, knob, value):
     finally:
         lib.l2s_debug_set(b"res_mode", 0)
         lib.l2s_debug_set(b"res_msub", 8)
+        lib.l2s_debug_set(b"res_quad_pct", 115)
     assert torch.isfinite(a).all()
     assert torch.equal(a, b), float((a - b).abs().max())
 
