@@ -54,7 +54,8 @@ struct CondParams {
   int mel_dtype;
   const float* spk_vec;    // (B,E) projected speaker vectors (multi) or null
   const float* dict;       // (num_embeddings,E)
-  const float* wt;         // unit ConvT weights repacked [4][E_in][E_out]
+  const float* tab;        // unit table folded through the ConvTranspose1d taps at load: [4][num_embeddings][E], tab[j][id] = W_j^T dict[id]
+  const float* wt;         // unit ConvT weights repacked [4][E_in][E_out] (only used to build the table)
   const float* wt_bias;    // [E]
   const float* fc_t;       // fc weight transposed [E_in][E_out]
   const float* fc_bias;    // [E]
@@ -74,7 +75,6 @@ constexpr int kCondThreads = kCondE * kCondSplit;
 // latency bound.  Splitting the reductions over four thread groups quadruples the warps for the same loads.
 template <typename Ta>
 __global__ void __launch_bounds__(kCondThreads) cond_multi_kernel(const CondParams p) {
-  __shared__ float s_emb[kCondFrames / 2 + 2][kCondE];   // units i0-1 .. i0+4
   __shared__ float s_act[kCondFrames][kCondE];
   __shared__ float s_part[kCondSplit][kCondFrames][kCondE];
   const int b = blockIdx.y;
@@ -86,54 +86,50 @@ __global__ void __launch_bounds__(kCondThreads) cond_multi_kernel(const CondPara
   constexpr int FPG = kCondFrames / kCondSplit;           // frames each group finishes
   Ta* cond = reinterpret_cast<Ta*>(p.cond) + ((long long)b * p.frames) * p.cin_pad;
 
-  // (1) gather: an exact row copy of the unit table
-  for (int r = g; r < kCondFrames / 2 + 2; r += kCondSplit) {
-    const int i = i0 - 1 + r;
-    float v = 0.f;
+  // (1) unit ids of this block: i0-1 .. i0+4 (clamped, sticky error flag like the reference's device assert)
+  __shared__ int s_id[kCondFrames / 2 + 2];
+  if (threadIdx.x < kCondFrames / 2 + 2) {
+    const int i = i0 - 1 + (int)threadIdx.x;
+    int id = -1;                                            // -1: outside the utterance (contributes zero)
     if (i >= 0 && i < p.units) {
-      long long id = p.code[(long long)b * p.units + i];
-      if (id < 0 || id >= p.num_embeddings) {
-        if (c == 0) atomicOr(p.err_flag, 1);
-        id = id < 0 ? 0 : p.num_embeddings - 1;
+      long long v = p.code[(long long)b * p.units + i];
+      if (v < 0 || v >= p.num_embeddings) {
+        atomicOr(p.err_flag, 1);
+        v = v < 0 ? 0 : p.num_embeddings - 1;
       }
-      v = p.dict[id * kCondE + c];
-      if (p.embed_tap && r >= 1 && r <= kCondFrames / 2) p.embed_tap[((long long)b * p.units + i) * kCondE + c] = v;
+      id = (int)v;
     }
-    s_emb[r][c] = v;
+    s_id[threadIdx.x] = id;
   }
   __syncthreads();
-
-  // (2) ConvTranspose1d(E,E,4,stride 2,pad 1): out[2i] = W1 x[i] + W3 x[i-1], out[2i+1] = W2 x[i] + W0 x[i+1]
-  float acc[kCondFrames];
-#pragma unroll
-  for (int f = 0; f < kCondFrames; ++f) acc[f] = 0.f;
-#pragma unroll 4
-  for (int ci = g * KQ; ci < (g + 1) * KQ; ++ci) {
-    const float w0 = p.wt[(0 * kCondE + ci) * kCondE + c];
-    const float w1 = p.wt[(1 * kCondE + ci) * kCondE + c];
-    const float w2 = p.wt[(2 * kCondE + ci) * kCondE + c];
-    const float w3 = p.wt[(3 * kCondE + ci) * kCondE + c];
-#pragma unroll
-    for (int h = 0; h < kCondFrames / 2; ++h) {
-      const float xm = s_emb[h][ci], x0 = s_emb[h + 1][ci], xp = s_emb[h + 2][ci];
-      acc[2 * h] = fmaf(x0, w1, fmaf(xm, w3, acc[2 * h]));
-      acc[2 * h + 1] = fmaf(x0, w2, fmaf(xp, w0, acc[2 * h + 1]));
+  if (p.embed_tap) {                                        // test hook: the raw gathered rows, an exact copy of the table
+    for (int r = 1 + g; r <= kCondFrames / 2; r += kCondSplit) {
+      const int i = i0 - 1 + r;
+      if (i < p.units && s_id[r] >= 0) p.embed_tap[((long long)b * p.units + i) * kCondE + c] = p.dict[(long long)s_id[r] * kCondE + c];
     }
   }
-#pragma unroll
-  for (int f = 0; f < kCondFrames; ++f) s_part[g][f][c] = acc[f];
-  __syncthreads();
-  // (3) reduce the four partial sums (fixed order), bias, exact (erf) GELU
+  // (2) ConvTranspose1d(E,E,4,stride 2,pad 1) folded into the unit table: the layer acts on one of 200 table
+  // rows, so W_j^T dict[id] is precomputed per (tap, id) at load and a frame is two gathers and an add:
+  //   out[2i] = P1[u_i] + P3[u_{i-1}],  out[2i+1] = P2[u_i] + P0[u_{i+1}]   (+ bias)
+  // (3) exact (erf) GELU.  Each thread group finishes two of the eight frames.
   {
     const float bias = p.wt_bias[c];
+    const long long tap_stride = (long long)p.num_embeddings * kCondE;
 #pragma unroll
     for (int j = 0; j < FPG; ++j) {
       const int f = g * FPG + j;
-      const float y = bias + ((s_part[0][f][c] + s_part[1][f][c]) + (s_part[2][f][c] + s_part[3][f][c]));
+      const int h = f >> 1;                                 // unit i0 + h is s_id[h + 1]
+      const int id0 = s_id[h + 1];
+      const int idn = (f & 1) ? s_id[h + 2] : s_id[h];      // odd frames look ahead, even frames look back
+      const int t_self = (f & 1) ? 2 : 1, t_nb = (f & 1) ? 0 : 3;
+      float y = bias;
+      if (id0 >= 0) y += p.tab[t_self * tap_stride + (long long)id0 * kCondE + c];
+      if (idn >= 0) y += p.tab[t_nb * tap_stride + (long long)idn * kCondE + c];
       s_act[f][c] = 0.5f * y * (1.0f + erff(y * 0.70710678118654752440f));
     }
   }
   __syncthreads();
+  float acc[kCondFrames];
   // (4) fc, same split
 #pragma unroll
   for (int f = 0; f < kCondFrames; ++f) acc[f] = 0.f;

@@ -107,6 +107,7 @@ struct l2s_vocoder {
   bool finalized = false;
   int device = -1, num_sms = 0;
   // device-side small weights
+  float* d_unit_tab = nullptr;   // [4][num_embeddings][E]: the unit table folded through the ConvTranspose1d taps
   float *d_dict = nullptr, *d_spk_w = nullptr, *d_spk_b = nullptr, *d_wt = nullptr, *d_wt_b = nullptr, *d_fc_t = nullptr,
         *d_fc_b = nullptr, *d_post_w = nullptr;
   float post_bias = 0.f;
@@ -737,6 +738,7 @@ int forward_impl(l2s_vocoder* v, void* stream, const int64_t* code, const void* 
     cp.spk_vec = ws.spk_vec;
     cp.dict = v->d_dict;
     cp.wt = v->d_wt;
+    cp.tab = v->d_unit_tab;
     cp.wt_bias = v->d_wt_b;
     cp.fc_t = v->d_fc_t;
     cp.fc_bias = v->d_fc_b;
@@ -943,6 +945,25 @@ int l2s_finalize(l2s_vocoder* v, int device) {
     v->d_wt = dev_upload<float>(v, wt.data(), wt.size(), &e);
     if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, cudaGetErrorString(e));
     v->d_wt_b = dev_upload<float>(v, v->weights["layer.0.bias"].data(), E, &e);
+    {
+      // tab[j][id][co] = sum_ci dict[id][ci] * W[ci][co][j], accumulated in double and rounded once
+      const std::vector<float>& d = v->weights["dict.weight"];
+      const int n_emb = c.num_embeddings;
+      std::vector<float> tab((size_t)4 * n_emb * E);
+      std::vector<double> acc((size_t)E);
+      for (int j = 0; j < 4; ++j)
+        for (int id = 0; id < n_emb; ++id) {
+          std::fill(acc.begin(), acc.end(), 0.0);
+          for (int ci = 0; ci < E; ++ci) {
+            const double x = d[(size_t)id * E + ci];
+            const float* wrow = &wt[((size_t)j * E + ci) * E];
+            for (int co = 0; co < E; ++co) acc[co] += x * (double)wrow[co];
+          }
+          for (int co = 0; co < E; ++co) tab[((size_t)j * n_emb + id) * E + co] = (float)acc[co];
+        }
+      v->d_unit_tab = dev_upload<float>(v, tab.data(), tab.size(), &e);
+      if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, cudaGetErrorString(e));
+    }
     const std::vector<float>& fw = v->weights["fc.weight"];   // (out, in)
     std::vector<float> ft((size_t)E * E);
     for (int o = 0; o < E; ++o)
