@@ -29,6 +29,7 @@
 namespace l2s {
 
 inline int g_pair_pref = 0;   // planning experiment switch (knob pair_pref)
+inline int g_pair_cg2 = 1;    // cluster plans run cta_group::2 MMAs (knob cg2)
 
 struct PairGeom {
   int c;             // channels (= cin = cout = MMA N)
@@ -46,6 +47,8 @@ struct PairGeom {
   int alias_at;          // 1: the A-slab ring lives inside the T-slab region (c1's inputs are dead once T is written)
   int region_bytes;      // shared memory of the A ring + T slab (max of the two when aliased)
   int cluster;           // 1, or 2: CTA pairs fetch each weight stage from L2 once (TMA multicast)
+  int cg2;               // cluster == 2 only: the pair runs cta_group::2 MMAs (M = 256: both CTAs' row tiles in one instruction,
+                         // each CTA holds and supplies HALF of every weight stage; only the leader CTA issues)
   int dual;              // planned so that two CTAs share one SM (<= 110 KB smem, <= 256 TMEM columns, 80 registers)
   int tile_words;        // fp32 words of one warp's transpose tile (32 rows x cw), or of its TMA staging (epi_tma)
   int epi_tma;           // 1: phase 2 streams the residual in and the results out with TMA through per-warp staging
@@ -259,12 +262,12 @@ __device__ __forceinline__ void epilogue_item_tma(const ConvParams& p, const Pai
 
 // MMAs of one weight stage for all msub accumulators with every stride and the instruction descriptor as
 // immediates (C >= 64: 128-byte operand rows, four K = 16 slices per 64-channel chunk).
-template <int C>
+template <int C, bool CG2 = false>
 __device__ __forceinline__ void pair_issue_stage(bool leader, int msub, uint32_t desc_hi, uint32_t a_lo, uint32_t tap_step,
                                                  uint32_t b_lo, int tap0, int t_end, uint32_t first_or, uint32_t d_base) {
   constexpr uint32_t kSubStep = (128u * 128u) >> 4;
-  constexpr uint32_t kTapW = ((uint32_t)C * 128u) >> 4;
-  constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)C >> 3) << 17) | ((128u >> 4) << 24);
+  constexpr uint32_t kTapW = ((uint32_t)(CG2 ? C / 2 : C) * 128u) >> 4;   // CTA pair: a CTA holds half of the weight rows
+  constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)C >> 3) << 17) | (((CG2 ? 256u : 128u) >> 4) << 24);
   uint32_t a_tap = a_lo + (uint32_t)tap0 * tap_step;
   for (int t = 0; t < t_end; ++t, b_lo += kTapW, a_tap += tap_step) {
     const uint32_t first = first_or | (uint32_t)(tap0 + t);
@@ -275,13 +278,16 @@ __device__ __forceinline__ void pair_issue_stage(bool leader, int msub, uint32_t
       for (int k = 0; k < 4; ++k) {
         const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(a_sub + 2u * k);
         const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2u * k);
-        if (leader) umma_bf16(d_addr, da, db, kIdesc, (first | (uint32_t)k) != 0u ? 1u : 0u);
+        if (leader) {
+          if constexpr (CG2) umma_bf16_cg2(d_addr, da, db, kIdesc, (first | (uint32_t)k) != 0u ? 1u : 0u);
+          else umma_bf16(d_addr, da, db, kIdesc, (first | (uint32_t)k) != 0u ? 1u : 0u);
+        }
       }
     }
   }
 }
 
-template <int MODE, bool DUAL, bool EPI_TMA>
+template <int MODE, bool DUAL, bool EPI_TMA, bool CG2 = false>
 __global__ void __maxnreg__(DUAL ? 80 : 168)
 pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
                const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmRes,
@@ -331,11 +337,11 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
     for (int i = 0; i < g.sa; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < g.sb; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], (uint32_t)g.cluster); }
+    for (int i = 0; i < g.sb; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], CG2 ? 1u : (uint32_t)g.cluster); }
     mbar_init(d1_full, 1);
-    mbar_init(t_full, kTcEpiWarps);
+    mbar_init(t_full, (CG2 ? 2 : 1) * kTcEpiWarps);     // CTA pair: the leader's barrier collects both CTAs' epilogue warps
     mbar_init(d2_full, 1);
-    mbar_init(d2_empty, kTcEpiWarps);
+    mbar_init(d2_empty, (CG2 ? 2 : 1) * kTcEpiWarps);
     mbar_init(t_free, 1);
     if (EPI_TMA) {
       for (int i = 0; i < 2 * kTcEpiWarps; ++i) mbar_init(&res_full[i], 1);
@@ -344,7 +350,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc_dyn(tmem_slot, (uint32_t)g.tmem_cols);
+  if (warp == 1) { if constexpr (CG2) tmem_alloc_cg2(tmem_slot, (uint32_t)g.tmem_cols); else tmem_alloc_dyn(tmem_slot, (uint32_t)g.tmem_cols); }
   if (warp >= 2) {
     // rows [mt, t_rows) of every T chunk are read by the last taps of c2 but never written: zero them once
     const int tail_bytes = (g.t_rows - g.mt) * g.rb;
@@ -396,15 +402,26 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&a_empty[ia], pa ^ 1u);
         if (kc == 0) L2S_TRACE(0, it_no, 1);
         if (leader) {
-          mbar_expect_tx(&a_full[ia], (uint32_t)g.slab_bytes);
           uint8_t* dst = slabA + (size_t)ia * g.slab_bytes;
-          for (int l = 0; l < g.n_loads; ++l)
-            tma_load_3d(dst + (size_t)l * box_bytes, &tmA, &a_full[ia], ch0, row0 + l * g.box_rows, b);
+          if constexpr (CG2) {   // both CTAs' slabs complete on the pair leader's barrier
+            if (crank == 0) mbar_expect_tx(&a_full[ia], 2u * (uint32_t)g.slab_bytes);
+            for (int l = 0; l < g.n_loads; ++l)
+              tma_load_3d_cg2(dst + (size_t)l * box_bytes, &tmA, &a_full[ia], ch0, row0 + l * g.box_rows, b);
+          } else {
+            mbar_expect_tx(&a_full[ia], (uint32_t)g.slab_bytes);
+            for (int l = 0; l < g.n_loads; ++l)
+              tma_load_3d(dst + (size_t)l * box_bytes, &tmA, &a_full[ia], ch0, row0 + l * g.box_rows, b);
+          }
         }
         if (++ia == g.sa) { ia = 0; pa ^= 1u; }
         for (int ts = 0; ts < g.n_tstages; ++ts) {
           mbar_wait(&b_empty[ib], pb ^ 1u);
-          if (leader) {
+          if constexpr (CG2) {   // this CTA's half of the stage, at the stage base; bytes counted on the leader's barrier
+            if (leader) {
+              if (crank == 0) mbar_expect_tx(&b_full[ib], (uint32_t)g.bstage_bytes);
+              tma_load_3d_cg2(stageB + (size_t)ib * g.bstage_bytes, &tmW1, &b_full[ib], ch0, crank * half_rows, ts * g.tb);
+            }
+          } else if (leader) {
             mbar_expect_tx(&b_full[ib], (uint32_t)g.bstage_bytes);
             if (g.cluster > 1)
               tma_load_3d_mc(stageB + (size_t)ib * g.bstage_bytes + (size_t)crank * half_rows * g.rb, &tmW1, &b_full[ib], ch0,
@@ -419,7 +436,12 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ch0 = kc * (g.rb >> 1);
         for (int ts = 0; ts < g.n_tstages; ++ts) {
           mbar_wait(&b_empty[ib], pb ^ 1u);
-          if (leader) {
+          if constexpr (CG2) {
+            if (leader) {
+              if (crank == 0) mbar_expect_tx(&b_full[ib], (uint32_t)g.bstage_bytes);
+              tma_load_3d_cg2(stageB + (size_t)ib * g.bstage_bytes, &tmW2, &b_full[ib], ch0, crank * half_rows, ts * g.tb);
+            }
+          } else if (leader) {
             mbar_expect_tx(&b_full[ib], (uint32_t)g.bstage_bytes);
             if (g.cluster > 1)
               tma_load_3d_mc(stageB + (size_t)ib * g.bstage_bytes + (size_t)crank * half_rows * g.rb, &tmW2, &b_full[ib], ch0,
@@ -444,7 +466,13 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int ia = 0, ib = 0;
     uint32_t pa = 0, pb = 0, pt = 0, pd2 = 0;
     int it_no = 0;
-    for (int w = walk0; w < walk_n; w += walkers, ++it_no) {
+    constexpr bool cg2 = CG2;
+    auto commit = [&](uint64_t* bar, bool both) {   // both: the partner CTA waits on its own copy of this barrier too
+      if constexpr (CG2) umma_commit_cg2(bar, mc_mask);
+      else if (both && g.cluster > 1) umma_commit_mc(bar, mc_mask);
+      else umma_commit(bar);
+    };
+    for (int w = (cg2 && crank != 0) ? walk_n : walk0; w < walk_n; w += walkers, ++it_no) {   // CTA pair: the leader issues for both
       // ---- c1: D1 += xa(slab, row shift j*d) . W1[j]
       for (int kc = 0; kc < g.kc; ++kc) {
         if (kc == 0) L2S_TRACE(1, it_no, 0);
@@ -457,7 +485,11 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           uint32_t b_lo = desc_lo_fixed | ((smem_u32(stageB + (size_t)ib * g.bstage_bytes) & 0x3FFFFu) >> 4);
           const int t_end = min(g.tb, g.k - ts * g.tb);
-          if (g.c == 256) { pair_issue_stage<256>(leader, g.msub, desc_hi, a_lo, (uint32_t)g.dil * row_step, b_lo, ts * g.tb, t_end, (uint32_t)kc, tmem_base); }
+          if constexpr (CG2) {
+            if (g.c == 256) pair_issue_stage<256, true>(leader, g.msub, desc_hi, a_lo, (uint32_t)g.dil * row_step, b_lo, ts * g.tb, t_end, (uint32_t)kc, tmem_base);
+            else pair_issue_stage<128, true>(leader, g.msub, desc_hi, a_lo, (uint32_t)g.dil * row_step, b_lo, ts * g.tb, t_end, (uint32_t)kc, tmem_base);
+          }
+          else if (g.c == 256) { pair_issue_stage<256>(leader, g.msub, desc_hi, a_lo, (uint32_t)g.dil * row_step, b_lo, ts * g.tb, t_end, (uint32_t)kc, tmem_base); }
           else if (g.c == 128) { pair_issue_stage<128>(leader, g.msub, desc_hi, a_lo, (uint32_t)g.dil * row_step, b_lo, ts * g.tb, t_end, (uint32_t)kc, tmem_base); }
           else for (int t = 0; t < t_end; ++t, b_lo += tapw_step) {
             const int tap = ts * g.tb + t;
@@ -475,18 +507,18 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 issue_chunk<1>(leader, d_addr, desc_hi, a_sub, b_lo, g.idesc, first);
             }
           }
-          if (leader) { if (g.cluster > 1) umma_commit_mc(&b_empty[ib], mc_mask); else umma_commit(&b_empty[ib]); }
+          if (leader) commit(&b_empty[ib], true);
           if (++ib == g.sb) { ib = 0; pb ^= 1u; }
         }
-        if (leader) umma_commit(&a_empty[ia]);
+        if (leader) commit(&a_empty[ia], false);
         if (++ia == g.sa) { ia = 0; pa ^= 1u; }
       }
-      if (leader) umma_commit(d1_full);
+      if (leader) commit(d1_full, false);
       L2S_TRACE(1, it_no, 2);
       // ---- c2: D2 += T(slab, row shift j) . W2[j]   (T written by the epilogue warps)
-      mbar_wait(t_full, pt);
+      if constexpr (CG2) mbar_wait_cluster(t_full, pt); else mbar_wait(t_full, pt);
       pt ^= 1u;
-      mbar_wait(d2_empty, pd2 ^ 1u);
+      if constexpr (CG2) mbar_wait_cluster(d2_empty, pd2 ^ 1u); else mbar_wait(d2_empty, pd2 ^ 1u);
       pd2 ^= 1u;
       L2S_TRACE(1, it_no, 3);
       tc_fence_after();
@@ -497,7 +529,11 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           uint32_t b_lo = desc_lo_fixed | ((smem_u32(stageB + (size_t)ib * g.bstage_bytes) & 0x3FFFFu) >> 4);
           const int t_end = min(g.tb, g.k - ts * g.tb);
-          if (g.c == 256) { pair_issue_stage<256>(leader, g.msub, desc_hi, t_lo, row_step, b_lo, ts * g.tb, t_end, (uint32_t)kc, tmem_base + (uint32_t)acc_cols); }
+          if constexpr (CG2) {
+            if (g.c == 256) pair_issue_stage<256, true>(leader, g.msub, desc_hi, t_lo, row_step, b_lo, ts * g.tb, t_end, (uint32_t)kc, tmem_base + (uint32_t)acc_cols);
+            else pair_issue_stage<128, true>(leader, g.msub, desc_hi, t_lo, row_step, b_lo, ts * g.tb, t_end, (uint32_t)kc, tmem_base + (uint32_t)acc_cols);
+          }
+          else if (g.c == 256) { pair_issue_stage<256>(leader, g.msub, desc_hi, t_lo, row_step, b_lo, ts * g.tb, t_end, (uint32_t)kc, tmem_base + (uint32_t)acc_cols); }
           else if (g.c == 128) { pair_issue_stage<128>(leader, g.msub, desc_hi, t_lo, row_step, b_lo, ts * g.tb, t_end, (uint32_t)kc, tmem_base + (uint32_t)acc_cols); }
           else for (int t = 0; t < t_end; ++t, b_lo += tapw_step) {
             const int tap = ts * g.tb + t;
@@ -515,11 +551,11 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 issue_chunk<1>(leader, d_addr, desc_hi, a_sub, b_lo, g.idesc, first);
             }
           }
-          if (leader) { if (g.cluster > 1) umma_commit_mc(&b_empty[ib], mc_mask); else umma_commit(&b_empty[ib]); }
+          if (leader) commit(&b_empty[ib], true);
           if (++ib == g.sb) { ib = 0; pb ^= 1u; }
         }
       }
-      if (leader) { umma_commit(d2_full); umma_commit(t_free); }
+      if (leader) { commit(d2_full, false); commit(t_free, false); }
     }
   } else {
     // ---------------------------------------------------------------- epilogue
@@ -574,7 +610,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(t_full);
+      if (lane == 0) { if constexpr (CG2) mbar_arrive_cluster(t_full, 0u); else mbar_arrive(t_full); }   // CTA pair: the leader's MMA thread waits
       if (warp == 2) L2S_TRACE(2, it_no, 1);
       // ---- phase 2: D2 -> global (the wait on d2_full happens inside, after the first residual loads are issued)
       {
@@ -596,7 +632,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (warp == 2) L2S_TRACE(2, it_no, 2);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(d2_empty);
+      if (lane == 0) { if constexpr (CG2) mbar_arrive_cluster(d2_empty, 0u); else mbar_arrive(d2_empty); }
       if (warp == 2) L2S_TRACE(2, it_no, 3);
     }
     if (EPI_TMA && lane == 0) bulk_wait_all();   // every TMA store has landed before the CTA exits
@@ -611,7 +647,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (P.span && threadIdx.x == 0) atomicMax(&P.span[1], (unsigned long long)gtime());
   if (P.trace && threadIdx.x == 0 && blockIdx.x < 512) P.trace[768 + blockIdx.x * 3 + 2] = gtime();
   if (g.cluster > 1) cluster_sync_all();      // no CTA leaves while its partner may still multicast into it
-  if (warp == 1) tmem_dealloc_dyn(tmem_base, (uint32_t)g.tmem_cols);
+  if (warp == 1) { if constexpr (CG2) tmem_dealloc_cg2(tmem_base, (uint32_t)g.tmem_cols); else tmem_dealloc_dyn(tmem_base, (uint32_t)g.tmem_cols); }
 }
 
 // ------------------------------------------------------------------ host side
@@ -685,7 +721,9 @@ inline bool pair_plan_with(int c, int k, int dil, int lin, int batch, int smem_b
     g.total_items = batch * g.m_items;
     g.idesc = umma_idesc_bf16(128u, (uint32_t)c);
     // weight multicast pays where weights dominate the L2 traffic and a stage is one tap (tb == 1): C >= 128
-    g.cluster = (!dual && cluster_ok && c >= 128 && g.tb == 1 && (c / 2) % 8 == 0 && g.total_items >= 2) ? 2 : 1;
+    // plain weight multicast only for one-CTA-per-SM plans; cta_group::2 pairs also for the two-CTAs-per-SM plans
+    g.cluster = ((!dual || g_pair_cg2) && cluster_ok && c >= 128 && g.tb == 1 && (c / 2) % 8 == 0 && g.total_items >= 2) ? 2 : 1;
+    g.cg2 = (g.cluster == 2 && g_pair_cg2 && (c == 128 || c == 256) && !g.epi_tma) ? 1 : 0;
     *out = g;
     return true;
   }
@@ -702,7 +740,7 @@ inline bool pair_plan(int c, int k, int dil, int lin, int batch, int smem_budget
   if (allow_dual && want_tma &&
       pair_plan_with(c, k, dil, lin, batch, 112 * 1024, true, false, allow_alias, 16, 2, true, want_tma_alias, out) && out->epi_tma)
     return true;
-  if (allow_dual && pair_plan_with(c, k, dil, lin, batch, 112 * 1024, true, false, allow_alias, 16, 2, false, false, out)) return true;
+  if (allow_dual && pair_plan_with(c, k, dil, lin, batch, 112 * 1024, true, allow_cluster && g_pair_cg2 != 0, allow_alias, 16, 2, false, false, out)) return true;
   // single CTA per SM: 32-column epilogue chunks (full 128-byte lines) as long as >= 3 weight stages still fit,
   // else 16-column chunks (smaller transpose tiles) so the room goes to the weight ring
   if (g_pair_pref == 1 && c >= 256 &&
@@ -716,16 +754,16 @@ struct PairEpiMaps {
   CUtensorMap res, raw, raw_tail, act, act_tail;   // only read by the EPI_TMA kernels
 };
 
-template <int MODE, bool DUAL, bool EPI_TMA>
+template <int MODE, bool DUAL, bool EPI_TMA, bool CG2 = false>
 inline cudaError_t launch_pair_mode(const PairParams& P, const CUtensorMap& tmA, const CUtensorMap& tmW1,
                                     const CUtensorMap& tmW2, const PairEpiMaps& em, int grid, cudaStream_t stream) {
   static bool configured[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(pair_tc_kernel<MODE, DUAL, EPI_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(pair_tc_kernel<MODE, DUAL, EPI_TMA, CG2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(pair_tc_kernel<MODE, DUAL, EPI_TMA>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(pair_tc_kernel<MODE, DUAL, EPI_TMA, CG2>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     configured[dev] = true;
@@ -751,7 +789,7 @@ inline cudaError_t launch_pair_mode(const PairParams& P, const CUtensorMap& tmA,
   }
   cfg.attrs = attr;
   cfg.numAttrs = (unsigned)na;
-  return cudaLaunchKernelEx(&cfg, pair_tc_kernel<MODE, DUAL, EPI_TMA>, tmA, tmW1, tmW2, em.res, em.raw, em.raw_tail, em.act,
+  return cudaLaunchKernelEx(&cfg, pair_tc_kernel<MODE, DUAL, EPI_TMA, CG2>, tmA, tmW1, tmW2, em.res, em.raw, em.raw_tail, em.act,
                             em.act_tail, P);
 }
 
@@ -780,6 +818,17 @@ inline cudaError_t launch_pair_tc(const ConvParams& c, const float* bias1, const
     if (mode == 5) return launch_pair_mode<5, true, true>(P, tmA, tmW1, tmW2, em, grid, stream);
     if (mode == 13) return launch_pair_mode<13, true, true>(P, tmA, tmW1, tmW2, em, grid, stream);
     return cudaErrorInvalidValue;
+  }
+  if (g.cg2) {       // CTA pairs issuing cta_group::2 MMAs: its own instantiations (see pair_tc_kernel)
+    switch (mode) {
+#define L2S_PMODE2(m)                                                                                  \
+  case m:                                                                                              \
+    return g.dual ? launch_pair_mode<m, true, false, true>(P, tmA, tmW1, tmW2, em, grid, stream)       \
+                  : launch_pair_mode<m, false, false, true>(P, tmA, tmW1, tmW2, em, grid, stream);
+      L2S_PMODE2(5) L2S_PMODE2(7) L2S_PMODE2(11) L2S_PMODE2(13) L2S_PMODE2(15)
+#undef L2S_PMODE2
+      default: return cudaErrorInvalidValue;
+    }
   }
   switch (mode) {
 #define L2S_PMODE(m)                                                                          \

@@ -34,8 +34,9 @@ struct Knobs {
   long long dual = 1;
   long long span_ptr = 0;          // device array [launch][2]: min CTA start / max CTA end of every tcgen05 launch
   long long trace_launch = -1;     // index of the fused-step launch of a forward that gets trace_ptr
-  long long cluster = 0;           // fused steps with C >= 128: CTA pairs share weight loads (TMA multicast); measured
-                                   // neutral on B200 (the weight ring depth, not L2 read volume, bounds those layers)
+  long long cluster = 1;           // fused steps with C >= 128 run as CTA pairs (cluster of 2).  With cg2 (default) the pair issues
+                                   // cta_group::2 MMAs: each CTA holds half of every weight stage (stage 0 -9 %, stage 1 -4 %).
+                                   // Plain weight multicast (cg2 = 0) measured neutral.
   long long alias_at = 1;          // fused steps with C >= 128: A-slab ring shares the T-slab shared memory
   long long epi_tma = 0;           // dual fused steps (C <= 64, residual + raw [+ act]): TMA-streamed phase 2 (1: where it fits
                                    // without aliasing, 2: also aliased).  Bit-exact, measured neutral: TMA-store completion
@@ -1170,6 +1171,7 @@ int l2s_debug_set(const char* key, int64_t value) {
   else if (k == "epi_tma") g_knobs.epi_tma = value;
   else if (k == "pdl") g_tc_pdl = (int)value;
   else if (k == "pair_pref") g_pair_pref = (int)value;
+  else if (k == "cg2") g_pair_cg2 = (int)value;
   else if (k == "pair_smem") g_knobs.pair_smem = value;
   else if (k == "epi_prof") { int on = (int)value; cudaMemcpyToSymbol(g_epi_prof_on, &on, sizeof on); }
   else if (k == "trace_launch") g_knobs.trace_launch = value;

@@ -300,10 +300,10 @@ def test_whole_resblock_tilings_agree(pkg, weights, knob, value):
     assert torch.equal(a, b), float((a - b).abs().max())
 
 
-@pytest.mark.parametrize("knob", ["dual", "cluster", "alias_at", "epi_tma", "pdl"])
+@pytest.mark.parametrize("knob", ["dual", "cluster", "cg2", "alias_at", "epi_tma", "pdl"])
 def test_fused_kernel_variants_agree(pkg, weights, knob):
-    """Two-CTAs-per-SM plans (dual) and CTA-pair weight multicast (cluster) change scheduling only:
-    the waveform must not change by a bit."""
+    """Two-CTAs-per-SM plans (dual), CTA pairs (cluster) with plain weight multicast or cta_group::2 MMAs (cg2) and
+    the other fused-step variants change scheduling only: the waveform must not change by a bit."""
     h, sds = weights
     code, mel, spkr = vo.synthetic_inputs(3, 150, seed=33)
     g = make_gen(pkg, h, sds["trained"], "bf16")
@@ -316,7 +316,8 @@ def test_fused_kernel_variants_agree(pkg, weights, knob):
             outs.append(g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV)).clone())
     finally:
         lib.l2s_debug_set(b"dual", 1)
-        lib.l2s_debug_set(b"cluster", 0)
+        lib.l2s_debug_set(b"cluster", 1)
+        lib.l2s_debug_set(b"cg2", 1)
         lib.l2s_debug_set(b"alias_at", 1)
         lib.l2s_debug_set(b"epi_tma", 0)
         lib.l2s_debug_set(b"pdl", 0)
