@@ -418,7 +418,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&b_empty[ib], pb ^ 1u);
           if constexpr (CG2) {   // this CTA's half of the stage, at the stage base; bytes counted on the leader's barrier
             if (leader) {
-              if (crank == 0) mbar_expect_tx(&b_full[ib], (uint32_t)g.bstage_bytes);
+              if (crank == 0) mbar_expect_tx(&b_full[ib], 2u * (uint32_t)g.bstage_bytes);   // a stage slot holds this CTA's half
               tma_load_3d_cg2(stageB + (size_t)ib * g.bstage_bytes, &tmW1, &b_full[ib], ch0, crank * half_rows, ts * g.tb);
             }
           } else if (leader) {
@@ -438,7 +438,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&b_empty[ib], pb ^ 1u);
           if constexpr (CG2) {
             if (leader) {
-              if (crank == 0) mbar_expect_tx(&b_full[ib], (uint32_t)g.bstage_bytes);
+              if (crank == 0) mbar_expect_tx(&b_full[ib], 2u * (uint32_t)g.bstage_bytes);
               tma_load_3d_cg2(stageB + (size_t)ib * g.bstage_bytes, &tmW2, &b_full[ib], ch0, crank * half_rows, ts * g.tb);
             }
           } else if (leader) {
@@ -673,7 +673,9 @@ inline bool pair_plan_with(int c, int k, int dil, int lin, int batch, int smem_b
   if (tb > k) tb = k;
   g.tb = tb;
   g.n_tstages = (k + tb - 1) / tb;
-  g.bstage_bytes = tb * c * g.rb;
+  const int full_stage = tb * c * g.rb;
+  // CTA pairs issuing cta_group::2 MMAs keep only their half of every weight stage
+  const bool want_cg2 = (!dual || g_pair_cg2) && cluster_ok && g_pair_cg2 && (c == 128 || c == 256) && tb == 1 && !g.epi_tma;
   const int bar_bytes = 1024 + 512 + 1024 + 1024 + kTcEpiWarps * g.tile_words * 4;   // alignment slack, barriers, staging alignment, bias1, tiles
   int msub = (dual ? 128 : 256) / c;
   if (msub < 1) msub = 1;
@@ -696,6 +698,10 @@ inline bool pair_plan_with(int c, int k, int dil, int lin, int batch, int smem_b
     // give the ring the room by letting the A-slab ring share the T-slab region.
     g.alias_at = (alias_ok && (c >= 128 || force_alias)) ? 1 : 0;
     const int t_bytes = g.kc * g.t_chunk_bytes;
+    g.m_items = (lin + g.r_out - 1) / g.r_out;
+    g.total_items = batch * g.m_items;
+    const bool cg2_here = want_cg2 && g.total_items >= 2;
+    g.bstage_bytes = cg2_here ? full_stage / 2 : full_stage;
     int sa = g.kc + 1 < 4 ? g.kc + 1 : 4, sb = 4;
     auto region = [&](int sa_) {
       const int a_bytes = sa_ * g.slab_bytes;
@@ -717,13 +723,12 @@ inline bool pair_plan_with(int c, int k, int dil, int lin, int batch, int smem_b
     while (cols < 2 * msub * c) cols <<= 1;
     if (cols > (dual ? 256 : 512)) continue;
     g.tmem_cols = cols;
-    g.m_items = (lin + g.r_out - 1) / g.r_out;
-    g.total_items = batch * g.m_items;
     g.idesc = umma_idesc_bf16(128u, (uint32_t)c);
     // weight multicast pays where weights dominate the L2 traffic and a stage is one tap (tb == 1): C >= 128
     // plain weight multicast only for one-CTA-per-SM plans; cta_group::2 pairs also for the two-CTAs-per-SM plans
     g.cluster = ((!dual || g_pair_cg2) && cluster_ok && c >= 128 && g.tb == 1 && (c / 2) % 8 == 0 && g.total_items >= 2) ? 2 : 1;
-    g.cg2 = (g.cluster == 2 && g_pair_cg2 && (c == 128 || c == 256) && !g.epi_tma) ? 1 : 0;
+    g.cg2 = (g.cluster == 2 && cg2_here) ? 1 : 0;
+    if (cg2_here && !g.cg2) continue;   // (cannot happen: the same conditions) stage size and mode must agree
     *out = g;
     return true;
   }
