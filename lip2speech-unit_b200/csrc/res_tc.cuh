@@ -48,6 +48,7 @@ struct ResGeom {
   int tmem_cols, cw, dual, tile_words;
   int ne;                   // epilogue warps: 8, or 4 in the four-CTAs-per-SM plans (one warp per TMEM lane quadrant)
   int ctas_per_sm;          // 1, 2 (dual) or 4 (quad)
+  int cg2;                  // 1: CTA pairs (cluster of 2) issue cta_group::2 MMAs; a CTA keeps half of every weight stage
   uint32_t idesc;
   int smem_bytes;
 };
@@ -172,9 +173,8 @@ __device__ __forceinline__ void res_addbias_x(const ResGeom& g, const ResLane& w
 // loads: a row is 64..256 contiguous bytes, so the sectors it touches are fully used by this lane's consecutive
 // loads (L1 serves the second half), and no shared-memory transpose is needed on the way in.
 __device__ __forceinline__ void res_load_x(const ResParams& P, const ResLane& w, uint8_t* slab, uint32_t x_quad, int b,
-                                           int t_row0, const float* sbias2) {
-  const ResGeom& g = P.g;
-  const int lin = P.c.lin;
+                                           int t_row0, const float* sbias2, int lin) {
+  const ResGeom& g = P.g;   // lin: rows of the utterance (0 for the dummy item of an odd CTA pair: everything reads as zero)
   const int n_units = (g.msub * g.c) >> 5;
   const int cmask = g.c - 1;
   const bool c16 = g.c == 16;
@@ -306,14 +306,14 @@ __device__ __forceinline__ void res_output(const ConvParams& p, float* tile, uin
 // instruction descriptor and every descriptor stride are immediates: with run-time values the compiler re-loaded
 // them from the constant bank next to every UTCHMMA, and those dependent loads (not the tensor core) set the pace
 // of these small N = C MMAs.
-template <int C>
+template <int C, bool CG2 = false>
 __device__ __forceinline__ void res_issue_stage(bool leader, int msub, uint32_t desc_hi, uint32_t a_tap0_lo, uint32_t tap_step,
                                                 uint32_t b_lo, int tap0, int t_end, uint32_t d_base) {
   constexpr int K16 = C / 16;
   constexpr uint32_t kRb = 2 * C;
   constexpr uint32_t kSubStep = (128u * kRb) >> 4;
-  constexpr uint32_t kTapW = ((uint32_t)C * kRb) >> 4;
-  constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)C >> 3) << 17) | ((128u >> 4) << 24);
+  constexpr uint32_t kTapW = ((uint32_t)(CG2 ? C / 2 : C) * kRb) >> 4;      // CTA pair: a CTA holds half of the weight rows
+  constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)C >> 3) << 17) | (((CG2 ? 256u : 128u) >> 4) << 24);
   uint32_t a_tap = a_tap0_lo + (uint32_t)tap0 * tap_step;
   for (int t = 0; t < t_end; ++t, b_lo += kTapW, a_tap += tap_step) {
     uint32_t a_sub = a_tap;
@@ -323,13 +323,19 @@ __device__ __forceinline__ void res_issue_stage(bool leader, int msub, uint32_t 
       for (int k = 0; k < K16; ++k) {
         const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(a_sub + 2u * k);
         const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2u * k);
-        if (leader) umma_bf16(d_addr, da, db, kIdesc, 1u);    // both convs accumulate: D1 starts as the bias, X as x
+        if (leader) {                                         // both convs accumulate: D1 starts as the bias, X as x
+          if constexpr (CG2) umma_bf16_cg2(d_addr, da, db, kIdesc, 1u); else umma_bf16(d_addr, da, db, kIdesc, 1u);
+        }
       }
     }
   }
 }
 
-template <int MODE, bool DUAL>
+// CG2: the grid is launched as CTA pairs (cluster of 2) walking items 2j, 2j + 1 in lockstep; the leader CTA's MMA
+// thread issues cta_group::2 MMAs (M = 256: both tiles), each CTA loads HALF of every weight stage and keeps its own
+// X / D1 / S; barriers the MMA thread waits on live in the leader and collect both CTAs' arrivals, its commits are
+// multicast to both.  (Own instantiation: a kernel that contains cta_group::2 code cannot be launched without a cluster.)
+template <int MODE, bool DUAL, bool CG2 = false>
 __global__ void __maxnreg__(DUAL ? 80 : 168)
 res_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -356,11 +362,11 @@ res_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 2 * g.n_dil; ++i) tma_prefetch_desc(&maps.w[i]);
     for (int i = 0; i < g.sb; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    mbar_init(s_full, (uint32_t)g.ne);
+    mbar_init(s_full, (uint32_t)(CG2 ? 2 * g.ne : g.ne));
     mbar_init(d_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc_dyn(tmem_slot, (uint32_t)g.tmem_cols);
+  if (warp == 1) { if constexpr (CG2) tmem_alloc_cg2(tmem_slot, (uint32_t)g.tmem_cols); else tmem_alloc_dyn(tmem_slot, (uint32_t)g.tmem_cols); }
   if (warp >= 2) {
     // the pad rows above and below the tile are read by the outer taps but never written: zero them once
     const int pad_bytes = g.pad * g.rb;
@@ -378,19 +384,26 @@ res_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG2) cluster_sync_all();        // the partner's barriers exist before anything is signalled to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int acc_cols = g.msub * g.c;            // X at [0, acc_cols), D1 at [acc_cols, 2 acc_cols)
+  // item walk: a CTA pair advances in lockstep (pair j handles items 2j + rank); an odd total leaves a dummy item
+  const int crank = CG2 ? (int)cluster_ctarank() : 0;
+  const int walkers = CG2 ? (int)gridDim.x / 2 : (int)gridDim.x;
+  const int walk0 = CG2 ? (int)blockIdx.x / 2 : (int)blockIdx.x;
+  const int walk_n = CG2 ? (g.total_items + 1) / 2 : g.total_items;
+  auto item_of = [&](int wk) { return CG2 ? 2 * wk + crank : wk; };
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (weights only)
     const bool leader = elect_one();
     int ib = 0;
     uint32_t pb = 0;
-    for (int item = blockIdx.x; item < g.total_items; item += gridDim.x) {
+    for (int wk = walk0; wk < walk_n; wk += walkers) {
       // The next item's x (and branch-sum) rows are one contiguous range: pull them into L2 now, a whole item
       // ahead, so that the load phase and the output epilogue see L2 latency instead of DRAM latency.
-      const int nxt = item + (int)gridDim.x;
+      const int nxt = wk + walkers < walk_n ? item_of(wk + walkers) : g.total_items;
       if (leader && nxt < g.total_items) {
         const int nb = nxt / g.m_items;
         const int nq = (nxt - nb * g.m_items) * g.r_out;
@@ -411,8 +424,13 @@ res_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
         for (int ts = 0; ts < g.n_tstages; ++ts) {
           mbar_wait(&b_empty[ib], pb ^ 1u);
           if (leader) {
-            mbar_expect_tx(&b_full[ib], (uint32_t)g.bstage_bytes);
-            tma_load_3d(stageB + (size_t)ib * g.bstage_bytes, &maps.w[cv], &b_full[ib], 0, 0, ts * g.tb);
+            if constexpr (CG2) {   // this CTA's half of the stage; the bytes of both halves are counted on the leader's barrier
+              if (crank == 0) mbar_expect_tx(&b_full[ib], 2u * (uint32_t)g.bstage_bytes);
+              tma_load_3d_cg2(stageB + (size_t)ib * g.bstage_bytes, &maps.w[cv], &b_full[ib], 0, crank * (g.c / 2), ts * g.tb);
+            } else {
+              mbar_expect_tx(&b_full[ib], (uint32_t)g.bstage_bytes);
+              tma_load_3d(stageB + (size_t)ib * g.bstage_bytes, &maps.w[cv], &b_full[ib], 0, 0, ts * g.tb);
+            }
           }
           if (++ib == g.sb) { ib = 0; pb ^= 1u; }
         }
@@ -429,14 +447,15 @@ res_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
     int ib = 0;
     uint32_t pb = 0, ps = 0;
     int ntr = 0;
-    for (int item = blockIdx.x; item < g.total_items; item += gridDim.x) {
+    auto commit = [&](uint64_t* bar) { if constexpr (CG2) umma_commit_cg2(bar, (uint16_t)3); else umma_commit(bar); };
+    for (int wk = (CG2 && crank != 0) ? walk_n : walk0; wk < walk_n; wk += walkers) {   // CTA pair: the leader issues for both
       for (int cv = 0; cv < 2 * g.n_dil; ++cv) {
         const int st = cv >> 1;
         const bool second = (cv & 1) != 0;
         const int dil = second ? 1 : g.dil[st];
         const int halo = second ? g.h2 : g.h1[st];
         L2S_RTRACE(128, ntr);
-        mbar_wait(s_full, ps);
+        if constexpr (CG2) mbar_wait_cluster(s_full, ps); else mbar_wait(s_full, ps);
         ps ^= 1u;
         tc_fence_after();
         L2S_RTRACE(128, ntr);
@@ -447,13 +466,13 @@ res_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
           tc_fence_after();
           const uint32_t b_lo = desc_lo_fixed | ((smem_u32(stageB + (size_t)ib * g.bstage_bytes) & 0x3FFFFu) >> 4);
           const int t_end = min(g.tb, g.k - ts * g.tb);
-          if (g.c == 64) res_issue_stage<64>(leader, g.msub, desc_hi, a_tap0, (uint32_t)dil * row_step, b_lo, ts * g.tb, t_end, d_base);
-          else if (g.c == 32) res_issue_stage<32>(leader, g.msub, desc_hi, a_tap0, (uint32_t)dil * row_step, b_lo, ts * g.tb, t_end, d_base);
-          else res_issue_stage<16>(leader, g.msub, desc_hi, a_tap0, (uint32_t)dil * row_step, b_lo, ts * g.tb, t_end, d_base);
-          if (leader) umma_commit(&b_empty[ib]);
+          if (g.c == 64) res_issue_stage<64, CG2>(leader, g.msub, desc_hi, a_tap0, (uint32_t)dil * row_step, b_lo, ts * g.tb, t_end, d_base);
+          else if (g.c == 32) res_issue_stage<32, CG2>(leader, g.msub, desc_hi, a_tap0, (uint32_t)dil * row_step, b_lo, ts * g.tb, t_end, d_base);
+          else res_issue_stage<16, CG2>(leader, g.msub, desc_hi, a_tap0, (uint32_t)dil * row_step, b_lo, ts * g.tb, t_end, d_base);
+          if (leader) commit(&b_empty[ib]);
           if (++ib == g.sb) { ib = 0; pb ^= 1u; }
         }
-        if (leader) umma_commit(d_full);
+        if (leader) commit(d_full);
         L2S_RTRACE(128, ntr);
       }
     }
@@ -475,17 +494,20 @@ res_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(s_full);
+      if (lane == 0) { if constexpr (CG2) mbar_arrive_cluster(s_full, 0u); else mbar_arrive(s_full); }   // pair: the leader's MMA thread waits
     };
     res_prebias_d1(g, w, d1_quad, sbias);            // bias of the first c1
-    for (int item = blockIdx.x; item < g.total_items; item += gridDim.x) {
-      const int b = item / g.m_items;
-      const int mi = item - b * g.m_items;
+    for (int wk = walk0; wk < walk_n; wk += walkers) {
+      const int item = item_of(wk);
+      const bool dummy = item >= g.total_items;    // odd item count: the pair's last partner computes on zeros and stores nothing
+      const int b = dummy ? 0 : item / g.m_items;
+      const int mi = dummy ? 0 : item - b * g.m_items;
       const int q0 = mi * g.r_out;                 // first output row of the item
       const int t_row0 = q0 - g.h_tot;             // position of tile row 0
-      const bool edge = t_row0 < 0 || t_row0 + g.mt > p.lin;   // some tile rows lie outside the utterance
+      const int lin = dummy ? 0 : p.lin;
+      const bool edge = t_row0 < 0 || t_row0 + g.mt > lin;     // some tile rows lie outside the utterance
       L2S_RTRACE(0, ntr);
-      res_load_x(P, w, slab, x_quad, b, t_row0, sbias + 64);
+      res_load_x(P, w, slab, x_quad, b, t_row0, sbias + 64, lin);
       L2S_RTRACE(0, ntr);
       publish();
       for (int st = 0; st < g.n_dil; ++st) {
@@ -496,10 +518,10 @@ res_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
         tc_fence_after();
         L2S_RTRACE(0, ntr);
         {
-          long long* tr = (P.trace && blockIdx.x == 0 && warp == 2 && st == 0 && item < 3 * (int)gridDim.x)
+          long long* tr = (!CG2 && P.trace && blockIdx.x == 0 && warp == 2 && st == 0 && item < 3 * (int)gridDim.x)
                               ? P.trace + 256 + 16 * (item / (int)gridDim.x) : nullptr;
-          if (edge) res_phase<true>(g, w, slab, d1_quad, t_row0, p.lin, tr);
-          else res_phase<false>(g, w, slab, d1_quad, t_row0, p.lin, tr);
+          if (edge) res_phase<true>(g, w, slab, d1_quad, t_row0, lin, tr);
+          else res_phase<false>(g, w, slab, d1_quad, t_row0, lin, tr);
         }
         L2S_RTRACE(0, ntr);
         publish();
@@ -510,15 +532,15 @@ res_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
           pd ^= 1u;
           tc_fence_after();
           L2S_RTRACE(0, ntr);
-          if (edge) res_phase<true>(g, w, slab, x_quad, t_row0, p.lin);
-          else res_phase<false>(g, w, slab, x_quad, t_row0, p.lin);
+          if (edge) res_phase<true>(g, w, slab, x_quad, t_row0, lin);
+          else res_phase<false>(g, w, slab, x_quad, t_row0, lin);
           L2S_RTRACE(0, ntr);
           publish();
           res_addbias_x(g, w, x_quad, sbias + (2 * (st + 1) + 1) * 64);           // while the next c1 runs
         }
       }
       // ---- output: X -> global (rows [q0, q0 + r_out) of the tile only)
-      const int row_lim = min(p.lin, q0 + g.r_out);
+      const int row_lim = dummy ? 0 : min(p.lin, q0 + g.r_out);
       if (g.c % CW == 0) res_output<CW, MODE, !DUAL>(p, tile, x_quad, b, t_row0, q0, row_lim, g.msub, g.c, w, d_full, pd);
       else res_output<16, MODE, !DUAL>(p, tile, x_quad, b, t_row0, q0, row_lim, g.msub, g.c, w, d_full, pd);
       pd ^= 1u;
@@ -532,10 +554,13 @@ res_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
   tc_fence_before();
   __syncthreads();
   if (P.span && threadIdx.x == 0) atomicMax(&P.span[1], (unsigned long long)gtime());
-  if (warp == 1) tmem_dealloc_dyn(tmem_base, (uint32_t)g.tmem_cols);
+  if constexpr (CG2) cluster_sync_all();        // no CTA leaves while its partner may still signal it
+  if (warp == 1) { if constexpr (CG2) tmem_dealloc_cg2(tmem_base, (uint32_t)g.tmem_cols); else tmem_dealloc_dyn(tmem_base, (uint32_t)g.tmem_cols); }
 }
 
 // ------------------------------------------------------------------ host side
+
+inline int g_res_cg2 = 1;   // one-CTA-per-SM whole-ResBlock plans run as CTA pairs issuing cta_group::2 MMAs (knob res_cg2)
 
 // kind: 0 = one CTA per SM (168 registers, 32-column epilogue chunks), 1 = two (80 registers, <= 112 KB, <= 256 TMEM
 // columns), 2 = four CTAs per SM with four epilogue warps each (<= 55 KB, <= 128 TMEM columns): more independent
@@ -575,7 +600,13 @@ inline bool res_plan_with(int c, int k, int n_dil, const int* dil, int lin, int 
   if (tb > k) tb = k;
   g.tb = tb;
   g.n_tstages = (k + tb - 1) / tb;
-  g.bstage_bytes = tb * c * g.rb;
+  g.m_items = (lin + g.r_out - 1) / g.r_out;
+  g.total_items = batch * g.m_items;
+  // CTA pairs issuing cta_group::2 MMAs keep half of every weight stage.  Only for the one-CTA-per-SM plans (the
+  // MMA-bound C = 64, k = 11 ResBlock: 281 -> 263 us); with two or four CTAs per SM the pair's lockstep costs more
+  // overlap than the halved weight traffic gains (measured: k = 3 / 7 ResBlocks 10-20 % slower).
+  g.cg2 = (g_res_cg2 && kind == 0 && c >= 32 && g.total_items >= 2) ? 1 : 0;
+  g.bstage_bytes = tb * (g.cg2 ? c / 2 : c) * g.rb;
   g.s_bytes = ((g.mt + 2 * g.pad) * g.rb + 1023) & ~1023;
   if ((msub * c) % 32 != 0) return false;   // the phases walk the TMEM region in 32-column units
   const int fixed = 1024 + 192 + 2 * kResMaxDil * 64 * 4 + g.ne * g.tile_words * 4 + g.s_bytes;   // slack, barriers, biases, tiles, S
@@ -587,8 +618,6 @@ inline bool res_plan_with(int c, int k, int n_dil, const int* dil, int lin, int 
     ++sb;
   g.sb = sb;
   g.smem_bytes = fixed + sb * g.bstage_bytes;
-  g.m_items = (lin + g.r_out - 1) / g.r_out;
-  g.total_items = batch * g.m_items;
   g.idesc = umma_idesc_bf16(128u, (uint32_t)c);
   *out = g;
   return true;
@@ -623,21 +652,32 @@ inline bool res_plan(int c, int k, int n_dil, const int* dil, int lin, int batch
   return true;
 }
 
-template <int MODE, bool DUAL>
+template <int MODE, bool DUAL, bool CG2 = false>
 inline cudaError_t launch_res_mode(const ResParams& P, const ResMaps& maps, int grid, cudaStream_t stream) {
   static bool configured[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(res_tc_kernel<MODE, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(res_tc_kernel<MODE, DUAL, CG2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(res_tc_kernel<MODE, DUAL>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(res_tc_kernel<MODE, DUAL, CG2>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     configured[dev] = true;
   }
-  res_tc_kernel<MODE, DUAL><<<grid, 64 + 32 * P.g.ne, (size_t)P.g.smem_bytes, stream>>>(maps, P);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)(64 + 32 * P.g.ne));
+  cfg.dynamicSmemBytes = (size_t)P.g.smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CG2 ? 1u : 0u;
+  return cudaLaunchKernelEx(&cfg, res_tc_kernel<MODE, DUAL, CG2>, maps, P);
 }
 
 inline cudaError_t launch_res_tc(const ResParams& P, const ResMaps& maps, int num_ctas, cudaStream_t stream) {
@@ -646,10 +686,17 @@ inline cudaError_t launch_res_tc(const ResParams& P, const ResMaps& maps, int nu
   const int cap = num_ctas * g.ctas_per_sm;
   int grid = g.total_items < cap ? g.total_items : cap;
   if (grid < 1) grid = 1;
+  if (g.cg2) {                               // CTA pairs: even grid, one pair per two items at most
+    const int pairs_needed = (g.total_items + 1) / 2;
+    int pairs = cap / 2 < pairs_needed ? cap / 2 : pairs_needed;
+    if (pairs < 1) pairs = 1;
+    grid = 2 * pairs;
+  }
   const int mode = ((c.acc_in || c.div != 1.0f) ? kEpiAcc : 0) | (c.out_raw ? kEpiRaw : 0) | (c.out_act ? kEpiAct : 0);
   switch (mode) {
-#define L2S_RMODE(m)                                                                \
-  case m:                                                                           \
+#define L2S_RMODE(m)                                                                                        \
+  case m:                                                                                                   \
+    if (g.cg2) return g.dual ? launch_res_mode<m, true, true>(P, maps, grid, stream) : launch_res_mode<m, false, true>(P, maps, grid, stream); \
     return g.dual ? launch_res_mode<m, true>(P, maps, grid, stream) : launch_res_mode<m, false>(P, maps, grid, stream);
     L2S_RMODE(4) L2S_RMODE(6) L2S_RMODE(8) L2S_RMODE(10) L2S_RMODE(12) L2S_RMODE(14)
 #undef L2S_RMODE

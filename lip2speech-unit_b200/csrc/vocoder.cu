@@ -498,7 +498,8 @@ int run_res(l2s_vocoder* v, int i, int j, cudaStream_t st, int batch, int lin, c
   for (int m = 0; m < c.n_dil; ++m) {
     ConvLayer& c1 = v->convs[v->rb_c1[i][j][m]];
     ConvLayer& c2 = v->convs[v->rb_c2[i][j][m]];
-    if (!ensure_w_map(c1, g.rb, g.c, g.tb) || !ensure_w_map(c2, g.rb, g.c, g.tb))
+    const int w_rows = g.cg2 ? g.c / 2 : g.c;   // CTA pairs: each CTA loads half of the output-channel rows of a stage
+    if (!ensure_w_map(c1, g.rb, w_rows, g.tb) || !ensure_w_map(c2, g.rb, w_rows, g.tb))
       return fail(v, L2S_ERR_CUDA, "cuTensorMapEncodeTiled failed for the weights of " + c1.name);
     maps.w[2 * m] = c1.tmW;
     maps.w[2 * m + 1] = c2.tmW;
@@ -1166,6 +1167,7 @@ int l2s_debug_set(const char* key, int64_t value) {
   else if (k == "res_msub") g_knobs.res_msub = value;
   else if (k == "res_single_pct") g_res_single_pct = (int)value;
   else if (k == "res_quad_pct") g_res_quad_pct = (int)value;
+  else if (k == "res_cg2") g_res_cg2 = (int)value;
   else if (k == "cluster") g_knobs.cluster = value;
   else if (k == "alias_at") g_knobs.alias_at = value;
   else if (k == "epi_tma") g_knobs.epi_tma = value;
