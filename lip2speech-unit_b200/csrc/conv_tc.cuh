@@ -56,6 +56,7 @@ struct TcGeom {
   int cw;            // epilogue chunk width in columns: 32 when nt % 32 == 0, else 16
   int ctas_per_sm;   // 2: planned so that two CTAs fit one SM
   int total_items;
+  int cg2;               // 1: CTA pairs (cluster of 2) issue cta_group::2 MMAs over two row tiles; a CTA keeps half of a W stage
   int per_tap;           // 1: probe/fallback mode, one A tile per tap by TMA (no row-shifted descriptors)
   uint32_t idesc;
   int smem_bytes;
@@ -364,7 +365,7 @@ __device__ __forceinline__ void epilogue_item_rows(const ConvParams& p, float* t
 }
 
 // K16 consecutive K = 16 slices of one (tap, 64-channel chunk): descriptors advance by 32 bytes.
-template <int K16>
+template <int K16, bool CG2 = false>
 __device__ __forceinline__ void issue_chunk(bool leader, uint32_t d_addr, uint32_t desc_hi, uint32_t a_lo, uint32_t b_lo,
                                             uint32_t idesc, uint32_t first, bool tf32 = false) {
 #pragma unroll
@@ -372,7 +373,8 @@ __device__ __forceinline__ void issue_chunk(bool leader, uint32_t d_addr, uint32
     const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2u * k);
     const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2u * k);
     if (leader) {
-      if (tf32) umma_tf32(d_addr, da, db, idesc, (first | (uint32_t)k) != 0u ? 1u : 0u);
+      if constexpr (CG2) umma_bf16_cg2(d_addr, da, db, idesc, (first | (uint32_t)k) != 0u ? 1u : 0u);   // bf16 plans only
+      else if (tf32) umma_tf32(d_addr, da, db, idesc, (first | (uint32_t)k) != 0u ? 1u : 0u);
       else umma_bf16(d_addr, da, db, idesc, (first | (uint32_t)k) != 0u ? 1u : 0u);
     }
   }
@@ -381,7 +383,10 @@ __device__ __forceinline__ void issue_chunk(bool leader, uint32_t d_addr, uint32
 #ifndef L2S_TC_MAXNREG
 #define L2S_TC_MAXNREG 80
 #endif
-template <int MODE>
+// CG2 (own instantiations: such code cannot be launched without a cluster): CTA pairs walk two neighbouring row tiles
+// of the same column tile in lockstep; the leader's MMA thread issues cta_group::2 MMAs (M = 256), each CTA loads its own
+// A slab and HALF of every W stage, completions are counted on the leader's barriers, commits are multicast to both.
+template <int MODE, bool CG2 = false>
 __global__ void __maxnreg__(L2S_TC_MAXNREG)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -421,12 +426,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmW);
     for (int i = 0; i < g.sa; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < g.sb; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kTcEpiWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], (CG2 ? 2 : 1) * kTcEpiWarps); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc_dyn(tmem_slot, (uint32_t)g.tmem_cols);
+  if (warp == 1) { if constexpr (CG2) tmem_alloc_cg2(tmem_slot, (uint32_t)g.tmem_cols); else tmem_alloc_dyn(tmem_slot, (uint32_t)g.tmem_cols); }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG2) cluster_sync_all();      // the partner's barriers exist before anything is signalled to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // PDL: the prologue above may overlap the previous kernel's tail; its data is touched only after this wait
@@ -435,6 +441,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int items_per_b = g.m_items * g.n_ntiles;
   const int acc_cols = g.msub * g.nt;
+  // work walk.  Unpaired: item = (b, mi, ni).  CTA pairs: pair index = (b, mp, ni), rank r takes row tile mi = 2 mp + r
+  // (a row tile past the end reads zero-filled rows and stores nothing).
+  const int crank = CG2 ? (int)cluster_ctarank() : 0;
+  const int walkers = CG2 ? (int)gridDim.x / 2 : (int)gridDim.x;
+  const int walk0 = CG2 ? (int)blockIdx.x / 2 : (int)blockIdx.x;
+  const int pairs_per_b = ((g.m_items + 1) / 2) * g.n_ntiles;
+  const int walk_n = CG2 ? P.c.batch * pairs_per_b : g.total_items;
+  auto decode = [&](int wk, int& b, int& mi, int& ni) {
+    if constexpr (CG2) {
+      b = wk / pairs_per_b;
+      const int rem = wk - b * pairs_per_b;
+      const int mp = rem / g.n_ntiles;
+      ni = rem - mp * g.n_ntiles;
+      mi = 2 * mp + crank;
+    } else {
+      b = wk / items_per_b;
+      const int rem = wk - b * items_per_b;
+      mi = rem / g.n_ntiles;
+      ni = rem - mi * g.n_ntiles;
+    }
+  };
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -445,11 +472,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t pa = 0, pb = 0;
     const uint32_t box_bytes = (uint32_t)(g.box_rows * g.rb);
     int it_no = 0;
-    for (int item = blockIdx.x; item < g.total_items; item += gridDim.x, ++it_no) {
-      const int b = item / items_per_b;
-      const int rem = item - b * items_per_b;
-      const int mi = rem / g.n_ntiles;
-      const int ni = rem - mi * g.n_ntiles;
+    for (int wk = walk0; wk < walk_n; wk += walkers, ++it_no) {
+      int b, mi, ni;
+      decode(wk, b, mi, ni);
       const int row0 = mi * 128 * g.msub + g.min_off;
       for (int kc = 0; kc < g.kc; ++kc) {
         const int ch0 = kc * (g.rb / g.esz);
@@ -458,10 +483,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&a_empty[ia], pa ^ 1u);
           if (kc == 0) L2S_TRACE(0, it_no, 1);
           if (leader) {
-            mbar_expect_tx(&a_full[ia], (uint32_t)g.slab_bytes);
             uint8_t* dst = slabA + (size_t)ia * g.slab_bytes;
-            for (int l = 0; l < g.n_loads; ++l)
-              tma_load_3d(dst + (size_t)l * box_bytes, &tmA, &a_full[ia], ch0, row0 + l * g.box_rows, b);
+            if constexpr (CG2) {   // both CTAs' slabs complete on the pair leader's barrier
+              if (crank == 0) mbar_expect_tx(&a_full[ia], 2u * (uint32_t)g.slab_bytes);
+              for (int l = 0; l < g.n_loads; ++l)
+                tma_load_3d_cg2(dst + (size_t)l * box_bytes, &tmA, &a_full[ia], ch0, row0 + l * g.box_rows, b);
+            } else {
+              mbar_expect_tx(&a_full[ia], (uint32_t)g.slab_bytes);
+              for (int l = 0; l < g.n_loads; ++l)
+                tma_load_3d(dst + (size_t)l * box_bytes, &tmA, &a_full[ia], ch0, row0 + l * g.box_rows, b);
+            }
           }
           if (++ia == g.sa) { ia = 0; pa ^= 1u; }
         }
@@ -479,8 +510,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           mbar_wait(&b_empty[ib], pb ^ 1u);
           if (leader) {
-            mbar_expect_tx(&b_full[ib], (uint32_t)g.bstage_bytes);
-            tma_load_3d(stageB + (size_t)ib * g.bstage_bytes, &tmW, &b_full[ib], ch0, ni * g.nt, ts * g.tb);
+            if constexpr (CG2) {   // this CTA's half of the stage's output-channel rows
+              if (crank == 0) mbar_expect_tx(&b_full[ib], 2u * (uint32_t)g.bstage_bytes);
+              tma_load_3d_cg2(stageB + (size_t)ib * g.bstage_bytes, &tmW, &b_full[ib], ch0, ni * g.nt + crank * (g.nt / 2), ts * g.tb);
+            } else {
+              mbar_expect_tx(&b_full[ib], (uint32_t)g.bstage_bytes);
+              tma_load_3d(stageB + (size_t)ib * g.bstage_bytes, &tmW, &b_full[ib], ch0, ni * g.nt, ts * g.tb);
+            }
           }
           if (++ib == g.sb) { ib = 0; pb ^= 1u; }
         }
@@ -496,15 +532,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t desc_hi = (uint32_t)(tmpl >> 32);
     const uint32_t desc_lo_fixed = (uint32_t)tmpl;            // LBO field
     const uint32_t sub_step = (uint32_t)(128 * g.rb) >> 4;   // next 128-row accumulator
-    const uint32_t tapw_step = (uint32_t)(g.nt * g.rb) >> 4; // next tap inside a W stage
+    const uint32_t tapw_step = (uint32_t)((CG2 ? g.nt / 2 : g.nt) * g.rb) >> 4; // next tap inside a W stage
     int ia = 0, ib = 0;
     uint32_t pa = 0, pb = 0;
     uint32_t pacc0 = 0, pacc1 = 0;
     int buf = 0;
     int it_no = 0;
-    for (int item = blockIdx.x; item < g.total_items; item += gridDim.x, ++it_no) {
+    auto commit = [&](uint64_t* bar) { if constexpr (CG2) umma_commit_cg2(bar, (uint16_t)3); else umma_commit(bar); };
+    for (int wk = (CG2 && crank != 0) ? walk_n : walk0; wk < walk_n; wk += walkers, ++it_no) {   // pair: the leader issues for both
       L2S_TRACE(1, it_no, 0);
-      mbar_wait(&acc_empty[buf], (buf ? pacc1 : pacc0) ^ 1u);
+      if constexpr (CG2) mbar_wait_cluster(&acc_empty[buf], (buf ? pacc1 : pacc0) ^ 1u);
+      else mbar_wait(&acc_empty[buf], (buf ? pacc1 : pacc0) ^ 1u);
       L2S_TRACE(1, it_no, 1);
       tc_fence_after();
       const uint32_t d_base = tmem_base + (uint32_t)(buf * acc_cols);
@@ -533,28 +571,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t d_addr = d_base;
             if (g.k16 == 4) {
               for (int sub = 0; sub < g.msub; ++sub, a_sub += sub_step, d_addr += (uint32_t)g.nt)
-                issue_chunk<4>(leader, d_addr, desc_hi, a_sub, b_lo, g.idesc, first, g.esz == 4);
+                issue_chunk<4, CG2>(leader, d_addr, desc_hi, a_sub, b_lo, g.idesc, first, g.esz == 4);
             } else if (g.k16 == 2) {
               for (int sub = 0; sub < g.msub; ++sub, a_sub += sub_step, d_addr += (uint32_t)g.nt)
-                issue_chunk<2>(leader, d_addr, desc_hi, a_sub, b_lo, g.idesc, first, g.esz == 4);
+                issue_chunk<2, CG2>(leader, d_addr, desc_hi, a_sub, b_lo, g.idesc, first, g.esz == 4);
             } else {
               for (int sub = 0; sub < g.msub; ++sub, a_sub += sub_step, d_addr += (uint32_t)g.nt)
-                issue_chunk<1>(leader, d_addr, desc_hi, a_sub, b_lo, g.idesc, first, g.esz == 4);
+                issue_chunk<1, CG2>(leader, d_addr, desc_hi, a_sub, b_lo, g.idesc, first, g.esz == 4);
             }
           }
-          if (leader) umma_commit(&b_empty[ib]);   // W stage free once these MMAs retire
+          if (leader) commit(&b_empty[ib]);   // W stage free once these MMAs retire
           if (++ib == g.sb) { ib = 0; pb ^= 1u; }
           if (g.per_tap) {
-            if (leader) umma_commit(&a_empty[ia]);
+            if (leader) commit(&a_empty[ia]);
             if (++ia == g.sa) { ia = 0; pa ^= 1u; }
           }
         }
         if (!g.per_tap) {
-          if (leader) umma_commit(&a_empty[ia]);    // slab free
+          if (leader) commit(&a_empty[ia]);    // slab free
           if (++ia == g.sa) { ia = 0; pa ^= 1u; }
         }
       }
-      if (leader) umma_commit(&acc_full[buf]);      // accumulators complete -> epilogue
+      if (leader) commit(&acc_full[buf]);      // accumulators complete -> epilogue
       L2S_TRACE(1, it_no, 3);
       if (buf) pacc1 ^= 1u; else pacc0 ^= 1u;
       buf ^= 1;
@@ -567,11 +605,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t pacc0 = 0, pacc1 = 0;
     int buf = 0;
     int it_no = 0;
-    for (int item = blockIdx.x; item < g.total_items; item += gridDim.x, ++it_no) {
-      const int b = item / items_per_b;
-      const int rem = item - b * items_per_b;
-      const int mi = rem / g.n_ntiles;
-      const int ni = rem - mi * g.n_ntiles;
+    for (int wk = walk0; wk < walk_n; wk += walkers, ++it_no) {
+      int b, mi, ni;
+      decode(wk, b, mi, ni);
       if (warp == 2) L2S_TRACE(2, it_no, 0);
       const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * acc_cols);
       const uint32_t par = buf ? pacc1 : pacc0;
@@ -584,7 +620,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (warp == 2) L2S_TRACE(2, it_no, 1);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (lane == 0) { if constexpr (CG2) mbar_arrive_cluster(&acc_empty[buf], 0u); else mbar_arrive(&acc_empty[buf]); }
       if (warp == 2) L2S_TRACE(2, it_no, 2);
       if (buf) pacc1 ^= 1u; else pacc0 ^= 1u;
       buf ^= 1;
@@ -599,7 +635,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #endif
   if (P.span && threadIdx.x == 0) atomicMax(&P.span[1], (unsigned long long)gtime());
   if (P.trace && threadIdx.x == 0 && blockIdx.x < 512) P.trace[768 + blockIdx.x * 3 + 2] = gtime();
-  if (warp == 1) tmem_dealloc_dyn(tmem_base, (uint32_t)g.tmem_cols);
+  if constexpr (CG2) cluster_sync_all();      // no CTA leaves while its partner may still signal it
+  if (warp == 1) { if constexpr (CG2) tmem_dealloc_cg2(tmem_base, (uint32_t)g.tmem_cols); else tmem_dealloc_dyn(tmem_base, (uint32_t)g.tmem_cols); }
 }
 
 // ------------------------------------------------------------------ host side
@@ -652,6 +689,7 @@ struct TcTune {
   int dual = 1;                // try the two-CTAs-per-SM plan first
   int max_ctas = 0;            // 0: number of SMs
   int max_nt = 256;            // widest column tile (MMA N)
+  int cg2 = 1;                 // one-CTA-per-SM bf16 plans run as CTA pairs issuing cta_group::2 MMAs (knob tc_cg2)
 };
 
 // Shape-only planning (no device pointers): valid for any batch with the same (lin, mrows).
@@ -695,7 +733,10 @@ inline bool tc_plan_with(const ConvParams& c, int batch, const TcTune& tune, int
   if (tb > c.ntaps) tb = c.ntaps;
   g.tb = tb;
   g.n_tstages = (c.ntaps + tb - 1) / tb;
-  g.bstage_bytes = tb * g.nt * g.rb;
+  // CTA pairs (cta_group::2): bf16 only, one CTA per SM (the two-CTAs-per-SM plans are the HBM-bound narrow layers),
+  // each CTA keeps half of a W stage
+  g.cg2 = (tune.cg2 && !tune.per_tap && g.esz == 2 && acc_cols_cap == 256 && g.nt % 32 == 0 && batch * g.m_items >= 2) ? 1 : 0;
+  g.bstage_bytes = tb * (g.cg2 ? g.nt / 2 : g.nt) * g.rb;
   // ring depths within the shared-memory budget
   const int bar_bytes = 1024 + 320 + kTcEpiWarps * kEpiTileWords * 4;  // alignment slack, barriers + TMEM slot, epilogue tiles
   int sa = g.kc + 1 < kTcMaxStagesA ? g.kc + 1 : kTcMaxStagesA;
@@ -717,7 +758,7 @@ inline bool tc_plan_with(const ConvParams& c, int batch, const TcTune& tune, int
   if (cols > 512) return false;
   g.tmem_cols = cols;
   g.total_items = batch * g.m_items * g.n_ntiles;
-  g.idesc = g.esz == 4 ? umma_idesc_tf32(128u, (uint32_t)g.nt) : umma_idesc_bf16(128u, (uint32_t)g.nt);
+  g.idesc = g.esz == 4 ? umma_idesc_tf32(128u, (uint32_t)g.nt) : umma_idesc_bf16(g.cg2 ? 256u : 128u, (uint32_t)g.nt);
   g.cw = g.nt % 32 == 0 ? 32 : 16;
   g.ctas_per_sm = 1;
   *out = g;
@@ -740,17 +781,17 @@ inline bool tc_plan(const ConvParams& c, int batch, const TcTune& tune, TcGeom* 
   return tc_plan_with(c, batch, tune, 256, tune.smem_budget, out);
 }
 
-template <int MODE>
+template <int MODE, bool CG2 = false>
 inline cudaError_t launch_conv_tc_mode(const TcParams& P, const CUtensorMap& tmA, const CUtensorMap& tmW, int grid,
                                        cudaStream_t stream) {
   static bool configured[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<MODE, CG2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     // all of the SM's unified L1/shared storage as shared memory, so that two ~110 KB CTAs co-reside
-    e = cudaFuncSetAttribute(conv_tc_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(conv_tc_kernel<MODE, CG2>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     configured[dev] = true;
@@ -760,12 +801,23 @@ inline cudaError_t launch_conv_tc_mode(const TcParams& P, const CUtensorMap& tmA
   cfg.blockDim = dim3(kTcThreads);
   cfg.dynamicSmemBytes = (size_t)P.g.smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  unsigned na = 0;
+  if (CG2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (g_tc_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = g_tc_pdl ? 1u : 0u;
-  return cudaLaunchKernelEx(&cfg, conv_tc_kernel<MODE>, tmA, tmW, P);
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, conv_tc_kernel<MODE, CG2>, tmA, tmW, P);
 }
 
 inline cudaError_t launch_conv_tc(const ConvParams& c, const TcGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmW,
@@ -779,10 +831,16 @@ inline cudaError_t launch_conv_tc(const ConvParams& c, const TcGeom& g, const CU
   const int cap = num_ctas * (g.ctas_per_sm > 1 ? g.ctas_per_sm : 1);
   int grid = g.total_items < cap ? g.total_items : cap;
   if (grid < 1) grid = 1;
+  if (g.cg2) {                               // CTA pairs: even grid, one pair per (b, row-tile pair, column tile)
+    const int pairs_needed = c.batch * ((g.m_items + 1) / 2) * g.n_ntiles;
+    int pairs = cap / 2 < pairs_needed ? cap / 2 : pairs_needed;
+    if (pairs < 1) pairs = 1;
+    grid = 2 * pairs;
+  }
   const int mode = (c.res ? kEpiRes : 0) | ((c.acc_in || c.div != 1.0f) ? kEpiAcc : 0) | (c.out_raw ? kEpiRaw : 0) |
                    (c.out_act ? kEpiAct : 0);
   switch (mode) {
-#define L2S_MODE(m) case m: return launch_conv_tc_mode<m>(P, tmA, tmW, grid, stream);
+#define L2S_MODE(m) case m: return g.cg2 ? launch_conv_tc_mode<m, true>(P, tmA, tmW, grid, stream) : launch_conv_tc_mode<m>(P, tmA, tmW, grid, stream);
     L2S_MODE(4) L2S_MODE(5) L2S_MODE(6) L2S_MODE(7) L2S_MODE(8) L2S_MODE(9) L2S_MODE(10) L2S_MODE(11) L2S_MODE(12)
     L2S_MODE(13) L2S_MODE(14) L2S_MODE(15)
 #undef L2S_MODE

@@ -52,6 +52,7 @@ struct Knobs {
   long long trace_ptr = 0;         // device pointer for the kernel trace of l2s_debug_conv (0: off)
   long long max_msub = 8;
   long long max_nt = 256;
+  long long tc_cg2 = 1;            // conv_pre / upsampling convs (one CTA per SM, bf16) run as CTA pairs with cta_group::2 MMAs
   long long epi_pf = 0;            // fused-step kernels: 1 = L2 prefetch of the residual tile, 2 = L1 prefetch of the next chunk
   long long slab_cap = 40960;
   long long max_ctas = 0;
@@ -304,6 +305,7 @@ TcTune current_tune(const l2s_vocoder* v) {
   TcTune t;
   t.max_msub = (int)g_knobs.max_msub;
   t.max_nt = (int)g_knobs.max_nt;
+  t.cg2 = (int)g_knobs.tc_cg2;
   t.slab_cap = (int)g_knobs.slab_cap;
   t.per_tap = (int)g_knobs.per_tap;
   t.sa_min = (int)g_knobs.sa_min;
@@ -364,12 +366,13 @@ int run_conv(l2s_vocoder* v, ConvLayer& L, cudaStream_t st, int batch, int lin, 
     TcTune tune = current_tune(v);
     TcGeom g;
     if (!tc_plan(p, batch, tune, &g)) return fail(v, L2S_ERR_UNSUPPORTED, "no tcgen05 plan for " + L.name);
-    if (!L.has_tmW || L.tm_nt != g.nt || L.tm_tb != g.tb) {
+    const int w_rows = g.cg2 ? g.nt / 2 : g.nt;   // CTA pairs: each CTA loads half of a stage's output-channel rows
+    if (!L.has_tmW || L.tm_nt != w_rows || L.tm_tb != g.tb) {
       if (!make_tmap_3d(&L.tmW, L.w_dev, g.esz, (uint64_t)L.cin_pad, (uint64_t)L.ntot, (uint64_t)L.ntaps,
-                        (uint32_t)(g.rb / g.esz), (uint32_t)g.nt, (uint32_t)g.tb))
+                        (uint32_t)(g.rb / g.esz), (uint32_t)w_rows, (uint32_t)g.tb))
         return fail(v, L2S_ERR_CUDA, "cuTensorMapEncodeTiled failed for the weights of " + L.name);
       L.has_tmW = true;
-      L.tm_nt = g.nt;
+      L.tm_nt = w_rows;
       L.tm_tb = g.tb;
     }
     CUtensorMap tmA;
@@ -1106,7 +1109,7 @@ int l2s_debug_conv(const l2s_conv_desc* d, int32_t impl, int32_t device, void* s
     if (!tc_plan(p, d->batch, tune, &g)) { say("no tcgen05 plan"); return L2S_ERR_UNSUPPORTED; }
     CUtensorMap tmA, tmW;
     if (!make_tmap_3d(&tmW, d->w, g.esz, (uint64_t)d->cin_pad, (uint64_t)d->ntot, (uint64_t)d->ntaps,
-                      (uint32_t)(g.rb / g.esz), (uint32_t)g.nt, (uint32_t)g.tb) ||
+                      (uint32_t)(g.rb / g.esz), (uint32_t)(g.cg2 ? g.nt / 2 : g.nt), (uint32_t)g.tb) ||
         !make_tmap_3d(&tmA, d->in, g.esz, (uint64_t)d->cin_pad, (uint64_t)d->lin, (uint64_t)d->batch,
                       (uint32_t)(g.rb / g.esz), (uint32_t)g.box_rows, 1u)) {
       say("cuTensorMapEncodeTiled failed");
@@ -1182,6 +1185,7 @@ int l2s_debug_set(const char* key, int64_t value) {
   else if (k == "trace_ptr") g_knobs.trace_ptr = value;
   else if (k == "max_msub") g_knobs.max_msub = value;
   else if (k == "max_nt") g_knobs.max_nt = value;
+  else if (k == "tc_cg2") g_knobs.tc_cg2 = value;
   else if (k == "epi_pf") g_knobs.epi_pf = value;
   else if (k == "slab_cap") g_knobs.slab_cap = value;
   else if (k == "max_ctas") g_knobs.max_ctas = value;
