@@ -213,9 +213,12 @@ __global__ void cond_unit_kernel(const CondUnitParams p) {
 }
 
 // Waveform head.  in: fp32 channels-last (B,L,C) MRF mean of the last stage.
+constexpr int kPostMaxC = 64;
+
 struct PostParams {
   const float* in;
-  const float* w;      // [7][C]
+  float wc[7 * kPostMaxC];   // [7][C] weights, passed by value: they sit in the constant bank and feed the FMAs directly
+                             // (read from shared memory they doubled the kernel's shared-memory traffic)
   float bias;
   float* out;          // (B,L) or null
   int16_t* out_i16;    // (B,L) or null
@@ -223,18 +226,15 @@ struct PostParams {
 };
 
 constexpr int kPostTile = 256;
-constexpr int kPostMaxC = 64;
 
 // pitch (floats) of a staged row: a multiple of 4 (float4 reads) that spreads 8 consecutive rows over all banks
 __host__ __device__ inline int post_pitch(int c) { return c + 4; }
 
 __global__ void __launch_bounds__(kPostTile) post_kernel(const PostParams p) {
   extern __shared__ __align__(16) float s_x[];   // [(kPostTile + 6)][post_pitch(C)]
-  __shared__ __align__(16) float s_w[7 * kPostMaxC];
   const int b = blockIdx.y;
   const int l0 = blockIdx.x * kPostTile;
   const int c = p.c, pitch = post_pitch(c), c4 = c >> 2;
-  for (int i = threadIdx.x; i < 7 * c; i += kPostTile) s_w[i] = p.w[i];
   const float4* in4 = reinterpret_cast<const float4*>(p.in + (long long)b * p.len * c);
   const int n4 = (kPostTile + 6) * c4;
   for (int i = threadIdx.x; i < n4; i += kPostTile) {
@@ -256,10 +256,11 @@ __global__ void __launch_bounds__(kPostTile) post_kernel(const PostParams p) {
 #pragma unroll
   for (int j = 0; j < 7; ++j) {
     const float4* xr = reinterpret_cast<const float4*>(s_x + (threadIdx.x + j) * pitch);
-    const float4* wr = reinterpret_cast<const float4*>(s_w + j * c);
+    const float* wr = p.wc + j * c;
     for (int q = 0; q < c4; ++q) {
-      const float4 x = xr[q], w = wr[q];
-      acc = fmaf(x.x, w.x, acc); acc = fmaf(x.y, w.y, acc); acc = fmaf(x.z, w.z, acc); acc = fmaf(x.w, w.w, acc);
+      const float4 x = xr[q];
+      acc = fmaf(x.x, wr[4 * q], acc); acc = fmaf(x.y, wr[4 * q + 1], acc);
+      acc = fmaf(x.z, wr[4 * q + 2], acc); acc = fmaf(x.w, wr[4 * q + 3], acc);
     }
   }
   const float y = tanhf(acc);

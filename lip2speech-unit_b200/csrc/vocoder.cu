@@ -113,6 +113,7 @@ struct l2s_vocoder {
   float *d_dict = nullptr, *d_spk_w = nullptr, *d_spk_b = nullptr, *d_wt = nullptr, *d_wt_b = nullptr, *d_fc_t = nullptr,
         *d_fc_b = nullptr, *d_post_w = nullptr;
   float post_bias = 0.f;
+  std::vector<float> post_w_host;   // conv_post weights [7][C], handed to the kernel by value
   int* err_host = nullptr;   // mapped pinned
   int* err_dev = nullptr;
   std::vector<void*> dev_allocs;
@@ -827,7 +828,7 @@ int forward_impl(l2s_vocoder* v, void* stream, const int64_t* code, const void* 
   // ---- waveform head
   PostParams pp{};
   pp.in = ws.acc;
-  pp.w = v->d_post_w;
+  for (size_t i = 0; i < v->post_w_host.size() && i < sizeof(pp.wc) / sizeof(float); ++i) pp.wc[i] = v->post_w_host[i];
   pp.bias = v->post_bias;
   pp.out = out;
   pp.out_i16 = out_i16;
@@ -992,6 +993,7 @@ int l2s_finalize(l2s_vocoder* v, int device) {
     for (int ch = 0; ch < C; ++ch)
       for (int j = 0; j < 7; ++j) pw[(size_t)j * C + ch] = w[(size_t)ch * 7 + j];
     v->d_post_w = dev_upload<float>(v, pw.data(), pw.size(), &e);
+    v->post_w_host = pw;
     if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, cudaGetErrorString(e));
     v->post_bias = v->weights["conv_post.bias"][0];
   }
