@@ -541,8 +541,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto commit = [&](uint64_t* bar) { if constexpr (CG2) umma_commit_cg2(bar, (uint16_t)3); else umma_commit(bar); };
     for (int wk = (CG2 && crank != 0) ? walk_n : walk0; wk < walk_n; wk += walkers, ++it_no) {   // pair: the leader issues for both
       L2S_TRACE(1, it_no, 0);
-      if constexpr (CG2) mbar_wait_cluster(&acc_empty[buf], (buf ? pacc1 : pacc0) ^ 1u);
-      else mbar_wait(&acc_empty[buf], (buf ? pacc1 : pacc0) ^ 1u);
+      mbar_wait(&acc_empty[buf], (buf ? pacc1 : pacc0) ^ 1u);
       L2S_TRACE(1, it_no, 1);
       tc_fence_after();
       const uint32_t d_base = tmem_base + (uint32_t)(buf * acc_cols);
@@ -620,7 +619,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (warp == 2) L2S_TRACE(2, it_no, 1);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) { if constexpr (CG2) mbar_arrive_cluster(&acc_empty[buf], 0u); else mbar_arrive(&acc_empty[buf]); }
+      if (lane == 0) { if constexpr (CG2) mbar_arrive_cluster(&acc_empty[buf], 0u, (uint32_t)crank); else mbar_arrive(&acc_empty[buf]); }
       if (warp == 2) L2S_TRACE(2, it_no, 2);
       if (buf) pacc1 ^= 1u; else pacc0 ^= 1u;
       buf ^= 1;

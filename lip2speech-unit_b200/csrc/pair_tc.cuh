@@ -516,9 +516,9 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (leader) commit(d1_full, false);
       L2S_TRACE(1, it_no, 2);
       // ---- c2: D2 += T(slab, row shift j) . W2[j]   (T written by the epilogue warps)
-      if constexpr (CG2) mbar_wait_cluster(t_full, pt); else mbar_wait(t_full, pt);
+      mbar_wait(t_full, pt);
       pt ^= 1u;
-      if constexpr (CG2) mbar_wait_cluster(d2_empty, pd2 ^ 1u); else mbar_wait(d2_empty, pd2 ^ 1u);
+      mbar_wait(d2_empty, pd2 ^ 1u);
       pd2 ^= 1u;
       L2S_TRACE(1, it_no, 3);
       tc_fence_after();
@@ -610,7 +610,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) { if constexpr (CG2) mbar_arrive_cluster(t_full, 0u); else mbar_arrive(t_full); }   // CTA pair: the leader's MMA thread waits
+      if (lane == 0) { if constexpr (CG2) mbar_arrive_cluster(t_full, 0u, (uint32_t)crank); else mbar_arrive(t_full); }   // CTA pair: the leader's MMA thread waits
       if (warp == 2) L2S_TRACE(2, it_no, 1);
       // ---- phase 2: D2 -> global (the wait on d2_full happens inside, after the first residual loads are issued)
       {
@@ -632,7 +632,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (warp == 2) L2S_TRACE(2, it_no, 2);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) { if constexpr (CG2) mbar_arrive_cluster(d2_empty, 0u); else mbar_arrive(d2_empty); }
+      if (lane == 0) { if constexpr (CG2) mbar_arrive_cluster(d2_empty, 0u, (uint32_t)crank); else mbar_arrive(d2_empty); }
       if (warp == 2) L2S_TRACE(2, it_no, 3);
     }
     if (EPI_TMA && lane == 0) bulk_wait_all();   // every TMA store has landed before the CTA exits

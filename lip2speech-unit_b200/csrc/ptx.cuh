@@ -216,27 +216,20 @@ __device__ __forceinline__ void tma_load_3d_cg2(void* smem_dst, const void* tmap
       "l"(0x1000000000000000ull)   // L2 evict-normal
       : "memory");
 }
-// Wait with cluster-scope acquire: the arrivals come from the partner CTA's threads (mbar_arrive_cluster).
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0, ok = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, P;\n\t}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (ok) break;
-    if (++spins > (1u << 26)) __trap();
+// Arrive on the barrier at the same offset in CTA `rank` of the cluster (rank == own rank: a plain local arrive).
+// Default semantics on purpose: a `.release.cluster` arrive compiles to MEMBAR.ALL + ERRBAR, i.e. waits for every
+// outstanding global store of the thread, and a `.acquire.cluster` try_wait executes CCTL.IVALL (L1 invalidate) on
+// every poll (both seen in the ncu source view; they cost the CTA-pair kernels ~5 %).  What crosses the CTA boundary
+// here is shared memory / TMEM consumed by the tensor core, ordered by fence.proxy.async and tcgen05 fences.
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank, uint32_t my_rank) {
+  if (rank == my_rank) {
+    mbar_arrive(bar);
+    return;
   }
-}
-// mbarrier arrive on the barrier at the same offset in CTA `rank` of the cluster.
-__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
       "r"(rank)
       : "memory");
 }

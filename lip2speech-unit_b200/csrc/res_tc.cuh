@@ -455,7 +455,7 @@ res_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
         const int dil = second ? 1 : g.dil[st];
         const int halo = second ? g.h2 : g.h1[st];
         L2S_RTRACE(128, ntr);
-        if constexpr (CG2) mbar_wait_cluster(s_full, ps); else mbar_wait(s_full, ps);
+        mbar_wait(s_full, ps);
         ps ^= 1u;
         tc_fence_after();
         L2S_RTRACE(128, ntr);
@@ -494,7 +494,7 @@ res_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) { if constexpr (CG2) mbar_arrive_cluster(s_full, 0u); else mbar_arrive(s_full); }   // pair: the leader's MMA thread waits
+      if (lane == 0) { if constexpr (CG2) mbar_arrive_cluster(s_full, 0u, (uint32_t)crank); else mbar_arrive(s_full); }   // pair: the leader's MMA thread waits
     };
     res_prebias_d1(g, w, d1_quad, sbias);            // bias of the first c1
     for (int wk = walk0; wk < walk_n; wk += walkers) {
