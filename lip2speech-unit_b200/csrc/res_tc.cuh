@@ -560,7 +560,8 @@ res_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
 
 // ------------------------------------------------------------------ host side
 
-inline int g_res_cg2 = 1;   // one-CTA-per-SM whole-ResBlock plans run as CTA pairs issuing cta_group::2 MMAs (knob res_cg2)
+inline int g_res_cg2 = 4;   // whole-ResBlock plans run as CTA pairs issuing cta_group::2 MMAs (knob res_cg2: 0 off, 1 one-CTA-per-SM
+                            // plans only, 2 + dual, 3 + quad, 4 + C = 16)
 
 // kind: 0 = one CTA per SM (168 registers, 32-column epilogue chunks), 1 = two (80 registers, <= 112 KB, <= 256 TMEM
 // columns), 2 = four CTAs per SM with four epilogue warps each (<= 55 KB, <= 128 TMEM columns): more independent
@@ -602,10 +603,10 @@ inline bool res_plan_with(int c, int k, int n_dil, const int* dil, int lin, int 
   g.n_tstages = (k + tb - 1) / tb;
   g.m_items = (lin + g.r_out - 1) / g.r_out;
   g.total_items = batch * g.m_items;
-  // CTA pairs issuing cta_group::2 MMAs keep half of every weight stage.  Only for the one-CTA-per-SM plans (the
-  // MMA-bound C = 64, k = 11 ResBlock: 281 -> 263 us); with two or four CTAs per SM the pair's lockstep costs more
-  // overlap than the halved weight traffic gains (measured: k = 3 / 7 ResBlocks 10-20 % slower).
-  g.cg2 = (g_res_cg2 && kind == 0 && c >= 32 && g.total_items >= 2) ? 1 : 0;
+  // CTA pairs issuing cta_group::2 MMAs keep half of every weight stage.  Measured on cfg2 (with default-semantics
+  // barrier operations, see mbar_arrive_cluster): C=64 k=11 281 -> 252 us, k=7 185 -> 171, C=32 k=11 185 -> 171, C=16 k=11
+  // 146 -> 140; nothing gets slower.
+  g.cg2 = (g_res_cg2 && (kind == 0 || g_res_cg2 >= 2 + (kind == 2 ? 1 : 0)) && (c >= 32 || g_res_cg2 >= 4) && g.total_items >= 2) ? 1 : 0;   // knob: 2 also dual, 3 also quad, 4 also C = 16
   g.bstage_bytes = tb * (g.cg2 ? c / 2 : c) * g.rb;
   g.s_bytes = ((g.mt + 2 * g.pad) * g.rb + 1023) & ~1023;
   if ((msub * c) % 32 != 0) return false;   // the phases walk the TMEM region in 32-column units

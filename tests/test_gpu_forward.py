@@ -279,7 +279,7 @@ def test_whole_resblock_kernels_match_steps(pkg, weights, frames):
     check(ref, y, "bf16", f"whole-ResBlock kernels, {frames} frames")
 
 
-@pytest.mark.parametrize("knob,value", [("res_mode", 1), ("res_mode", 2), ("res_quad_pct", 200), ("res_quad_pct", 0), ("res_cg2", 0), ("res_msub", 2),
+@pytest.mark.parametrize("knob,value", [("res_mode", 1), ("res_mode", 2), ("res_quad_pct", 200), ("res_quad_pct", 0), ("res_cg2", 0), ("res_cg2", 1), ("res_msub", 2),
                                         ("res_msub", 4)])
 def test_whole_resblock_tilings_agree(pkg, weights, knob, value):
     """Tile size, CTAs per SM (1 / 2 / 4) and epilogue warps per CTA (8 / 4) of the whole-ResBlock kernel change the
@@ -296,7 +296,7 @@ def test_whole_resblock_tilings_agree(pkg, weights, knob, value):
         lib.l2s_debug_set(b"res_mode", 0)
         lib.l2s_debug_set(b"res_msub", 8)
         lib.l2s_debug_set(b"res_quad_pct", 115)
-        lib.l2s_debug_set(b"res_cg2", 1)
+        lib.l2s_debug_set(b"res_cg2", 4)
     assert torch.isfinite(a).all()
     assert torch.equal(a, b), float((a - b).abs().max())
 
