@@ -734,7 +734,7 @@ inline bool tc_plan_with(const ConvParams& c, int batch, const TcTune& tune, int
   g.n_tstages = (c.ntaps + tb - 1) / tb;
   // CTA pairs (cta_group::2): bf16 only, one CTA per SM (the two-CTAs-per-SM plans are the HBM-bound narrow layers),
   // each CTA keeps half of a W stage
-  g.cg2 = (tune.cg2 && !tune.per_tap && g.esz == 2 && acc_cols_cap == 256 && g.nt % 32 == 0 && batch * g.m_items >= 2) ? 1 : 0;
+  g.cg2 = (tune.cg2 && !tune.per_tap && g.esz == 2 && (acc_cols_cap == 256 || tune.cg2 >= 2) && g.nt % 32 == 0 && batch * g.m_items >= 2) ? 1 : 0;
   g.bstage_bytes = tb * (g.cg2 ? g.nt / 2 : g.nt) * g.rb;
   // ring depths within the shared-memory budget
   const int bar_bytes = 1024 + 320 + kTcEpiWarps * kEpiTileWords * 4;  // alignment slack, barriers + TMEM slot, epilogue tiles
