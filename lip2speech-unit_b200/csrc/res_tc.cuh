@@ -634,17 +634,22 @@ inline int g_res_quad_pct = 115;    // planner: score weight (percent) of a four
 inline bool res_plan(int c, int k, int n_dil, const int* dil, int lin, int batch, int mode, int max_msub, ResGeom* out) {
   ResGeom best{};
   double best_score = 0.0;
+  int dual_mt = 0;            // tile of the best two-CTAs-per-SM plan (kind 1 is scored before kind 0)
   for (int kind = 2; kind >= 0; --kind) {
     if ((mode == 1 && kind != 1) || (mode == 2 && kind != 0) || (mode == 3 && kind != 2)) continue;
     if (kind == 2 && mode != 3 && g_res_quad_pct <= 0) continue;
+    double kind_best = 0.0;
     for (int msub = max_msub < 8 ? max_msub : 8; msub >= 1; --msub) {
       ResGeom g;
       if (!res_plan_with(c, k, n_dil, dil, lin, batch, kind, msub, &g)) continue;
       // useful rows per computed row, weighted by how well the kind overlaps MMA and epilogue phases (from the
-      // measured sweeps); tiles much longer than the utterance waste the rest
+      // measured sweeps); tiles much longer than the utterance waste the rest.  One CTA per SM is discounted less
+      // when two CTAs only fit 256-row tiles (C = 64, k = 7: 171 -> 160 us as one 512-row tile per SM).
       const int covered = g.m_items * g.r_out;
-      const double w = kind == 2 ? 0.01 * (g_res_quad_pct > 0 ? g_res_quad_pct : 100) : (kind == 1 ? 1.0 : 0.01 * g_res_single_pct);
+      const double single_w = 0.01 * g_res_single_pct + ((dual_mt > 0 && dual_mt <= 256) ? 0.10 : 0.0);
+      const double w = kind == 2 ? 0.01 * (g_res_quad_pct > 0 ? g_res_quad_pct : 100) : (kind == 1 ? 1.0 : single_w);
       const double score = (double)g.r_out / g.mt * ((double)lin / covered) * w;
+      if (kind == 1 && score > kind_best) { kind_best = score; dual_mt = g.mt; }
       if (score > best_score) { best_score = score; best = g; }
     }
   }
