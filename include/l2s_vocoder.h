@@ -170,11 +170,6 @@ int l2s_debug_conv(const l2s_conv_desc* d, int32_t impl, int32_t device, void* s
  * layer name).  L2S_ERR_INVALID past the last launch.  Synchronises on the event. */
 int l2s_debug_layer_time(l2s_vocoder* v, int32_t idx, float* ms, double* flops, char* name, int32_t name_len);
 
-/* Debug: cycle accounting of one epilogue warp (enable with knob epi_prof = 1): out8[0] TMEM load + wait,
- * [1] transpose stores, [2] finish (bias / residual / stores), [3] chunks, [4] locate + residual issue,
- * [5] accumulator-barrier wait.  Reads and resets.  Synchronises. */
-int l2s_debug_epi_prof(long long* out8);
-
 /* Override a tuning / descriptor knob (tests and probes only): force_simt,
  * stop_after_stage, stop_after_pre, per_tap, sa_min, dual, cluster, alias_at, epi_tma, pdl, use_graph, fuse_pairs, trace_launch, span_ptr, plan_report, trace_ptr, max_msub, slab_cap, max_ctas,
  * embed_tap, layer_events. */

@@ -43,7 +43,7 @@ class ConvDesc(C.Structure):
 EXPORTS = [
     "l2s_create", "l2s_destroy", "l2s_set_weight", "l2s_finalize", "l2s_workspace_bytes", "l2s_hop",
     "l2s_forward", "l2s_forward_i16", "l2s_poll_index_error", "l2s_launch_count", "l2s_last_error",
-    "l2s_version", "l2s_debug_tap", "l2s_debug_conv", "l2s_debug_set", "l2s_debug_layer_time", "l2s_debug_epi_prof",
+    "l2s_version", "l2s_debug_tap", "l2s_debug_conv", "l2s_debug_set", "l2s_debug_layer_time",
 ]
 
 _lib = None
@@ -90,8 +90,6 @@ def load():
     lib.l2s_debug_conv.restype = C.c_int
     lib.l2s_debug_layer_time.argtypes = [vp, i32, C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_char_p, i32]
     lib.l2s_debug_layer_time.restype = C.c_int
-    lib.l2s_debug_epi_prof.argtypes = [C.POINTER(C.c_longlong)]
-    lib.l2s_debug_epi_prof.restype = C.c_int
     lib.l2s_debug_set.argtypes = [C.c_char_p, i64]
     lib.l2s_debug_set.restype = C.c_int
     _lib = lib

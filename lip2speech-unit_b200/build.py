@@ -1,51 +1,82 @@
 """Builds the C-ABI CUDA library in-tree (lib/libl2s_vocoder.so) for sm_100a.
 
-    python lip2speech-unit_b200/build.py [--force]
+    python lip2speech-unit_b200/build.py [--force] [-v]
 
-nvcc cross-compiles without a GPU; the built .so travels to the GPU box with the
-repo snapshot (it is git-ignored, not gpurun-ignored).
+One object per translation unit under csrc/ (the tcgen05 kernel families each live in their own .cu so that they
+compile in parallel and an edit rebuilds only what depends on it: dependencies come from nvcc -MD), then one
+link.  nvcc cross-compiles without a GPU; the built .so travels to the GPU box with the repo snapshot (it is
+git-ignored, not gpurun-ignored).
 """
+import concurrent.futures
 import os
+import re
 import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
+OBJ_DIR = os.path.join(LIB_DIR, "obj")
 LIB_PATH = os.path.join(LIB_DIR, "libl2s_vocoder.so")
-SOURCES = [os.path.join(CSRC, "vocoder.cu")]
-NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
-]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
-def _deps():
-    out = [os.path.join(HERE, "..", "include", "l2s_vocoder.h")]
-    for f in os.listdir(CSRC):
-        if f.endswith((".cu", ".cuh", ".h")):
-            out.append(os.path.join(CSRC, f))
-    return out
+def _sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _obj(src):
+    return os.path.join(OBJ_DIR, os.path.splitext(os.path.basename(src))[0] + ".o")
+
+
+def _deps_of(src):
+    """Files the object depends on, from the nvcc -MD output of its last build (None: never built)."""
+    dep = _obj(src)[:-2] + ".d"
+    if not os.path.exists(dep) or not os.path.exists(_obj(src)):
+        return None
+    with open(dep) as f:
+        text = f.read().replace("\\\n", " ")
+    files = text.split(":", 1)[1].split() if ":" in text else []
+    return [p for p in files if not p.startswith(("/usr/", "/opt/"))] + [src, os.path.abspath(__file__)]
+
+
+def _stale(src) -> bool:
+    deps = _deps_of(src)
+    if deps is None:
+        return True
+    t = os.path.getmtime(_obj(src))
+    return any((not os.path.exists(d)) or os.path.getmtime(d) > t for d in deps)
 
 
 def needs_build() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    return any(os.path.getmtime(d) > t for d in _deps())
+    return any(_stale(s) or os.path.getmtime(_obj(s)) > t for s in _sources())
+
+
+def _compile(src, nvcc, verbose):
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-MD", "-MF", _obj(src)[:-2] + ".d", "-c", "-o", _obj(src), src]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    return src, cmd, proc
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    todo = [s for s in _sources() if force or _stale(s)]
+    with concurrent.futures.ThreadPoolExecutor(max_workers=max(1, min(len(todo), os.cpu_count() or 1))) as pool:
+        for src, cmd, proc in pool.map(lambda s: _compile(s, nvcc, verbose), todo):
+            if proc.returncode != 0:
+                raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+            if verbose:
+                sys.stderr.write(proc.stderr)
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + [_obj(s) for s in _sources()]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
-    if verbose:
-        sys.stderr.write(proc.stderr)
+        raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
     return LIB_PATH
 
 

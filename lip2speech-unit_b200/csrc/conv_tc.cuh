@@ -79,21 +79,6 @@ __device__ __forceinline__ long long gtime() {
     if (P.trace && blockIdx.x == 0 && (slot) < 64 && lane == 0) P.trace[((role) * 64 + (slot)) * 4 + (ev)] = gtime(); \
   } while (0)
 
-// debug cycle accounting of one epilogue warp (CTA 0, warp 2): [0] tmem ld+wait, [1] transpose stores, [2] finish, [3] chunks,
-// [4] locate + residual issue, [5] barrier wait
-__device__ long long g_epi_prof[8];
-__device__ int g_epi_prof_on = 0;
-// accumulated in shared memory (a global read-modify-write per region would itself cost ~700 cycles), flushed at kernel end
-__device__ __forceinline__ long long* epi_prof_smem() {
-  __shared__ long long s_prof[8];
-  return s_prof;
-}
-#ifdef L2S_EPI_PROF   // build with -DL2S_EPI_PROF to enable the epilogue cycle accounting
-#define L2S_PROF_ON (g_epi_prof_on && blockIdx.x == 0 && (threadIdx.x >> 5) == 2)
-#else
-#define L2S_PROF_ON false
-#endif
-
 __device__ __forceinline__ float round_tf32(float v) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
@@ -227,26 +212,12 @@ __device__ __forceinline__ void epi_prefetch(const ConvParams& p, const EpiChunk
 template <int CW>
 __device__ __forceinline__ void epi_stage(float4* tile4, uint32_t taddr, int lane) {
   uint32_t r[CW];
-  const bool prof = L2S_PROF_ON;
-  long long t0 = 0;
-  if (prof) t0 = clock64();
   if constexpr (CW == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
   tmem_ld_wait();      // kept adjacent to the load: see epilogue_item_rows
-  long long t1 = 0;
-  if (prof) {
-    // force the loaded registers to be consumed before reading the clock: true TMEM -> RF latency
-    uint32_t x = 0;
-#pragma unroll
-    for (int j = 0; j < CW; ++j) x ^= r[j];
-    if (x == 0x7fc12345u) epi_prof_smem()[7] += 1;
-    t1 = clock64();
-    if ((threadIdx.x & 31) == 0) epi_prof_smem()[0] += t1 - t0;
-  }
 #pragma unroll
   for (int j = 0; j < CW / 4; ++j)
     tile4[epi_slot<CW>(lane, j)] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
                                                __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-  if (prof && (threadIdx.x & 31) == 0) { epi_prof_smem()[1] += clock64() - t1; epi_prof_smem()[3] += 1; }
 }
 
 // Stage 3: read back column-per-lane, apply bias / residual / branch sum / mean / leaky-ReLU, store.
@@ -318,25 +289,16 @@ __device__ __forceinline__ void epilogue_item_rows(const ConvParams& p, float* t
                           crow, c4, row_lim, row_lo);
   };
   auto finish = [&](const EpiChunk& c, const float4 (&rv)[CW / 4], const float4 (&av)[CW / 4]) {
-    const bool prof = L2S_PROF_ON;
-    long long t0 = 0;
-    if (prof) t0 = clock64();
     if (__all_sync(0xffffffffu, c.okmask == kAll)) epi_finish<CW, MODE, true>(p, c, tile4, rv, av, crow, c4);
     else epi_finish<CW, MODE, false>(p, c, tile4, rv, av, crow, c4);
-    if (prof && lane == 0) epi_prof_smem()[2] += clock64() - t0;
   };
   int s = 0, cc = half;
   while (cc >= cps) { cc -= cps; ++s; }
   bool have = s < msub;
   EpiChunk ca{}, cb{};
   float4 rva[CW / 4], rvb[CW / 4], av[CW / 4];
-  long long tw0 = 0;
-  if (L2S_PROF_ON) tw0 = clock64();
   if (have) { ca = locate(s, cc); epi_load_res<CW, MODE>(p, ca, rva); }
-  long long tw1 = 0;
-  if (L2S_PROF_ON) { tw1 = clock64(); if (lane == 0) epi_prof_smem()[4] += tw1 - tw0; }
   mbar_wait(bar, parity);
-  if (L2S_PROF_ON && lane == 0) epi_prof_smem()[5] += clock64() - tw1;
   tc_fence_after();
   while (have) {
     // ---- chunk A
@@ -410,9 +372,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-#ifdef L2S_EPI_PROF
-  if (g_epi_prof_on && threadIdx.x < 8) epi_prof_smem()[threadIdx.x] = 0;
-#endif
   if (P.span && threadIdx.x == 0) atomicMin(&P.span[0], (unsigned long long)gtime());
   if (P.trace && threadIdx.x == 0 && blockIdx.x < 512) {   // debug: which SM ran this CTA, and when
     uint32_t smid;
@@ -629,9 +588,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncwarp();
   tc_fence_before();
   __syncthreads();
-#ifdef L2S_EPI_PROF
-  if (g_epi_prof_on && blockIdx.x == 0 && threadIdx.x < 8) atomicAdd(reinterpret_cast<unsigned long long*>(&g_epi_prof[threadIdx.x]), (unsigned long long)epi_prof_smem()[threadIdx.x]);
-#endif
   if (P.span && threadIdx.x == 0) atomicMax(&P.span[1], (unsigned long long)gtime());
   if (P.trace && threadIdx.x == 0 && blockIdx.x < 512) P.trace[768 + blockIdx.x * 3 + 2] = gtime();
   if constexpr (CG2) cluster_sync_all();      // no CTA leaves while its partner may still signal it
@@ -819,9 +775,14 @@ inline cudaError_t launch_conv_tc_mode(const TcParams& P, const CUtensorMap& tmA
   return cudaLaunchKernelEx(&cfg, conv_tc_kernel<MODE, CG2>, tmA, tmW, P);
 }
 
-inline cudaError_t launch_conv_tc(const ConvParams& c, const TcGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmW,
-                                  int num_ctas, cudaStream_t stream, long long* trace = nullptr,
-                                  unsigned long long* span = nullptr) {
+// Defined in tu_conv_tc.cu (the only translation unit that instantiates conv_tc_kernel); declared everywhere else.
+#ifndef L2S_TU_CONV_TC
+cudaError_t launch_conv_tc(const ConvParams& c, const TcGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmW,
+                           int num_ctas, cudaStream_t stream, long long* trace = nullptr,
+                           unsigned long long* span = nullptr);
+#else
+cudaError_t launch_conv_tc(const ConvParams& c, const TcGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmW,
+                           int num_ctas, cudaStream_t stream, long long* trace, unsigned long long* span) {
   TcParams P;
   P.c = c;
   P.g = g;
@@ -846,5 +807,6 @@ inline cudaError_t launch_conv_tc(const ConvParams& c, const TcGeom& g, const CU
     default: return cudaErrorInvalidValue;   // a conv with no output
   }
 }
+#endif  // L2S_TU_CONV_TC
 
 }  // namespace l2s

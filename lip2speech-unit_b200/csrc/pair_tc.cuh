@@ -328,9 +328,6 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     P.trace[768 + blockIdx.x * 3 + 0] = smid;
     P.trace[768 + blockIdx.x * 3 + 1] = gtime();
   }
-#ifdef L2S_EPI_PROF
-  if (g_epi_prof_on && threadIdx.x < 8) epi_prof_smem()[threadIdx.x] = 0;
-#endif
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -641,9 +638,6 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncwarp();
   tc_fence_before();
   __syncthreads();
-#ifdef L2S_EPI_PROF
-  if (g_epi_prof_on && blockIdx.x == 0 && threadIdx.x < 8) atomicAdd(reinterpret_cast<unsigned long long*>(&g_epi_prof[threadIdx.x]), (unsigned long long)epi_prof_smem()[threadIdx.x]);
-#endif
   if (P.span && threadIdx.x == 0) atomicMax(&P.span[1], (unsigned long long)gtime());
   if (P.trace && threadIdx.x == 0 && blockIdx.x < 512) P.trace[768 + blockIdx.x * 3 + 2] = gtime();
   if (g.cluster > 1) cluster_sync_all();      // no CTA leaves while its partner may still multicast into it
@@ -799,9 +793,15 @@ inline cudaError_t launch_pair_mode(const PairParams& P, const CUtensorMap& tmA,
 }
 
 // c: the c2 epilogue description (bias = b2, res, acc_in, outputs, div, slope, lin = mrows = L, ntot = C, out_valid = L * C).
-inline cudaError_t launch_pair_tc(const ConvParams& c, const float* bias1, const PairGeom& g, const CUtensorMap& tmA,
-                                  const CUtensorMap& tmW1, const CUtensorMap& tmW2, const PairEpiMaps& em, int num_ctas,
-                                  cudaStream_t stream, long long* trace = nullptr, unsigned long long* span = nullptr) {
+// Defined in tu_pair_tc.cu (the only translation unit that instantiates pair_tc_kernel); declared everywhere else.
+#ifndef L2S_TU_PAIR_TC
+cudaError_t launch_pair_tc(const ConvParams& c, const float* bias1, const PairGeom& g, const CUtensorMap& tmA,
+                           const CUtensorMap& tmW1, const CUtensorMap& tmW2, const PairEpiMaps& em, int num_ctas,
+                           cudaStream_t stream, long long* trace = nullptr, unsigned long long* span = nullptr);
+#else
+cudaError_t launch_pair_tc(const ConvParams& c, const float* bias1, const PairGeom& g, const CUtensorMap& tmA,
+                           const CUtensorMap& tmW1, const CUtensorMap& tmW2, const PairEpiMaps& em, int num_ctas,
+                           cudaStream_t stream, long long* trace, unsigned long long* span) {
   PairParams P;
   P.c = c;
   P.bias1 = bias1;
@@ -845,5 +845,6 @@ inline cudaError_t launch_pair_tc(const ConvParams& c, const float* bias1, const
     default: return cudaErrorInvalidValue;   // a ResBlock step always has the residual and an output
   }
 }
+#endif  // L2S_TU_PAIR_TC
 
 }  // namespace l2s

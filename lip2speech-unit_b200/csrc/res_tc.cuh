@@ -686,7 +686,11 @@ inline cudaError_t launch_res_mode(const ResParams& P, const ResMaps& maps, int 
   return cudaLaunchKernelEx(&cfg, res_tc_kernel<MODE, DUAL, CG2>, maps, P);
 }
 
-inline cudaError_t launch_res_tc(const ResParams& P, const ResMaps& maps, int num_ctas, cudaStream_t stream) {
+// Defined in tu_res_tc.cu (the only translation unit that instantiates res_tc_kernel); declared everywhere else.
+#ifndef L2S_TU_RES_TC
+cudaError_t launch_res_tc(const ResParams& P, const ResMaps& maps, int num_ctas, cudaStream_t stream);
+#else
+cudaError_t launch_res_tc(const ResParams& P, const ResMaps& maps, int num_ctas, cudaStream_t stream) {
   const ResGeom& g = P.g;
   const ConvParams& c = P.c;
   const int cap = num_ctas * g.ctas_per_sm;
@@ -709,5 +713,6 @@ inline cudaError_t launch_res_tc(const ResParams& P, const ResMaps& maps, int nu
     default: return cudaErrorInvalidValue;
   }
 }
+#endif  // L2S_TU_RES_TC
 
 }  // namespace l2s

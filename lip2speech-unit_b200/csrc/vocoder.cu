@@ -1120,13 +1120,8 @@ int l2s_debug_conv(const l2s_conv_desc* d, int32_t impl, int32_t device, void* s
     }
     e = launch_conv_tc(p, g, tmA, tmW, tune.max_ctas, st, reinterpret_cast<long long*>(g_knobs.trace_ptr));
     if (e == cudaSuccess && err && err_len > 0 && g_knobs.plan_report) {
-      int occ = -1;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_tc_kernel<8>, kTcThreads, g.smem_bytes);
-      cudaFuncAttributes fa{};
-      cudaFuncGetAttributes(&fa, conv_tc_kernel<8>);
-      snprintf(err, (size_t)err_len,
-               "plan msub=%d nt=%d kc=%d tb=%d sa=%d sb=%d smem=%d tmem=%d items=%d ctas_per_sm=%d occ=%d regs=%d",
-               g.msub, g.nt, g.kc, g.tb, g.sa, g.sb, g.smem_bytes, g.tmem_cols, g.total_items, g.ctas_per_sm, occ, fa.numRegs);
+      snprintf(err, (size_t)err_len, "plan msub=%d nt=%d kc=%d tb=%d sa=%d sb=%d smem=%d tmem=%d items=%d ctas_per_sm=%d",
+               g.msub, g.nt, g.kc, g.tb, g.sa, g.sb, g.smem_bytes, g.tmem_cols, g.total_items, g.ctas_per_sm);
     }
   }
   if (e != cudaSuccess) { say(cudaGetErrorString(e)); return L2S_ERR_CUDA; }
@@ -1143,16 +1138,6 @@ int l2s_debug_layer_time(l2s_vocoder* v, int32_t idx, float* ms, double* flops, 
   if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, cudaGetErrorString(e));
   if (flops) *flops = t.flops;
   if (name && name_len > 0) snprintf(name, (size_t)name_len, "%s", t.name.c_str());
-  return L2S_OK;
-}
-
-// debug: read (and reset) the epilogue cycle accounting; enable with l2s_debug_set("epi_prof", 1)
-int l2s_debug_epi_prof(long long* out8) {
-  if (!out8) return L2S_ERR_INVALID;
-  cudaDeviceSynchronize();
-  if (cudaMemcpyFromSymbol(out8, g_epi_prof, 8 * sizeof(long long)) != cudaSuccess) return L2S_ERR_CUDA;
-  long long z[8] = {0};
-  cudaMemcpyToSymbol(g_epi_prof, z, sizeof z);
   return L2S_OK;
 }
 
@@ -1181,7 +1166,6 @@ int l2s_debug_set(const char* key, int64_t value) {
   else if (k == "pair_pref") g_pair_pref = (int)value;
   else if (k == "cg2") g_pair_cg2 = (int)value;
   else if (k == "pair_smem") g_knobs.pair_smem = value;
-  else if (k == "epi_prof") { int on = (int)value; cudaMemcpyToSymbol(g_epi_prof_on, &on, sizeof on); }
   else if (k == "trace_launch") g_knobs.trace_launch = value;
   else if (k == "span_ptr") g_knobs.span_ptr = value;
   else if (k == "plan_report") g_knobs.plan_report = value;

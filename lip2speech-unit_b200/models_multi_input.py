@@ -21,7 +21,10 @@ import threading
 import torch
 import torch.nn as nn
 
-from . import _cabi
+try:                                   # package member (lip2speech_unit_b200.models_multi_input)
+    from . import _cabi
+except ImportError:                    # top-level module: this directory is on sys.path and shadows the reference's
+    import _cabi                       # models_multi_input.py (inference.py:28 `from models_multi_input import ...`)
 
 LRELU_SLOPE = 0.1
 

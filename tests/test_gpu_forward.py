@@ -1,12 +1,15 @@
 """Parity of the CUDA path (through the C ABI, via the drop-in classes) against
 the CPU oracle and the golden vectors made from the unmodified reference.
 
-Tolerances (stated per mode, vs the fp64 reference run):
-  fp32 mode  CUDA-core FFMA, fp32 storage      : SNR >= 100 dB, max-abs <= 2e-5
-  tf32 mode  tcgen05 kind::tf32, fp32 storage  : SNR >= 55 dB,  max-abs <= 5e-3
+Tolerances (stated per mode, vs the fp64 reference run; floors sit within 3 dB of what is measured on B200,
+profiles/r02_parity.txt; 1 int16 LSB of the waveform callers quantise = 3.05e-5):
+  fp32 mode  CUDA-core FFMA, fp32 storage      : SNR >= 113 dB, max-abs <= 2e-5 (< 1 LSB)   measured 116.5-132.8 dB
+  tf32 mode  tcgen05 kind::tf32, fp32 storage  : SNR >= 58 dB,  max-abs <= 4e-3 (131 LSB)   measured 59.8-63.1 dB
   bf16 mode  tcgen05 bf16 operands, fp32 accum,
-             fp32 residual stream              : SNR >= 35 dB on trained-like weights
-Unit-table indexing is bit-exact in both modes.
+             fp32 residual stream              : SNR >= 43 dB, max-abs <= 2e-2 (655 LSB) on trained-like weights,
+                                                 measured 45.8-47.0 dB / <= 1.2e-2 (393 LSB)
+  unit-only variant (shorter stack, rates [5,4,4,2,2]): bf16 >= 39 dB (measured 42.0), tf32 >= 57 dB (measured 59.8)
+Unit-table indexing is bit-exact in every mode.
 """
 import os
 
@@ -20,7 +23,8 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 DEV = "cuda:0"
 
-TOL = {"fp32": dict(snr=100.0, max_abs=2e-5), "bf16": dict(snr=35.0, max_abs=5e-2), "tf32": dict(snr=55.0, max_abs=5e-3)}
+TOL = {"fp32": dict(snr=113.0, max_abs=2e-5), "bf16": dict(snr=43.0, max_abs=2e-2), "tf32": dict(snr=58.0, max_abs=4e-3)}
+TOL_UNIT_ONLY = {"fp32": dict(snr=113.0, max_abs=2e-5), "bf16": dict(snr=39.0, max_abs=2e-2), "tf32": dict(snr=57.0, max_abs=4e-3)}
 
 
 def make_gen(pkg, h, sd, precision, cls="MelCodeGenerator", fold=True):
@@ -39,14 +43,15 @@ def weights():
     return h, {st: vo.init_state_dict(h, seed=1234, style=st) for st in ("ref", "trained")}
 
 
-def check(ref, y, precision, what):
+def check(ref, y, precision, what, tol=None):
+    tol = tol or TOL
     y = y.detach().cpu()
     assert y.shape == ref.shape, what
     assert torch.isfinite(y).all(), what
     snr, ma = vo.snr_db(ref, y), vo.max_abs(ref, y)
-    print(f"[parity] {what} {precision}: snr {snr:.2f} dB max-abs {ma:.3e}")
-    assert snr >= TOL[precision]["snr"], f"{what}: SNR {snr:.1f} dB"
-    assert ma <= TOL[precision]["max_abs"], f"{what}: max-abs {ma:.3e}"
+    print(f"[parity] {what} {precision}: snr {snr:.2f} dB max-abs {ma:.3e} = {ma * 32768.0:.1f} int16 LSB")
+    assert snr >= tol[precision]["snr"], f"{what}: SNR {snr:.1f} dB"
+    assert ma <= tol[precision]["max_abs"], f"{what}: max-abs {ma:.3e}"
     return snr, ma
 
 
@@ -115,7 +120,7 @@ def test_unit_only_variant(pkg, precision):
     z = np.load(os.path.join(GOLDEN, "unit_only_b2_u12.npz"))
     g = make_gen(pkg, h, sd, precision, cls="CodeGenerator")
     y = g(code=torch.from_numpy(z["code"]).to(DEV), spkr=torch.from_numpy(z["spkr"]).to(DEV))
-    check(torch.from_numpy(z["wave_trained"]), y, precision, "unit_only")
+    check(torch.from_numpy(z["wave_trained"]), y, precision, "unit_only", tol=TOL_UNIT_ONLY)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16", "tf32"])
@@ -475,4 +480,4 @@ def test_cfg2_shape_bf16_vs_fp32_device_reference(pkg, weights):
     assert torch.isfinite(b).all() and float(b.abs().max()) <= 1.0
     snr = vo.snr_db(a.cpu(), b.cpu())
     print(f"[parity] cfg2 bf16 vs fp32-device: snr {snr:.2f} dB max-abs {vo.max_abs(a.cpu(), b.cpu()):.3e}")
-    assert snr >= 35.0
+    assert snr >= 43.0
