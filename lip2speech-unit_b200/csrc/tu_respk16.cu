@@ -1,0 +1,4 @@
+// Translation unit that owns the C = 16 instantiations of the time-packed whole-ResBlock kernel.
+#define L2S_TU_RESPK_C 16
+#include <vector>
+#include "respk_tc.cuh"

@@ -19,6 +19,7 @@
 #include "pair_tc.cuh"
 #include "frontend.cuh"
 #include "res_tc.cuh"
+#include "respk_tc.cuh"
 
 using namespace l2s;
 
@@ -93,6 +94,11 @@ struct ConvLayer {
   CUtensorMap tmW;
   bool has_tmW = false;
   int tm_nt = 0, tm_tb = 0;
+  // time-packed whole-ResBlock kernel (respk_tc.cuh): block-Toeplitz copy [pk_groups][128][64] bf16
+  void* wpk_dev = nullptr;
+  int pk_groups = 0;
+  CUtensorMap tmWpk;
+  int tmpk_rows = 0, tmpk_tb = 0;
 };
 
 }  // namespace
@@ -107,6 +113,7 @@ struct l2s_vocoder {
   std::vector<std::vector<std::vector<int>>> rb_c1, rb_c2;  // [stage][branch][dil]
   std::vector<int> stage_ch;
   float* d_zero_bias = nullptr;                // 256 zeros: output epilogue of the whole-ResBlock kernel
+  std::vector<std::vector<float*>> pk_bias;    // [stage][branch]: [2 n_dil + 1][128] per-column constants of the time-packed kernel
   bool finalized = false;
   int device = -1, num_sms = 0;
   // device-side small weights
@@ -481,14 +488,86 @@ bool branch_geom(const l2s_vocoder* v, int i, int j, int lin, int batch, ResGeom
   return res_plan(a.cin, a.k, c.n_dil, dil, lin, batch, (int)g_knobs.res_mode, (int)g_knobs.res_msub, g);
 }
 
+// Time-packed plan of ResBlock (i, j), if there is one (respk_tc.cuh).
+bool branch_pk_geom(const l2s_vocoder* v, int i, int j, int lin, int batch, PkGeom* g) {
+  const l2s_config& c = v->cfg;
+  const ConvLayer& a = v->convs[v->rb_c1[i][j][0]];
+  int dil[kPkMaxDil];
+  if (c.n_dil > kPkMaxDil || a.cin != a.cout || a.cin_pad != a.cin || !a.wpk_dev || !v->pk_bias[i][j]) return false;
+  for (int m = 0; m < c.n_dil; ++m) {
+    const ConvLayer& a1 = v->convs[v->rb_c1[i][j][m]];
+    const ConvLayer& a2 = v->convs[v->rb_c2[i][j][m]];
+    if (a1.k != a.k || a2.k != a.k || a2.dil != 1 || !a1.wpk_dev || !a2.wpk_dev) return false;
+    dil[m] = a1.dil;
+  }
+  return pk_plan(a.cin, a.k, c.n_dil, dil, lin, batch, g);
+}
+
 // Every ResBlock of stage i runs as one whole-ResBlock kernel (bf16 mode, C <= 64, a plan exists for each branch).
 bool stage_branch_fused(const l2s_vocoder* v, int i, int lin, int batch) {
   if (!pairs_fused(v) || !g_knobs.fuse_branch || v->stage_ch[i] > 64) return false;
   for (int j = 0; j < v->cfg.n_rk; ++j) {
     ResGeom g;
-    if (!branch_geom(v, i, j, lin, batch, &g)) return false;
+    PkGeom pg;
+    if (!branch_pk_geom(v, i, j, lin, batch, &pg) && !branch_geom(v, i, j, lin, batch, &g)) return false;
   }
   return true;
+}
+
+// One whole ResBlock through the time-packed kernel.  L2S_ERR_UNSUPPORTED: no packed plan (the caller runs run_res).
+int run_respk(l2s_vocoder* v, int i, int j, cudaStream_t st, int batch, int lin, const float* x, float* out_raw, void* out_act,
+              const float* acc_in, float div, float slope) {
+  const l2s_config& c = v->cfg;
+  PkParams P{};
+  if (!branch_pk_geom(v, i, j, lin, batch, &P.g)) return L2S_ERR_UNSUPPORTED;
+  if (!pk_mode_supported(((acc_in || div != 1.0f) ? kEpiAcc : 0) | (out_raw ? kEpiRaw : 0) | (out_act ? kEpiAct : 0))) return L2S_ERR_UNSUPPORTED;
+  const PkGeom& g = P.g;
+  PkMaps maps;
+  double flops = 0.0;
+  const int w_rows = g.cg2 ? 64 : 128;
+  for (int m = 0; m < c.n_dil; ++m) {
+    for (int which = 0; which < 2; ++which) {
+      ConvLayer& L = v->convs[which ? v->rb_c2[i][j][m] : v->rb_c1[i][j][m]];
+      if (L.tmpk_rows != w_rows || L.tmpk_tb != g.tb) {
+        if (!make_tmap_bf16_3d(&L.tmWpk, L.wpk_dev, 64u, 128u, (uint64_t)L.pk_groups, 64u, (uint32_t)w_rows, (uint32_t)g.tb))
+          return fail(v, L2S_ERR_CUDA, "cuTensorMapEncodeTiled failed for the packed weights of " + L.name);
+        L.tmpk_rows = w_rows;
+        L.tmpk_tb = g.tb;
+      }
+      maps.w[2 * m + which] = L.tmWpk;
+      flops += 2.0 * L.cin * L.cout * L.k * (double)batch * lin;
+    }
+  }
+  for (int m = 2 * c.n_dil; m < 2 * kPkMaxDil; ++m) maps.w[m] = maps.w[0];
+  ConvParams& p = P.c;                        // output epilogue in packed terms: rows = blocks of P time steps, 128 columns
+  p.bias = v->pk_bias[i][j] + (size_t)(2 * c.n_dil) * 128;
+  p.out_raw = out_raw;
+  p.out_act = out_act;
+  p.acc_in = acc_in;
+  p.batch = batch;
+  p.lin = lin / g.P;
+  p.cin_pad = 128;
+  p.ntaps = g.k;
+  p.ntot = 128;
+  p.mrows = lin / g.P;
+  p.out_shift = 0;
+  p.out_valid = (long long)lin * g.c;
+  p.div = div;
+  p.slope = slope;
+  P.x = x;
+  P.bias_cols = v->pk_bias[i][j];
+  P.lin = lin;
+  P.span = g_knobs.span_ptr ? reinterpret_cast<unsigned long long*>(g_knobs.span_ptr) + 2 * v->tc_launches : nullptr;
+  ++v->tc_launches;
+  P.trace = (g_knobs.trace_ptr && g_knobs.trace_launch == v->res_launches) ? reinterpret_cast<long long*>(g_knobs.trace_ptr) : nullptr;
+  ++v->res_launches;
+  const std::string nm = v->convs[v->rb_c1[i][j][0]].name;
+  timed_begin(v, st, nm.substr(0, nm.find(".convs1")) + " (packed)", flops);
+  const int ctas = g_knobs.max_ctas > 0 ? (int)g_knobs.max_ctas : v->num_sms;
+  cudaError_t e = launch_respk_tc(P, maps, ctas, st);
+  timed_end(v, st);
+  if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, std::string("launch packed ResBlock ") + nm + ": " + cudaGetErrorString(e));
+  return L2S_OK;
 }
 
 // One whole ResBlock: x -> x + sum of its steps, then the branch sum / mean epilogue.
@@ -630,7 +709,8 @@ int run_chain(l2s_vocoder* v, cudaStream_t st, const Workspace& ws, int batch, i
           a_in = c.n_rk == 1 ? nullptr : ws.acc;
           dv = (float)c.n_rk;
         }
-        rc = run_res(v, i, j, st, batch, (int)len, ws.x, o_raw, o_act, a_in, dv, 0.1f);
+        rc = run_respk(v, i, j, st, batch, (int)len, ws.x, o_raw, o_act, a_in, dv, 0.1f);
+        if (rc == L2S_ERR_UNSUPPORTED) rc = run_res(v, i, j, st, batch, (int)len, ws.x, o_raw, o_act, a_in, dv, 0.1f);
         if (rc == L2S_ERR_UNSUPPORTED) return fail(v, L2S_ERR_STATE, "whole-ResBlock plan vanished");
         if (rc) return rc;
       }
@@ -937,6 +1017,33 @@ int l2s_finalize(l2s_vocoder* v, int device) {
     v->d_zero_bias = dev_upload<float>(v, zeros.data(), zeros.size(), &e);
     if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, cudaGetErrorString(e));
   }
+  // time-packed whole-ResBlock kernel: block-Toeplitz weights and per-column bias constants of the C <= 64 stages
+  v->pk_bias.assign((size_t)c.n_ups, std::vector<float*>((size_t)c.n_rk, nullptr));
+  for (int i = 0; bf && i < c.n_ups; ++i) {
+    const int ch = v->stage_ch[i];
+    if (ch != 16 && ch != 32 && ch != 64) continue;
+    for (int j = 0; j < c.n_rk; ++j) {
+      std::vector<float> cols((size_t)(2 * c.n_dil + 1) * 128, 0.f), run((size_t)ch, 0.f);
+      for (int m = 0; m < c.n_dil; ++m) {
+        for (int which = 0; which < 2; ++which) {
+          ConvLayer& L = v->convs[which ? v->rb_c2[i][j][m] : v->rb_c1[i][j][m]];
+          std::vector<float> pk;
+          pk_pack_weights(v->weights[L.name + ".weight"].data(), ch, L.k, &pk);
+          std::vector<uint16_t> hw(pk.size());
+          for (size_t q = 0; q < pk.size(); ++q) hw[q] = f2bf(pk[q]);
+          L.wpk_dev = dev_upload<uint16_t>(v, hw.data(), hw.size(), &e);
+          if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, std::string("upload packed ") + L.name + ": " + cudaGetErrorString(e));
+          L.pk_groups = (int)(pk.size() / (128 * 64));
+          const std::vector<float>& b = v->weights[L.name + ".bias"];
+          if (which) for (int q = 0; q < ch; ++q) run[q] += b[q];            // running sum of the c2 biases
+          for (int col = 0; col < 128; ++col) cols[(size_t)(2 * m + which) * 128 + col] = which ? run[col % ch] : b[col % ch];
+        }
+      }
+      for (int col = 0; col < 128; ++col) cols[(size_t)(2 * c.n_dil) * 128 + col] = run[col % ch];   // output epilogue: all c2 biases
+      v->pk_bias[i][j] = dev_upload<float>(v, cols.data(), cols.size(), &e);
+      if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, cudaGetErrorString(e));
+    }
+  }
   {
     const std::vector<float>& d = v->weights["dict.weight"];
     v->d_dict = dev_upload<float>(v, d.data(), d.size(), &e);
@@ -1159,6 +1266,10 @@ int l2s_debug_set(const char* key, int64_t value) {
   else if (k == "res_single_pct") g_res_single_pct = (int)value;
   else if (k == "res_quad_pct") g_res_quad_pct = (int)value;
   else if (k == "res_cg2") g_res_cg2 = (int)value;
+  else if (k == "pack") g_pk_on = (int)value;
+  else if (k == "pk_mode") g_pk_mode = (int)value;
+  else if (k == "pk_cg2") g_pk_cg2 = (int)value;
+  else if (k == "pk_single_pct") g_pk_single_pct = (int)value;
   else if (k == "cluster") g_knobs.cluster = value;
   else if (k == "alias_at") g_knobs.alias_at = value;
   else if (k == "epi_tma") g_knobs.epi_tma = value;

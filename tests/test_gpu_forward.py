@@ -294,16 +294,74 @@ def test_whole_resblock_tilings_agree(pkg, weights, knob, value):
     g = make_gen(pkg, h, sds["trained"], "bf16")
     lib = pkg._cabi.load()
     try:
+        lib.l2s_debug_set(b"pack", 0)             # the tap-by-tap whole-ResBlock kernel (the time-packed one is tested below)
         a = g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV)).clone()
         lib.l2s_debug_set(knob.encode(), value)
         b = g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV)).clone()
     finally:
+        lib.l2s_debug_set(b"pack", 1)
         lib.l2s_debug_set(b"res_mode", 0)
         lib.l2s_debug_set(b"res_msub", 8)
         lib.l2s_debug_set(b"res_quad_pct", 115)
         lib.l2s_debug_set(b"res_cg2", 4)
     assert torch.isfinite(a).all()
     assert torch.equal(a, b), float((a - b).abs().max())
+
+
+@pytest.mark.parametrize("knob,value", [("pk_mode", 1), ("pk_mode", 2), ("pk_cg2", 0)])
+@pytest.mark.parametrize("batch,frames", [(3, 150), (1, 34)])
+def test_packed_resblock_variants_agree(pkg, weights, knob, value, batch, frames):
+    """Time-packed whole-ResBlock kernel (respk_tc.cuh): tile size / CTAs per SM (pk_mode) and CTA pairs (pk_cg2) change
+    where an output element sits in a tile and which phase-major block holds it, not its arithmetic (the same offset
+    MMAs in the same order): the waveform must not change by a bit."""
+    h, sds = weights
+    code, mel, spkr = vo.synthetic_inputs(batch, frames, seed=33)
+    g = make_gen(pkg, h, sds["trained"], "bf16")
+    lib = pkg._cabi.load()
+    try:
+        a = g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV)).clone()
+        lib.l2s_debug_set(knob.encode(), value)
+        b = g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV)).clone()
+    finally:
+        lib.l2s_debug_set(b"pk_mode", 0)
+        lib.l2s_debug_set(b"pk_cg2", 1)
+    assert torch.isfinite(a).all()
+    assert torch.equal(a, b), float((a - b).abs().max())
+
+
+@pytest.mark.parametrize("batch,frames", [(2, 100), (1, 428), (4, 62)])
+def test_packed_vs_tap_by_tap_whole_resblock(pkg, weights, batch, frames):
+    """The time-packed kernel and the tap-by-tap whole-ResBlock kernel compute the same ResBlocks with a different
+    summation order (offset MMAs over P packed time steps vs one MMA per tap) and different bias insertion points:
+    MRF outputs of the three narrow stages agree to bf16-noise level, and both keep the bf16 tolerance to the oracle."""
+    h, sds = weights
+    code, mel, spkr = vo.synthetic_inputs(batch, frames, seed=21)
+    g = make_gen(pkg, h, sds["trained"], "bf16")
+    lib = pkg._cabi.load()
+    chans, rates = [256, 128, 64, 32, 16], [5, 20, 40, 80, 160]
+    outs = []
+    try:
+        for stage in (2, 3, 4):
+            taps = []
+            for pack in (0, 1):
+                lib.l2s_debug_set(b"pack", pack)
+                lib.l2s_debug_set(b"stop_after_stage", stage)
+                g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV))
+                taps.append(g.debug_tap("mrf", (batch, frames * rates[stage], chans[stage]), device=DEV))
+            snr = vo.snr_db(taps[0], taps[1])
+            print(f"[parity] packed vs tap-by-tap, MRF stage {stage}, {batch}x{frames}: {snr:.1f} dB")
+            assert torch.isfinite(taps[1]).all()
+            assert snr >= [60.0, 50.0, 45.0][stage - 2], (stage, snr)
+        lib.l2s_debug_set(b"stop_after_stage", -1)
+        for pack in (0, 1):
+            lib.l2s_debug_set(b"pack", pack)
+            outs.append(g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV)).cpu())
+    finally:
+        lib.l2s_debug_set(b"stop_after_stage", -1)
+        lib.l2s_debug_set(b"pack", 1)
+    ref = vo.mel_code_generator_forward(vo.fold_weight_norm(sds["trained"]), h, code, mel, spkr)
+    check(ref, outs[0], "bf16", f"tap-by-tap whole-ResBlock {batch}x{frames}")
+    check(ref, outs[1], "bf16", f"time-packed whole-ResBlock {batch}x{frames}")
 
 
 @pytest.mark.parametrize("knob", ["dual", "cluster", "cg2", "alias_at", "epi_tma", "pdl"])
