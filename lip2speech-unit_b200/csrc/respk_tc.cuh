@@ -145,6 +145,143 @@ __device__ __forceinline__ void pk_phase(const PkGeom& g, const PkLane& w, uint8
   }
 }
 
+// ---- table-driven fast path ---------------------------------------------------------------------------------
+// Where a thread's (unit, slot) lands in S depends only on the layout, not on the item, so every thread computes the
+// shared-memory offsets of its slots ONCE per kernel (tab[mapping][slot], 16-bit units of 16 bytes, 0xFFFF = the
+// layout does not hold this slot) and a phase is TMEM load -> + constants -> leaky-ReLU -> bf16 -> four stores at
+// tab ^ piece.  Mappings: 0 load (natural -> layout 0), 1 + 2s phase A of step s (layout s -> natural),
+// 2 + 2s phase B of step s (natural -> layout s + 1).  Tiles that touch an utterance edge take the generic path
+// above (they also zero what lies outside [0, L)).
+constexpr int kPkMaps = 2 * 3;     // the table path covers n_dil <= 3
+
+template <int C>
+__device__ __forceinline__ uint32_t pk_slot_offset(const PkGeom& g, int row, int col, bool src_nat, const PkLay& L) {
+  constexpr int P = 128 / C, Q = P / 2;
+  constexpr int LC = C == 16 ? 4 : (C == 32 ? 5 : 6), LP = 7 - LC, LQ = LP - 1;
+  const int j = col >> LC, ch = col & (C - 1);
+  const int xs = row * P + j;
+  int tau, xd;
+  if (src_nat) { tau = xs; xd = pk_pos(L, tau); }
+  else { tau = pk_tau(L, xs); xd = tau; }
+  if (tau < 0 || xd < 0) return 0xFFFFu;
+  const int drow = xd >> LP, de = xd & (P - 1);
+  const int h = de >> LQ, sl = de & (Q - 1);
+  return (uint32_t)(h * g.half_bytes + (kPkPadRows + drow) * 128 + (((((sl * C + ch) >> 3)) ^ (drow & 7)) << 4)) >> 4;
+}
+
+template <int C, int MSUB>
+struct PkTab {
+  static constexpr int SPU = C == 16 ? 2 : 1;              // slots (time steps, or half of one for C = 64) per 32-column unit
+  static constexpr int SLOTS = 2 * MSUB * SPU;             // per thread and phase
+  uint32_t v[kPkMaps][SLOTS / 2];                          // two 16-bit offsets per word
+  __device__ __forceinline__ uint32_t get(int m, int i) const { return (v[m][i >> 1] >> (16 * (i & 1))) & 0xFFFFu; }
+};
+
+template <int C, int MSUB>
+__device__ __forceinline__ void pk_build_tab(const PkGeom& g, const PkLane& w, PkTab<C, MSUB>& t) {
+  using T = PkTab<C, MSUB>;
+  const PkLay nat{1, 0u, g.mt};
+#pragma unroll
+  for (int m = 0; m < kPkMaps; ++m) {
+    const int st = m == 0 ? 0 : (m - 1) >> 1;
+    const bool to_nat = m != 0 && ((m - 1) & 1) == 0;       // phase A: layout st -> natural
+    const int li = m == 0 ? 0 : (to_nat ? st : st + 1);
+    const bool live = li < g.n_dil;
+    const PkLay L = live ? g.lay[li] : nat;
+#pragma unroll
+    for (int i = 0; i < T::SLOTS; i += 2) {
+      uint32_t pair = 0;
+#pragma unroll
+      for (int k2 = 0; k2 < 2; ++k2) {
+        const int idx = i + k2, ui = idx / T::SPU, sp = idx % T::SPU;
+        const int u = w.half + 2 * ui;
+        const int row = (u >> 2) * 128 + w.quad * 32 + w.lane;
+        const int col = (u & 3) * 32 + sp * (32 / T::SPU);
+        const uint32_t off = live ? pk_slot_offset<C>(g, row, col, !to_nat || L.d == 1, L) : 0xFFFFu;
+        pair |= off << (16 * k2);
+      }
+      t.v[m][i >> 1] = pair;
+    }
+  }
+}
+
+__device__ __forceinline__ void ldg256(const float* p, uint32_t* v) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p));
+}
+
+// leaky-ReLU -> bf16 -> the unit's four 16-byte pieces at tab ^ piece
+template <int C, int MSUB>
+__device__ __forceinline__ void pk_store_fast(uint8_t* slab, const uint32_t (&r)[32], const PkTab<C, MSUB>& t, int m, int ui) {
+  using T = PkTab<C, MSUB>;
+  const __nv_bfloat162 slope2 = __float2bfloat162_rn(0.1f);   // LRELU_SLOPE, models.py:13,38
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int sp = T::SPU == 2 ? e >> 1 : 0, pe = T::SPU == 2 ? (e & 1) : e;
+    const uint32_t a16 = t.get(m, ui * T::SPU + sp);
+    uint4 pk;
+    pk.x = lrelu_bf16x2(__uint_as_float(r[8 * e + 0]), __uint_as_float(r[8 * e + 1]), slope2);
+    pk.y = lrelu_bf16x2(__uint_as_float(r[8 * e + 2]), __uint_as_float(r[8 * e + 3]), slope2);
+    pk.z = lrelu_bf16x2(__uint_as_float(r[8 * e + 4]), __uint_as_float(r[8 * e + 5]), slope2);
+    pk.w = lrelu_bf16x2(__uint_as_float(r[8 * e + 6]), __uint_as_float(r[8 * e + 7]), slope2);
+    if (a16 != 0xFFFFu) *reinterpret_cast<uint4*>(slab + ((size_t)(a16 ^ (uint32_t)pe) << 4)) = pk;
+  }
+}
+
+template <int C, int MSUB>
+__device__ __forceinline__ void pk_phase_fast(const PkLane& w, uint8_t* slab, uint32_t t_quad, const float* bias_cols, const PkTab<C, MSUB>& t,
+                                              int m) {
+#pragma unroll
+  for (int ui = 0; ui < 2 * MSUB; ++ui) {
+    const int u = w.half + 2 * ui;
+    uint32_t r[32];
+    tmem_ld32(t_quad + (uint32_t)(32 * u), r);
+    tmem_ld_wait();
+    const float* bc = bias_cols + (u & 3) * 32;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 bq = *reinterpret_cast<const float4*>(bc + 4 * j);
+      r[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) + bq.x);
+      r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + bq.y);
+      r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + bq.z);
+      r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + bq.w);
+    }
+    pk_store_fast<C, MSUB>(slab, r, t, m, ui);
+  }
+}
+
+// x (global fp32) -> X (TMEM) and S = lrelu(x): every lane reads its own block row with 256-bit loads (each one a whole
+// 32-byte sector, so nothing depends on L1 keeping half-used sectors around); all of a thread's loads are in flight
+// before the first is consumed.  Blocks outside [0, L) are read as zeros (lrelu(0) = 0: the conv's zero padding).
+template <int C, int MSUB>
+__device__ __forceinline__ void pk_load_x_fast(const PkParams& P_, const PkLane& w, uint8_t* slab, uint32_t x_quad, int b, int t_row0, int lin,
+                                               const PkTab<C, MSUB>& t) {
+  constexpr int P = 128 / C;
+  const float* xb = P_.x + (long long)b * lin * C;
+  {
+#pragma unroll
+    for (int ui = 0; ui < 2 * MSUB; ++ui) {
+      const int u = w.half + 2 * ui;
+      const int tt = t_row0 + ((u >> 2) * 128 + w.quad * 32 + w.lane) * P;
+      const bool ok = tt >= 0 && tt < lin;
+      const float* src = xb + (long long)tt * C + (u & 3) * 32;
+      uint32_t r[32];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (ok) ldg256(src + 8 * q, &r[8 * q]);
+        else {
+#pragma unroll
+          for (int z = 0; z < 8; ++z) r[8 * q + z] = 0u;
+        }
+      }
+      tmem_st32(x_quad + (uint32_t)(32 * u), r);
+      pk_store_fast<C, MSUB>(slab, r, t, 0, ui);
+    }
+  }
+  tmem_st_wait();
+}
+
 // x (global fp32) -> X (TMEM) and S = lrelu(x) in the layout of the first c1.  A block row is P * C = 128 consecutive
 // floats of the utterance; every lane reads its own row (32 columns = one full 128-byte line per unit).
 template <int C>
@@ -295,6 +432,59 @@ __device__ __forceinline__ void pk_issue_stage(bool leader, int msub, int hc, in
   }
 }
 
+// All offset MMAs of one conv with every descriptor offset an immediate (HC = (k - 1) / 2 and MSUB compile-time): the
+// issuing thread's own instruction stream set the pace of the run-time version above (~250 cycles per MMA measured
+// against 64 cycles of tensor work).  Weight stages (TB groups each) are consumed from the ring as they land.
+template <int C, int HC, int MSUB, bool CG2, int TB>
+__device__ __forceinline__ void pk_issue_conv(bool leader, uint32_t desc_hi, uint32_t desc_lo_fixed, uint32_t s_lo, uint32_t half_step,
+                                              uint8_t* stageB, int bstage_bytes, int sb, uint64_t* b_full, uint64_t* b_empty, int& ib,
+                                              uint32_t& pb, uint32_t d_base, uint32_t acc_first) {
+  constexpr int P = 128 / C, Q = P / 2, K16 = C / 16;
+  constexpr int LP = C == 16 ? 3 : (C == 32 ? 2 : 1), LQ = LP - 1;
+  constexpr int N_OFF = P + 2 * HC, N_GROUPS = (N_OFF + Q - 1) / Q, N_TS = (N_GROUPS + TB - 1) / TB;
+  constexpr uint32_t kSlot = (2u * C) >> 4;
+  constexpr uint32_t kGroup = ((CG2 ? 64u : 128u) * 128u) >> 4;
+  constexpr uint32_t kSub = (128u * 128u) >> 4;
+  constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | (((CG2 ? 256u : 128u) >> 4) << 24);
+  const uint32_t s_hi = s_lo + half_step;
+#pragma unroll
+  for (int ts = 0; ts < N_TS; ++ts) {
+    mbar_wait(&b_full[ib], pb);
+    tc_fence_after();
+    const uint32_t b_lo = desc_lo_fixed | ((smem_u32(stageB + (size_t)ib * bstage_bytes) & 0x3FFFFu) >> 4);
+#pragma unroll
+    for (int gi = 0; gi < TB; ++gi) {
+#pragma unroll
+      for (int s = 0; s < Q; ++s) {
+        constexpr int dummy = 0; (void)dummy;
+        const int oi = (ts * TB + gi) * Q + s;               // compile-time after unrolling
+        if (oi < N_OFF) {
+          const int o = oi - HC;
+          const int shift = o >= 0 ? o / P : -((-o + P - 1) / P);
+          const int e = o - shift * P;
+          const uint32_t a_lo = ((e >> LQ) ? s_hi : s_lo) + (uint32_t)((kPkPadRows + shift) * 8) + (uint32_t)(e & (Q - 1)) * kSlot;
+          const uint32_t b_s = b_lo + (uint32_t)gi * kGroup + (uint32_t)s * kSlot;
+#pragma unroll
+          for (int sub = 0; sub < MSUB; ++sub) {
+#pragma unroll
+            for (int kk = 0; kk < K16; ++kk) {
+              const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + (uint32_t)sub * kSub + 2u * kk);
+              const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(b_s + 2u * kk);
+              const uint32_t acc = (oi == 0 && kk == 0) ? acc_first : 1u;
+              if (leader) {
+                if constexpr (CG2) umma_bf16_cg2(d_base + (uint32_t)sub * 128u, da, db, kIdesc, acc);
+                else umma_bf16(d_base + (uint32_t)sub * 128u, da, db, kIdesc, acc);
+              }
+            }
+          }
+        }
+      }
+    }
+    if (leader) { if constexpr (CG2) umma_commit_cg2(&b_empty[ib], (uint16_t)3); else umma_commit(&b_empty[ib]); }
+    if (++ib == sb) { ib = 0; pb ^= 1u; }
+  }
+}
+
 template <int C, int MODE, bool DUAL, bool CG2>
 __global__ void __maxnreg__(DUAL ? 80 : 168)
 respk_tc_kernel(const __grid_constant__ PkMaps maps, const PkParams P) {
@@ -408,15 +598,24 @@ respk_tc_kernel(const __grid_constant__ PkMaps maps, const PkParams P) {
         tc_fence_after();
         L2S_PTRACE(128, ntr);
         const uint32_t d_base = second ? tmem_base : tmem_base + (uint32_t)acc_cols;   // c2 accumulates onto X, c1 overwrites D1
-        for (int ts = 0; ts < g.n_tstages; ++ts) {
-          mbar_wait(&b_full[ib], pb);
-          tc_fence_after();
-          const uint32_t b_lo = desc_lo_fixed | ((smem_u32(stageB + (size_t)ib * g.bstage_bytes) & 0x3FFFFu) >> 4);
-          const int n_g = min(g.tb, g.n_groups - ts * g.tb);
-          pk_issue_stage<C, CG2>(leader, g.msub, g.hc, g.n_off, desc_hi, s_lo, half_step, b_lo, ts * g.tb, n_g, d_base, !second);
-          if (leader) commit(&b_empty[ib]);
-          if (++ib == g.sb) { ib = 0; pb ^= 1u; }
-        }
+        constexpr int MS = DUAL ? 1 : 2;
+        const uint32_t acc_first = second ? 1u : 0u;
+        if (g.tb == 2 && g.hc == 1)
+          pk_issue_conv<C, 1, MS, CG2, 2>(leader, desc_hi, desc_lo_fixed, s_lo, half_step, stageB, g.bstage_bytes, g.sb, b_full, b_empty, ib, pb, d_base, acc_first);
+        else if (g.tb == 2 && g.hc == 3)
+          pk_issue_conv<C, 3, MS, CG2, 2>(leader, desc_hi, desc_lo_fixed, s_lo, half_step, stageB, g.bstage_bytes, g.sb, b_full, b_empty, ib, pb, d_base, acc_first);
+        else if (g.tb == 2 && g.hc == 5)
+          pk_issue_conv<C, 5, MS, CG2, 2>(leader, desc_hi, desc_lo_fixed, s_lo, half_step, stageB, g.bstage_bytes, g.sb, b_full, b_empty, ib, pb, d_base, acc_first);
+        else
+          for (int ts = 0; ts < g.n_tstages; ++ts) {
+            mbar_wait(&b_full[ib], pb);
+            tc_fence_after();
+            const uint32_t b_lo = desc_lo_fixed | ((smem_u32(stageB + (size_t)ib * g.bstage_bytes) & 0x3FFFFu) >> 4);
+            const int n_g = min(g.tb, g.n_groups - ts * g.tb);
+            pk_issue_stage<C, CG2>(leader, g.msub, g.hc, g.n_off, desc_hi, s_lo, half_step, b_lo, ts * g.tb, n_g, d_base, !second);
+            if (leader) commit(&b_empty[ib]);
+            if (++ib == g.sb) { ib = 0; pb ^= 1u; }
+          }
         if (leader) commit(d_full);
         L2S_PTRACE(128, ntr);
       }
@@ -440,6 +639,10 @@ respk_tc_kernel(const __grid_constant__ PkMaps maps, const PkParams P) {
       if (lane == 0) { if constexpr (CG2) mbar_arrive_cluster(s_full, 0u, (uint32_t)crank); else mbar_arrive(s_full); }
     };
     const PkLay nat{1, 0u, g.mt};
+    constexpr int MS = DUAL ? 1 : 2;
+    PkTab<C, MS> tab;
+    const bool use_tab = g.n_dil <= 3;
+    if (use_tab) pk_build_tab<C, MS>(g, w, tab);
     for (int wk = walk0; wk < walk_n; wk += walkers) {
       const int item = item_of(wk);
       const bool dummy = item >= g.total_items;    // odd item count: the pair's last partner computes on zeros and stores nothing
@@ -450,7 +653,8 @@ respk_tc_kernel(const __grid_constant__ PkMaps maps, const PkParams P) {
       const int lin = dummy ? 0 : P.lin;
       const bool edge = t_row0 < 0 || t_row0 + g.mt > lin;
       L2S_PTRACE(0, ntr);
-      pk_load_x<C>(P, w, slab, x_quad, b, t_row0, lin);
+      if (use_tab) pk_load_x_fast<C, MS>(P, w, slab, x_quad, b, t_row0, lin, tab);
+      else pk_load_x<C>(P, w, slab, x_quad, b, t_row0, lin);
       L2S_PTRACE(0, ntr);
       publish();
       for (int st = 0; st < g.n_dil; ++st) {
@@ -460,7 +664,11 @@ respk_tc_kernel(const __grid_constant__ PkMaps maps, const PkParams P) {
         pd ^= 1u;
         tc_fence_after();
         L2S_PTRACE(0, ntr);
-        if (edge) pk_phase<C, true>(g, w, slab, d1_quad, sbias + (2 * st) * 128, g.lay[st].d == 1, g.lay[st].d == 1 ? nat : g.lay[st], t_row0, lin);
+        if (use_tab && !edge) {
+          if (st == 0) pk_phase_fast<C, MS>(w, slab, d1_quad, sbias, tab, 1);
+          else if (st == 1) pk_phase_fast<C, MS>(w, slab, d1_quad, sbias + 2 * 128, tab, 3);
+          else pk_phase_fast<C, MS>(w, slab, d1_quad, sbias + 4 * 128, tab, 5);
+        } else if (edge) pk_phase<C, true>(g, w, slab, d1_quad, sbias + (2 * st) * 128, g.lay[st].d == 1, g.lay[st].d == 1 ? nat : g.lay[st], t_row0, lin);
         else pk_phase<C, false>(g, w, slab, d1_quad, sbias + (2 * st) * 128, g.lay[st].d == 1, g.lay[st].d == 1 ? nat : g.lay[st], t_row0, lin);
         L2S_PTRACE(0, ntr);
         publish();
@@ -470,7 +678,10 @@ respk_tc_kernel(const __grid_constant__ PkMaps maps, const PkParams P) {
           pd ^= 1u;
           tc_fence_after();
           L2S_PTRACE(0, ntr);
-          if (edge) pk_phase<C, true>(g, w, slab, x_quad, sbias + (2 * st + 1) * 128, true, g.lay[st + 1], t_row0, lin);
+          if (use_tab && !edge) {
+            if (st == 0) pk_phase_fast<C, MS>(w, slab, x_quad, sbias + 1 * 128, tab, 2);
+            else pk_phase_fast<C, MS>(w, slab, x_quad, sbias + 3 * 128, tab, 4);
+          } else if (edge) pk_phase<C, true>(g, w, slab, x_quad, sbias + (2 * st + 1) * 128, true, g.lay[st + 1], t_row0, lin);
           else pk_phase<C, false>(g, w, slab, x_quad, sbias + (2 * st + 1) * 128, true, g.lay[st + 1], t_row0, lin);
           L2S_PTRACE(0, ntr);
           publish();

@@ -29,7 +29,7 @@ for _ in range(2):
 torch.cuda.synchronize()
 n_dil = 3
 for launch in [int(a) for a in sys.argv[1:] if "=" not in a] or [0, 2, 6, 8]:
-    tr = torch.zeros(256 + 64, dtype=torch.int64, device=dev)
+    tr = torch.zeros(640, dtype=torch.int64, device=dev)
     lib.l2s_debug_set(b"trace_ptr", tr.data_ptr()); lib.l2s_debug_set(b"trace_launch", launch)
     g(code=code, mel=mel, spkr=spkr)
     torch.cuda.synchronize()
@@ -37,7 +37,12 @@ for launch in [int(a) for a in sys.argv[1:] if "=" not in a] or [0, 2, 6, 8]:
     t = tr.cpu()
     e = [int(x) for x in t[:128].tolist() if int(x)]
     m = [int(x) for x in t[128:256].tolist() if int(x)]
-    fine = t[256:].view(4, 16)
+    fine = t[256:320].view(4, 16)
+    stg = [int(x) for x in t[320:448].tolist() if int(x)]
+    for ph in range(6):
+        row = [int(x) for x in t[448 + 16 * ph:448 + 16 * ph + 16].tolist() if int(x)]
+        if row:
+            print(f"  item 1 phase {'AB'[ph & 1]}{ph // 2}, per unit [start, tmem ld done, bias added, stored] us: " + " ".join(f"{(x - row[0]) / 1e3:.2f}" for x in row))
     if not e:
         print("launch", launch, "no stamps"); continue
     t0 = min(e[0], m[0])
@@ -57,6 +62,8 @@ for launch in [int(a) for a in sys.argv[1:] if "=" not in a] or [0, 2, 6, 8]:
     for it in range(len(m) // per_item_m):
         seg = m[it * per_item_m:(it + 1) * per_item_m]
         print(f"  M item {it}: " + " ".join(f"c{j // 3}[{(seg[j] - t0) / 1e3:.2f} {(seg[j + 1] - t0) / 1e3:.2f} {(seg[j + 2] - t0) / 1e3:.2f}]" for j in range(0, len(seg), 3)))
+    if stg:
+        print("  M weight stages [wait start, weights landed, MMAs issued] us: " + " ".join(f"[{(stg[j] - t0) / 1e3:.2f} {(stg[j + 1] - t0) / 1e3:.2f} {(stg[j + 2] - t0) / 1e3:.2f}]" for j in range(0, len(stg) - 2, 3)))
     for it in range(3):
         row = [int(x) for x in fine[it].tolist() if int(x)]
         if row:
