@@ -30,7 +30,8 @@
 
 namespace l2s {
 
-constexpr int kPkMaxDil = 4;
+constexpr int kPkMaxDil = 3;
+constexpr int kPkMaxBr = 3;        // ResBlocks (kernel-size branches of one MRF stage) fused into one launch
 constexpr int kPkPadRows = 8;      // zero rows above / below each slab (row shifts reach +-ceil(h / P) <= 4)
 
 struct PkLay {                     // block order of one conv's operand: d = 1 natural, else phase-major by d
@@ -40,24 +41,32 @@ struct PkLay {                     // block order of one conv's operand: d = 1 n
 };
 
 struct PkGeom {
-  int c, k, n_dil, hc;
+  int c, n_dil, n_br;              // n_br ResBlocks run back to back on every tile (branch fusion: x and the branch sum stay L2-hot)
+  int k[kPkMaxBr], hc[kPkMaxBr];
+  int n_off[kPkMaxBr], n_groups[kPkMaxBr], n_tstages[kPkMaxBr];   // offset MMAs, weight groups (Q offsets each), ring stages per conv
   int dil[kPkMaxDil];
   PkLay lay[kPkMaxDil];
   int P, Q;                        // time steps per block / per 128-byte slab row
-  int n_off, n_groups;             // offset MMAs per conv, weight groups (Q offsets each) per conv
   int msub, nr, mt, mt_v;          // accumulators, block rows, time steps of a tile, time steps that every layout maps
   int h_tot, hl;                   // summed halo, rounded up to a multiple of P (tile origin stays block aligned)
   int r_out, m_items, total_items;
   int half_bytes, s_bytes;
-  int tb, n_tstages, bstage_bytes, sb;
+  int tb, bstage_bytes, sb;
   int tmem_cols, cw, dual, tile_words, ctas_per_sm, cg2;
   int smem_bytes;
 };
 
+constexpr int kPkBiasRows = 2 * kPkMaxDil + 1;   // per branch: b1_s / running sum of b2 per step, then the sum of all c2 biases
+
 struct PkParams {
-  ConvParams c;                        // output epilogue in PACKED terms: lin = L / P block rows, ntot = 128, bias = sum of the c2 biases
-  const float* x;                      // fp32 residual stream entering the block, [B][L][C]
-  const float* bias_cols;              // [2 n_dil][128]: b1_s replicated over the P slots, then the running sum of b2_0..b2_s
+  ConvParams c;                        // output epilogue of the LAST branch in PACKED terms: lin = L / P block rows, ntot = 128
+  const float* x;                      // fp32 residual stream entering the block(s), [B][L][C]
+  const float* bias_cols;              // [n_br][kPkBiasRows][128]: b1_s replicated over the P slots / running sum of b2_0..b2_s, ..., sum of all b2
+  float* acc_buf;                      // n_br > 1: fp32 running branch sum [B][L][C] (written and re-read by the same thread)
+  // The same constants by value: they sit in the constant bank and feed the FADDs through the constant cache (read from
+  // shared memory they waited behind the MMA operand traffic: 0.3 us per unit measured).  [br][2 s] = b1_s,
+  // [br][2 s + 1] = b2_0 + .. + b2_s, [br][2 kPkMaxDil] = sum of all c2 biases (output); one value per channel.
+  float bias_ch[kPkMaxBr][kPkBiasRows][64];
   int lin;                             // L (time steps)
   PkGeom g;
   unsigned long long* span;            // debug: [0] min CTA start, [1] max CTA end (globaltimer)
@@ -69,7 +78,7 @@ struct PkParams {
   } while (0)
 
 struct PkMaps {
-  CUtensorMap w[2 * kPkMaxDil];        // Toeplitz weights of c1_0, c2_0, c1_1, c2_1, ...: [n_groups][128][64] bf16
+  CUtensorMap w[kPkMaxBr * 2 * kPkMaxDil];   // per branch: Toeplitz weights of c1_0, c2_0, c1_1, c2_1, ...: [n_groups][128][64] bf16
 };
 
 struct PkLane { int quad, half, lane; };
@@ -229,23 +238,30 @@ __device__ __forceinline__ void pk_store_fast(uint8_t* slab, const uint32_t (&r)
   }
 }
 
-template <int C, int MSUB>
-__device__ __forceinline__ void pk_phase_fast(const PkLane& w, uint8_t* slab, uint32_t t_quad, const float* bias_cols, const PkTab<C, MSUB>& t,
-                                              int m) {
+// SMEM_BIAS: the per-column constants come from shared memory ([128] floats, two-CTAs-per-SM kernels); else one value per
+// channel from the constant bank (kernel parameters), which keeps them off the shared-memory port the MMAs saturate.
+template <int C, int MSUB, bool SMEM_BIAS>
+__device__ __forceinline__ void pk_phase_fast(const PkLane& w, uint8_t* slab, uint32_t t_quad, const float* bias, const PkTab<C, MSUB>& t, int m) {
 #pragma unroll
   for (int ui = 0; ui < 2 * MSUB; ++ui) {
     const int u = w.half + 2 * ui;
     uint32_t r[32];
     tmem_ld32(t_quad + (uint32_t)(32 * u), r);
     tmem_ld_wait();
-    const float* bc = bias_cols + (u & 3) * 32;
+    if constexpr (SMEM_BIAS) {
+      const float* bc = bias + (u & 3) * 32;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 bq = *reinterpret_cast<const float4*>(bc + 4 * j);
-      r[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) + bq.x);
-      r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + bq.y);
-      r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + bq.z);
-      r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + bq.w);
+      for (int j = 0; j < 8; ++j) {
+        const float4 bq = *reinterpret_cast<const float4*>(bc + 4 * j);
+        r[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) + bq.x);
+        r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + bq.y);
+        r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + bq.z);
+        r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + bq.w);
+      }
+    } else {
+      const float* bc = bias + (((u & 3) * 32) & (C - 1));
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + bc[j & (C >= 32 ? 31 : C - 1)]);
     }
     pk_store_fast<C, MSUB>(slab, r, t, m, ui);
   }
@@ -397,6 +413,79 @@ __device__ __forceinline__ void pk_output(const ConvParams& p, float* tile, uint
   }
 }
 
+__device__ __forceinline__ void ldg256c(const float* p, uint32_t* v) {   // coherent: the running branch sum was written by this thread
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p) : "memory");
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
+               "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+
+// Output of a branch without the shared-memory transpose: every lane owns one block row (512 contiguous bytes of the
+// utterance) and moves it in whole 32-byte sectors (256-bit accesses), 16 columns at a time; the branch-sum sectors of
+// the next piece are pulled into L1 while the current one is finished.  bias: one value per channel (constant bank).
+template <int C, int MODE>
+__device__ __forceinline__ void pk_output_direct(const ConvParams& p, const float* bias, uint32_t t_base, int b, int row0, int row_lo, int row_lim,
+                                                 int msub, const PkLane& w, uint64_t* bar, uint32_t parity) {
+  const int n_units = 4 * msub;
+  const float inv_div = 1.0f / p.div;
+  const __nv_bfloat162 slope2 = __float2bfloat162_rn(p.slope);
+  auto unit_live = [&](int u) {
+    const int r0 = row0 + (u >> 2) * 128 + w.quad * 32;
+    return r0 < row_lim && r0 + 32 > row_lo;
+  };
+  auto elem0 = [&](int u, int hu) {   // flat element index of this lane's 16 columns
+    const int q = row0 + (u >> 2) * 128 + w.quad * 32 + w.lane;
+    return ((long long)b * p.lin + q) * 128 + (u & 3) * 32 + hu * 16;
+  };
+  auto row_ok = [&](int u) {
+    const int q = row0 + (u >> 2) * 128 + w.quad * 32 + w.lane;
+    return q >= row_lo && q < row_lim;
+  };
+  if constexpr ((MODE & kEpiAcc) != 0) {
+    for (int u = w.half; u < n_units; u += 2)
+      if (p.acc_in && unit_live(u) && row_ok(u)) prefetch_l1(p.acc_in + elem0(u, 0));   // one 128-byte line = the unit's 32 columns
+  }
+  mbar_wait(bar, parity);
+  tc_fence_after();
+  for (int u = w.half; u < n_units; u += 2) {
+    if (!unit_live(u)) continue;
+    const bool ok = row_ok(u);
+    const float* bc = bias + (((u & 3) * 32) & (C - 1));
+#pragma unroll
+    for (int hu = 0; hu < 2; ++hu) {
+      uint32_t r[16], a[16];
+      const long long e0 = elem0(u, hu);
+      if constexpr ((MODE & kEpiAcc) != 0) {
+        if (p.acc_in && ok) { ldg256c(p.acc_in + e0, a); ldg256c(p.acc_in + e0 + 8, a + 8); }
+        else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) a[j] = 0u;
+        }
+      }
+      tmem_ld16(t_base + (uint32_t)(32 * u + 16 * hu), r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float v = __uint_as_float(r[j]) + bc[(16 * hu + j) & (C >= 32 ? 31 : C - 1)];
+        if constexpr ((MODE & kEpiAcc) != 0) v = (v + __uint_as_float(a[j])) * inv_div;
+        r[j] = __float_as_uint(v);
+      }
+      if (ok) {
+        if constexpr ((MODE & kEpiRaw) != 0) { stg256(p.out_raw + e0, r); stg256(p.out_raw + e0 + 8, r + 8); }
+        if constexpr ((MODE & kEpiAct) != 0) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pk[j] = lrelu_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]), slope2);
+          stg256(reinterpret_cast<__nv_bfloat16*>(p.out_act) + e0, pk);
+        }
+      }
+    }
+  }
+}
+
 // Offset MMAs of one weight stage (groups g0 .. g0 + n_g) for all msub accumulators.
 template <int C, bool CG2>
 __device__ __forceinline__ void pk_issue_stage(bool leader, int msub, int hc, int n_off, uint32_t desc_hi, uint32_t s_lo, uint32_t half_step,
@@ -487,7 +576,7 @@ __device__ __forceinline__ void pk_issue_conv(bool leader, uint32_t desc_hi, uin
 
 template <int C, int MODE, bool DUAL, bool CG2>
 __global__ void __maxnreg__(DUAL ? 80 : 168)
-respk_tc_kernel(const __grid_constant__ PkMaps maps, const PkParams P) {
+respk_tc_kernel(const __grid_constant__ PkMaps maps, const __grid_constant__ PkParams P) {
   extern __shared__ uint8_t smem_raw[];
   const ConvParams& p = P.c;
   const PkGeom& g = P.g;
@@ -503,15 +592,15 @@ respk_tc_kernel(const __grid_constant__ PkMaps maps, const PkParams P) {
   uint64_t* s_full = b_empty + kTcMaxStagesB;   // S (and X) ready for the next conv: one arrival per epilogue warp
   uint64_t* d_full = s_full + 1;                // the conv's MMAs have retired (tcgen05.commit)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 1);
-  float* sbias = reinterpret_cast<float*>(bars + 24);                       // [2 n_dil][128]
-  float* epi_tiles = sbias + 2 * kPkMaxDil * 128;
+  float* sbias = reinterpret_cast<float*>(bars + 24);                       // [n_br][2 kPkMaxDil][128]
+  float* epi_tiles = sbias + kPkMaxBr * 2 * kPkMaxDil * 128;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   if (P.span && threadIdx.x == 0) atomicMin(&P.span[0], (unsigned long long)gtime());
 
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < 2 * g.n_dil; ++i) tma_prefetch_desc(&maps.w[i]);
+    for (int i = 0; i < g.n_br * 2 * kPkMaxDil; ++i) tma_prefetch_desc(&maps.w[i]);
     for (int i = 0; i < g.sb; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     mbar_init(s_full, (uint32_t)(CG2 ? 2 * kTcEpiWarps : kTcEpiWarps));
     mbar_init(d_full, 1);
@@ -523,7 +612,10 @@ respk_tc_kernel(const __grid_constant__ PkMaps maps, const PkParams P) {
     // multiplied by the zero entries of the Toeplitz weights)
     for (int o = (threadIdx.x - 64) * 16; o < g.s_bytes; o += ((int)blockDim.x - 64) * 16)
       *reinterpret_cast<uint4*>(slab + o) = make_uint4(0u, 0u, 0u, 0u);
-    for (int i = threadIdx.x - 64; i < 2 * g.n_dil * 128; i += (int)blockDim.x - 64) sbias[i] = P.bias_cols[i];
+    for (int i = threadIdx.x - 64; i < g.n_br * 2 * kPkMaxDil * 128; i += (int)blockDim.x - 64) {
+      const int br = i / (2 * kPkMaxDil * 128), rest = i - br * (2 * kPkMaxDil * 128);
+      sbias[i] = P.bias_cols[br * kPkBiasRows * 128 + rest];
+    }
     fence_proxy_async_smem();
   }
   tc_fence_before();
@@ -553,7 +645,7 @@ respk_tc_kernel(const __grid_constant__ PkMaps maps, const PkParams P) {
         const uint32_t bytes = (uint32_t)((hi - lo) * C * 4);
         for (uint32_t o = 0; o < bytes; o += 16384u)
           bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(P.x + e0) + o, min(16384u, bytes - o));
-        if ((MODE & kEpiAcc) != 0 && p.acc_in) {
+        if ((MODE & kEpiAcc) != 0 && p.acc_in && g.n_br == 1) {
           const int olo = max(nq, 0), ohi = min(nq + g.r_out, P.lin);
           const long long a0 = ((long long)nb * P.lin + olo) * C;
           const uint32_t ab = (uint32_t)((ohi - olo) * C * 4);
@@ -561,16 +653,18 @@ respk_tc_kernel(const __grid_constant__ PkMaps maps, const PkParams P) {
             bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.acc_in + a0) + o, min(16384u, ab - o));
         }
       }
+      for (int br = 0; br < g.n_br; ++br)
       for (int cv = 0; cv < 2 * g.n_dil; ++cv) {
-        for (int ts = 0; ts < g.n_tstages; ++ts) {
+        const CUtensorMap* wm = &maps.w[br * 2 * kPkMaxDil + cv];
+        for (int ts = 0; ts < g.n_tstages[br]; ++ts) {
           mbar_wait(&b_empty[ib], pb ^ 1u);
           if (leader) {
             if constexpr (CG2) {
               if (crank == 0) mbar_expect_tx(&b_full[ib], 2u * (uint32_t)g.bstage_bytes);
-              tma_load_3d_cg2(stageB + (size_t)ib * g.bstage_bytes, &maps.w[cv], &b_full[ib], 0, crank * 64, ts * g.tb);
+              tma_load_3d_cg2(stageB + (size_t)ib * g.bstage_bytes, wm, &b_full[ib], 0, crank * 64, ts * g.tb);
             } else {
               mbar_expect_tx(&b_full[ib], (uint32_t)g.bstage_bytes);
-              tma_load_3d(stageB + (size_t)ib * g.bstage_bytes, &maps.w[cv], &b_full[ib], 0, 0, ts * g.tb);
+              tma_load_3d(stageB + (size_t)ib * g.bstage_bytes, wm, &b_full[ib], 0, 0, ts * g.tb);
             }
           }
           if (++ib == g.sb) { ib = 0; pb ^= 1u; }
@@ -590,8 +684,10 @@ respk_tc_kernel(const __grid_constant__ PkMaps maps, const PkParams P) {
     int ntr = 0;
     auto commit = [&](uint64_t* bar) { if constexpr (CG2) umma_commit_cg2(bar, (uint16_t)3); else umma_commit(bar); };
     for (int wk = (CG2 && crank != 0) ? walk_n : walk0; wk < walk_n; wk += walkers) {   // CTA pair: the leader issues for both
+      for (int br = 0; br < g.n_br; ++br)
       for (int cv = 0; cv < 2 * g.n_dil; ++cv) {
         const bool second = (cv & 1) != 0;
+        const int hc = g.hc[br];
         L2S_PTRACE(128, ntr);
         mbar_wait(s_full, ps);
         ps ^= 1u;
@@ -600,19 +696,19 @@ respk_tc_kernel(const __grid_constant__ PkMaps maps, const PkParams P) {
         const uint32_t d_base = second ? tmem_base : tmem_base + (uint32_t)acc_cols;   // c2 accumulates onto X, c1 overwrites D1
         constexpr int MS = DUAL ? 1 : 2;
         const uint32_t acc_first = second ? 1u : 0u;
-        if (g.tb == 2 && g.hc == 1)
+        if (g.tb == 2 && hc == 1)
           pk_issue_conv<C, 1, MS, CG2, 2>(leader, desc_hi, desc_lo_fixed, s_lo, half_step, stageB, g.bstage_bytes, g.sb, b_full, b_empty, ib, pb, d_base, acc_first);
-        else if (g.tb == 2 && g.hc == 3)
+        else if (g.tb == 2 && hc == 3)
           pk_issue_conv<C, 3, MS, CG2, 2>(leader, desc_hi, desc_lo_fixed, s_lo, half_step, stageB, g.bstage_bytes, g.sb, b_full, b_empty, ib, pb, d_base, acc_first);
-        else if (g.tb == 2 && g.hc == 5)
+        else if (g.tb == 2 && hc == 5)
           pk_issue_conv<C, 5, MS, CG2, 2>(leader, desc_hi, desc_lo_fixed, s_lo, half_step, stageB, g.bstage_bytes, g.sb, b_full, b_empty, ib, pb, d_base, acc_first);
         else
-          for (int ts = 0; ts < g.n_tstages; ++ts) {
+          for (int ts = 0; ts < g.n_tstages[br]; ++ts) {
             mbar_wait(&b_full[ib], pb);
             tc_fence_after();
             const uint32_t b_lo = desc_lo_fixed | ((smem_u32(stageB + (size_t)ib * g.bstage_bytes) & 0x3FFFFu) >> 4);
-            const int n_g = min(g.tb, g.n_groups - ts * g.tb);
-            pk_issue_stage<C, CG2>(leader, g.msub, g.hc, g.n_off, desc_hi, s_lo, half_step, b_lo, ts * g.tb, n_g, d_base, !second);
+            const int n_g = min(g.tb, g.n_groups[br] - ts * g.tb);
+            pk_issue_stage<C, CG2>(leader, g.msub, hc, g.n_off[br], desc_hi, s_lo, half_step, b_lo, ts * g.tb, n_g, d_base, !second);
             if (leader) commit(&b_empty[ib]);
             if (++ib == g.sb) { ib = 0; pb ^= 1u; }
           }
@@ -652,6 +748,9 @@ respk_tc_kernel(const __grid_constant__ PkMaps maps, const PkParams P) {
       const int t_row0 = q0 - g.hl;                // time step of tile position 0 (multiple of P)
       const int lin = dummy ? 0 : P.lin;
       const bool edge = t_row0 < 0 || t_row0 + g.mt > lin;
+      const int row_lim = dummy ? 0 : min(P.lin, q0 + g.r_out) / PP;
+      for (int br = 0; br < g.n_br; ++br) {
+      const float* sb_br = sbias + br * (2 * kPkMaxDil * 128);
       L2S_PTRACE(0, ntr);
       if (use_tab) pk_load_x_fast<C, MS>(P, w, slab, x_quad, b, t_row0, lin, tab);
       else pk_load_x<C>(P, w, slab, x_quad, b, t_row0, lin);
@@ -665,11 +764,11 @@ respk_tc_kernel(const __grid_constant__ PkMaps maps, const PkParams P) {
         tc_fence_after();
         L2S_PTRACE(0, ntr);
         if (use_tab && !edge) {
-          if (st == 0) pk_phase_fast<C, MS>(w, slab, d1_quad, sbias, tab, 1);
-          else if (st == 1) pk_phase_fast<C, MS>(w, slab, d1_quad, sbias + 2 * 128, tab, 3);
-          else pk_phase_fast<C, MS>(w, slab, d1_quad, sbias + 4 * 128, tab, 5);
-        } else if (edge) pk_phase<C, true>(g, w, slab, d1_quad, sbias + (2 * st) * 128, g.lay[st].d == 1, g.lay[st].d == 1 ? nat : g.lay[st], t_row0, lin);
-        else pk_phase<C, false>(g, w, slab, d1_quad, sbias + (2 * st) * 128, g.lay[st].d == 1, g.lay[st].d == 1 ? nat : g.lay[st], t_row0, lin);
+          if (st == 0) pk_phase_fast<C, MS, DUAL>(w, slab, d1_quad, DUAL ? sb_br : P.bias_ch[br][0], tab, 1);
+          else if (st == 1) pk_phase_fast<C, MS, DUAL>(w, slab, d1_quad, DUAL ? sb_br + 2 * 128 : P.bias_ch[br][2], tab, 3);
+          else pk_phase_fast<C, MS, DUAL>(w, slab, d1_quad, DUAL ? sb_br + 4 * 128 : P.bias_ch[br][4], tab, 5);
+        } else if (edge) pk_phase<C, true>(g, w, slab, d1_quad, sb_br + (2 * st) * 128, g.lay[st].d == 1, g.lay[st].d == 1 ? nat : g.lay[st], t_row0, lin);
+        else pk_phase<C, false>(g, w, slab, d1_quad, sb_br + (2 * st) * 128, g.lay[st].d == 1, g.lay[st].d == 1 ? nat : g.lay[st], t_row0, lin);
         L2S_PTRACE(0, ntr);
         publish();
         if (st + 1 < g.n_dil) {
@@ -679,19 +778,40 @@ respk_tc_kernel(const __grid_constant__ PkMaps maps, const PkParams P) {
           tc_fence_after();
           L2S_PTRACE(0, ntr);
           if (use_tab && !edge) {
-            if (st == 0) pk_phase_fast<C, MS>(w, slab, x_quad, sbias + 1 * 128, tab, 2);
-            else pk_phase_fast<C, MS>(w, slab, x_quad, sbias + 3 * 128, tab, 4);
-          } else if (edge) pk_phase<C, true>(g, w, slab, x_quad, sbias + (2 * st + 1) * 128, true, g.lay[st + 1], t_row0, lin);
-          else pk_phase<C, false>(g, w, slab, x_quad, sbias + (2 * st + 1) * 128, true, g.lay[st + 1], t_row0, lin);
+            if (st == 0) pk_phase_fast<C, MS, DUAL>(w, slab, x_quad, DUAL ? sb_br + 1 * 128 : P.bias_ch[br][1], tab, 2);
+            else pk_phase_fast<C, MS, DUAL>(w, slab, x_quad, DUAL ? sb_br + 3 * 128 : P.bias_ch[br][3], tab, 4);
+          } else if (edge) pk_phase<C, true>(g, w, slab, x_quad, sb_br + (2 * st + 1) * 128, true, g.lay[st + 1], t_row0, lin);
+          else pk_phase<C, false>(g, w, slab, x_quad, sb_br + (2 * st + 1) * 128, true, g.lay[st + 1], t_row0, lin);
           L2S_PTRACE(0, ntr);
           publish();
         }
       }
       // ---- output: X -> global (time steps [q0, q0 + r_out) of the tile only), in block rows of the utterance
-      const int row_lim = dummy ? 0 : min(P.lin, q0 + g.r_out) / PP;
-      pk_output<CW, MODE, !DUAL>(p, tile, x_quad, b, t_row0 / PP, q0 / PP, row_lim, g.msub, w, d_full, pd);
+      if (br + 1 == g.n_br) {
+        if constexpr (DUAL) pk_output<CW, MODE, false>(p, tile, x_quad, b, t_row0 / PP, q0 / PP, row_lim, g.msub, w, d_full, pd);
+        else pk_output_direct<C, MODE>(p, P.bias_ch[br][2 * kPkMaxDil], x_quad, b, t_row0 / PP, q0 / PP, row_lim, g.msub, w, d_full, pd);
+      } else {
+        // a branch that is not the last: its result goes into (br == 0: starts) the fp32 running sum, which this same
+        // thread reads back when the next branch of the tile finishes
+        ConvParams pm = p;
+        pm.bias = P.bias_cols + (size_t)(br * kPkBiasRows + 2 * kPkMaxDil) * 128;
+        pm.out_raw = P.acc_buf;
+        pm.out_act = nullptr;
+        pm.acc_in = br ? P.acc_buf : nullptr;
+        pm.div = 1.0f;
+        if constexpr (DUAL) {
+          if (br == 0) pk_output<CW, kEpiRaw, false>(pm, tile, x_quad, b, t_row0 / PP, q0 / PP, row_lim, g.msub, w, d_full, pd);
+          else pk_output<CW, kEpiAcc | kEpiRaw, false>(pm, tile, x_quad, b, t_row0 / PP, q0 / PP, row_lim, g.msub, w, d_full, pd);
+        } else {
+          if (br == 0) pk_output_direct<C, kEpiRaw>(pm, P.bias_ch[br][2 * kPkMaxDil], x_quad, b, t_row0 / PP, q0 / PP, row_lim, g.msub, w, d_full, pd);
+          else pk_output_direct<C, kEpiAcc | kEpiRaw>(pm, P.bias_ch[br][2 * kPkMaxDil], x_quad, b, t_row0 / PP, q0 / PP, row_lim, g.msub, w, d_full, pd);
+        }
+      }
       pd ^= 1u;
       L2S_PTRACE(0, ntr);
+      tc_fence_before();
+      __syncwarp();
+      }
       tc_fence_before();
       __syncwarp();
     }
@@ -711,6 +831,11 @@ inline int g_pk_on = 1;          // knob pack: 0 = never use the time-packed ker
 inline int g_pk_mode = 0;        // knob pk_mode: 0 auto, 1 two CTAs per SM (msub 1), 2 one CTA per SM (msub 2)
 inline int g_pk_cg2 = 1;         // knob pk_cg2: CTA pairs with cta_group::2 MMAs
 inline int g_pk_single_pct = 80; // planner: weight (percent) of the one-CTA-per-SM plan (no MMA / epilogue overlap inside one CTA)
+inline int g_pk_fuse_br = 1;     // knob pk_fuse: the kernel-size branches of a stage run in ONE launch, back to back on every tile
+inline int g_pk_chan_mask = 32;  // knob pk_chan: channel counts (bit mask 16 | 32 | 64) the planner gives to the time-packed kernel.  Measured on
+                                 // cfg2 (per stage, us): C = 64 tap-by-tap 507 / packed 522, C = 32 378 / 346, C = 16 306 / 328: at two tiles in
+                                 // flight per SM (TMEM) the narrow stages are bound by the MMA <-> epilogue hand-offs, not by MMA time, so the
+                                 // 3x cheaper MMAs pay only where a tile carries enough MMA work per hand-off.
 
 // Block-Toeplitz expansion of one Conv1d weight (Cout, Cin, k) (PyTorch layout) into [n_groups][128][64]:
 // row n = j * C + co, 128-byte row of group g = Q offsets x C input channels, offset oi = g * Q + s holds
@@ -731,15 +856,31 @@ inline void pk_pack_weights(const float* w, int c, int k, std::vector<float>* ou
   }
 }
 
-inline bool pk_plan_with(int c, int k, int n_dil, const int* dil, int lin, int batch, int kind, PkGeom* out) {
+// n_br ResBlocks (kernel sizes ks[]) with the same dilation list run back to back on every tile; the tile geometry is
+// that of the widest halo.
+inline bool pk_plan_with(int c, int n_br, const int* ks, int n_dil, const int* dil, int lin, int batch, int kind, PkGeom* out) {
   PkGeom g{};
-  if ((c != 16 && c != 32 && c != 64) || k < 1 || k > kMaxTaps || (k & 1) == 0 || n_dil < 1 || n_dil > kPkMaxDil) return false;
-  g.c = c; g.k = k; g.n_dil = n_dil; g.hc = (k - 1) / 2;
+  if ((c != 16 && c != 32 && c != 64) || n_br < 1 || n_br > kPkMaxBr || n_dil < 1 || n_dil > kPkMaxDil) return false;
+  g.c = c; g.n_dil = n_dil; g.n_br = n_br;
   g.P = 128 / c; g.Q = g.P / 2;
   if (lin % g.P != 0) return false;                                   // utterance rows must be whole blocks
-  if ((g.hc + g.P - 1) / g.P > kPkPadRows / 2) return false;
-  g.n_off = g.P + k - 1;
-  g.n_groups = (g.n_off + g.Q - 1) / g.Q;
+  int hc_max = 0, max_ts = 0;
+  for (int b = 0; b < n_br; ++b) {
+    const int k = ks[b];
+    if (k < 1 || k > kMaxTaps || (k & 1) == 0) return false;
+    g.k[b] = k;
+    g.hc[b] = (k - 1) / 2;
+    if ((g.hc[b] + g.P - 1) / g.P > kPkPadRows / 2) return false;
+    g.n_off[b] = g.P + k - 1;
+    g.n_groups[b] = (g.n_off[b] + g.Q - 1) / g.Q;
+    if (g.n_groups[b] < 2) return false;
+    if (g.hc[b] > hc_max) hc_max = g.hc[b];
+  }
+  g.tb = 2;
+  for (int b = 0; b < n_br; ++b) {
+    g.n_tstages[b] = (g.n_groups[b] + g.tb - 1) / g.tb;
+    if (g.n_tstages[b] > max_ts) max_ts = g.n_tstages[b];
+  }
   g.dual = kind == 1 ? 1 : 0;
   g.msub = g.dual ? 1 : 2;
   g.nr = 128 * g.msub;
@@ -749,7 +890,7 @@ inline bool pk_plan_with(int c, int k, int n_dil, const int* dil, int lin, int b
     const int d = dil[s];
     if (d < 1 || d > 16) return false;
     g.dil[s] = d;
-    g.h_tot += (d + 1) * g.hc;
+    g.h_tot += (d + 1) * hc_max;
     const int nb = g.nr / d;                                          // blocks per phase
     g.lay[s].d = d;
     g.lay[s].magic = d == 1 ? 0u : (uint32_t)((0x100000000ull + (uint64_t)d - 1) / (uint64_t)d);
@@ -771,28 +912,26 @@ inline bool pk_plan_with(int c, int k, int n_dil, const int* dil, int lin, int b
   g.ctas_per_sm = g.dual ? 2 : 1;
   g.tmem_cols = 2 * g.msub * 128;
   g.cg2 = (g_pk_cg2 && g.total_items >= 2) ? 1 : 0;
-  g.tb = g.n_groups >= 2 ? 2 : 1;
-  g.n_tstages = (g.n_groups + g.tb - 1) / g.tb;
   g.bstage_bytes = g.tb * (g.cg2 ? 64 : 128) * 128;
-  const int fixed = 1024 + 192 + 2 * kPkMaxDil * 128 * 4 + kTcEpiWarps * g.tile_words * 4 + g.s_bytes;   // slack, barriers, biases, tiles, S
-  const int budget = g.dual ? 112 * 1024 : 220 * 1024;
+  const int fixed = 1024 + 192 + kPkMaxBr * 2 * kPkMaxDil * 128 * 4 + kTcEpiWarps * g.tile_words * 4 + g.s_bytes;   // slack, barriers, constants, tiles, S
+  const int budget = g.dual ? 113 * 1024 : 220 * 1024;
   int sb = 2;
   if (fixed + sb * g.bstage_bytes > budget) return false;
-  while (sb < kTcMaxStagesB && sb < 2 * g.n_tstages && fixed + (sb + 1) * g.bstage_bytes <= budget && (sb + 1) * g.bstage_bytes <= 96 * 1024) ++sb;
+  while (sb < kTcMaxStagesB && sb < 2 * max_ts && fixed + (sb + 1) * g.bstage_bytes <= budget && (sb + 1) * g.bstage_bytes <= 96 * 1024) ++sb;
   g.sb = sb;
   g.smem_bytes = fixed + sb * g.bstage_bytes;
   *out = g;
   return true;
 }
 
-inline bool pk_plan(int c, int k, int n_dil, const int* dil, int lin, int batch, PkGeom* out) {
-  if (!g_pk_on) return false;
+inline bool pk_plan(int c, int n_br, const int* ks, int n_dil, const int* dil, int lin, int batch, PkGeom* out) {
+  if (!g_pk_on || !(g_pk_chan_mask & c)) return false;
   PkGeom best{};
   double best_score = 0.0;
   for (int kind = 1; kind >= 0; --kind) {
     if ((g_pk_mode == 1 && kind != 1) || (g_pk_mode == 2 && kind != 0)) continue;
     PkGeom g;
-    if (!pk_plan_with(c, k, n_dil, dil, lin, batch, kind, &g)) continue;
+    if (!pk_plan_with(c, n_br, ks, n_dil, dil, lin, batch, kind, &g)) continue;
     const int covered = g.m_items * g.r_out;
     const double score = (double)g.r_out / g.mt * ((double)lin / covered) * (kind == 1 ? 1.0 : 0.01 * g_pk_single_pct);
     if (score > best_score) { best_score = score; best = g; }

@@ -113,7 +113,9 @@ struct l2s_vocoder {
   std::vector<std::vector<std::vector<int>>> rb_c1, rb_c2;  // [stage][branch][dil]
   std::vector<int> stage_ch;
   float* d_zero_bias = nullptr;                // 256 zeros: output epilogue of the whole-ResBlock kernel
-  std::vector<std::vector<float*>> pk_bias;    // [stage][branch]: [2 n_dil + 1][128] per-column constants of the time-packed kernel
+  std::vector<std::vector<float*>> pk_bias;    // [stage][branch]: [kPkBiasRows][128] per-column constants of the time-packed kernel
+  std::vector<float*> pk_bias_stage;           // [stage]: the same for all branches back to back, [n_rk][kPkBiasRows][128]
+  std::vector<std::vector<std::vector<float>>> pk_bias_host;   // [stage][branch]: [kPkBiasRows][64] per-channel copy handed to the kernel by value
   bool finalized = false;
   int device = -1, num_sms = 0;
   // device-side small weights
@@ -488,19 +490,31 @@ bool branch_geom(const l2s_vocoder* v, int i, int j, int lin, int batch, ResGeom
   return res_plan(a.cin, a.k, c.n_dil, dil, lin, batch, (int)g_knobs.res_mode, (int)g_knobs.res_msub, g);
 }
 
-// Time-packed plan of ResBlock (i, j), if there is one (respk_tc.cuh).
-bool branch_pk_geom(const l2s_vocoder* v, int i, int j, int lin, int batch, PkGeom* g) {
+// Time-packed plan of branches [j0, j0 + n_br) of stage i, if there is one (respk_tc.cuh).
+bool branch_pk_geom(const l2s_vocoder* v, int i, int j0, int n_br, int lin, int batch, PkGeom* g) {
   const l2s_config& c = v->cfg;
-  const ConvLayer& a = v->convs[v->rb_c1[i][j][0]];
-  int dil[kPkMaxDil];
-  if (c.n_dil > kPkMaxDil || a.cin != a.cout || a.cin_pad != a.cin || !a.wpk_dev || !v->pk_bias[i][j]) return false;
-  for (int m = 0; m < c.n_dil; ++m) {
-    const ConvLayer& a1 = v->convs[v->rb_c1[i][j][m]];
-    const ConvLayer& a2 = v->convs[v->rb_c2[i][j][m]];
-    if (a1.k != a.k || a2.k != a.k || a2.dil != 1 || !a1.wpk_dev || !a2.wpk_dev) return false;
-    dil[m] = a1.dil;
+  int dil[kPkMaxDil], ks[kPkMaxBr];
+  if (c.n_dil > kPkMaxDil || n_br < 1 || n_br > kPkMaxBr) return false;
+  const int ch = v->stage_ch[i];
+  for (int j = j0; j < j0 + n_br; ++j) {
+    const ConvLayer& a = v->convs[v->rb_c1[i][j][0]];
+    if (a.cin != a.cout || a.cin_pad != a.cin || a.cin != ch || !v->pk_bias[i][j]) return false;
+    ks[j - j0] = a.k;
+    for (int m = 0; m < c.n_dil; ++m) {
+      const ConvLayer& a1 = v->convs[v->rb_c1[i][j][m]];
+      const ConvLayer& a2 = v->convs[v->rb_c2[i][j][m]];
+      if (a1.k != a.k || a2.k != a.k || a2.dil != 1 || !a1.wpk_dev || !a2.wpk_dev) return false;
+      if (j == j0) dil[m] = a1.dil;
+      else if (dil[m] != a1.dil) return false;              // fused branches share the phase-major layouts
+    }
   }
-  return pk_plan(a.cin, a.k, c.n_dil, dil, lin, batch, g);
+  return pk_plan(ch, n_br, ks, c.n_dil, dil, lin, batch, g);
+}
+
+// All branches of stage i in one time-packed launch?
+bool stage_pk_fused(const l2s_vocoder* v, int i, int lin, int batch, PkGeom* g) {
+  return g_pk_fuse_br && v->cfg.n_rk >= 2 && v->cfg.n_rk <= kPkMaxBr && v->pk_bias_stage[i] &&
+         branch_pk_geom(v, i, 0, v->cfg.n_rk, lin, batch, g);
 }
 
 // Every ResBlock of stage i runs as one whole-ResBlock kernel (bf16 mode, C <= 64, a plan exists for each branch).
@@ -509,45 +523,50 @@ bool stage_branch_fused(const l2s_vocoder* v, int i, int lin, int batch) {
   for (int j = 0; j < v->cfg.n_rk; ++j) {
     ResGeom g;
     PkGeom pg;
-    if (!branch_pk_geom(v, i, j, lin, batch, &pg) && !branch_geom(v, i, j, lin, batch, &g)) return false;
+    if (!branch_pk_geom(v, i, j, 1, lin, batch, &pg) && !branch_geom(v, i, j, lin, batch, &g)) return false;
   }
   return true;
 }
 
-// One whole ResBlock through the time-packed kernel.  L2S_ERR_UNSUPPORTED: no packed plan (the caller runs run_res).
-int run_respk(l2s_vocoder* v, int i, int j, cudaStream_t st, int batch, int lin, const float* x, float* out_raw, void* out_act,
-              const float* acc_in, float div, float slope) {
+// Branches [j0, j0 + n_br) of stage i through the time-packed kernel (n_br > 1: one launch, the branches run back to back
+// on every tile and the running branch sum goes through acc_buf).  out_raw / out_act / acc_in / div describe the output
+// of the LAST branch.  L2S_ERR_UNSUPPORTED: no packed plan (the caller runs the tap-by-tap kernel per branch).
+int run_respk(l2s_vocoder* v, int i, int j0, int n_br, cudaStream_t st, int batch, int lin, const float* x, float* out_raw, void* out_act,
+              const float* acc_in, float* acc_buf, float div, float slope) {
   const l2s_config& c = v->cfg;
   PkParams P{};
-  if (!branch_pk_geom(v, i, j, lin, batch, &P.g)) return L2S_ERR_UNSUPPORTED;
+  if (!branch_pk_geom(v, i, j0, n_br, lin, batch, &P.g)) return L2S_ERR_UNSUPPORTED;
   if (!pk_mode_supported(((acc_in || div != 1.0f) ? kEpiAcc : 0) | (out_raw ? kEpiRaw : 0) | (out_act ? kEpiAct : 0))) return L2S_ERR_UNSUPPORTED;
+  if (n_br > 1 && (j0 != 0 || !v->pk_bias_stage[i] || !acc_buf)) return L2S_ERR_UNSUPPORTED;
   const PkGeom& g = P.g;
   PkMaps maps;
   double flops = 0.0;
   const int w_rows = g.cg2 ? 64 : 128;
-  for (int m = 0; m < c.n_dil; ++m) {
-    for (int which = 0; which < 2; ++which) {
-      ConvLayer& L = v->convs[which ? v->rb_c2[i][j][m] : v->rb_c1[i][j][m]];
-      if (L.tmpk_rows != w_rows || L.tmpk_tb != g.tb) {
-        if (!make_tmap_bf16_3d(&L.tmWpk, L.wpk_dev, 64u, 128u, (uint64_t)L.pk_groups, 64u, (uint32_t)w_rows, (uint32_t)g.tb))
-          return fail(v, L2S_ERR_CUDA, "cuTensorMapEncodeTiled failed for the packed weights of " + L.name);
-        L.tmpk_rows = w_rows;
-        L.tmpk_tb = g.tb;
+  for (int br = 0; br < n_br; ++br)
+    for (int m = 0; m < c.n_dil; ++m)
+      for (int which = 0; which < 2; ++which) {
+        ConvLayer& L = v->convs[which ? v->rb_c2[i][j0 + br][m] : v->rb_c1[i][j0 + br][m]];
+        if (L.tmpk_rows != w_rows || L.tmpk_tb != g.tb) {
+          if (!make_tmap_bf16_3d(&L.tmWpk, L.wpk_dev, 64u, 128u, (uint64_t)L.pk_groups, 64u, (uint32_t)w_rows, (uint32_t)g.tb))
+            return fail(v, L2S_ERR_CUDA, "cuTensorMapEncodeTiled failed for the packed weights of " + L.name);
+          L.tmpk_rows = w_rows;
+          L.tmpk_tb = g.tb;
+        }
+        maps.w[br * 2 * kPkMaxDil + 2 * m + which] = L.tmWpk;
+        flops += 2.0 * L.cin * L.cout * L.k * (double)batch * lin;
       }
-      maps.w[2 * m + which] = L.tmWpk;
-      flops += 2.0 * L.cin * L.cout * L.k * (double)batch * lin;
-    }
-  }
-  for (int m = 2 * c.n_dil; m < 2 * kPkMaxDil; ++m) maps.w[m] = maps.w[0];
+  for (int m = 0; m < kPkMaxBr * 2 * kPkMaxDil; ++m)
+    if (m / (2 * kPkMaxDil) >= n_br || m % (2 * kPkMaxDil) >= 2 * c.n_dil) maps.w[m] = maps.w[0];
+  const float* cols = n_br > 1 ? v->pk_bias_stage[i] : v->pk_bias[i][j0];      // [n_br][kPkBiasRows][128]
   ConvParams& p = P.c;                        // output epilogue in packed terms: rows = blocks of P time steps, 128 columns
-  p.bias = v->pk_bias[i][j] + (size_t)(2 * c.n_dil) * 128;
+  p.bias = cols + (size_t)((n_br - 1) * kPkBiasRows + 2 * kPkMaxDil) * 128;
   p.out_raw = out_raw;
   p.out_act = out_act;
-  p.acc_in = acc_in;
+  p.acc_in = n_br > 1 ? acc_buf : acc_in;
   p.batch = batch;
   p.lin = lin / g.P;
   p.cin_pad = 128;
-  p.ntaps = g.k;
+  p.ntaps = 1;
   p.ntot = 128;
   p.mrows = lin / g.P;
   p.out_shift = 0;
@@ -555,14 +574,16 @@ int run_respk(l2s_vocoder* v, int i, int j, cudaStream_t st, int batch, int lin,
   p.div = div;
   p.slope = slope;
   P.x = x;
-  P.bias_cols = v->pk_bias[i][j];
+  P.bias_cols = cols;
+  P.acc_buf = acc_buf;
+  for (int br = 0; br < n_br; ++br) memcpy(P.bias_ch[br], v->pk_bias_host[i][j0 + br].data(), sizeof(P.bias_ch[br]));
   P.lin = lin;
   P.span = g_knobs.span_ptr ? reinterpret_cast<unsigned long long*>(g_knobs.span_ptr) + 2 * v->tc_launches : nullptr;
   ++v->tc_launches;
   P.trace = (g_knobs.trace_ptr && g_knobs.trace_launch == v->res_launches) ? reinterpret_cast<long long*>(g_knobs.trace_ptr) : nullptr;
   ++v->res_launches;
-  const std::string nm = v->convs[v->rb_c1[i][j][0]].name;
-  timed_begin(v, st, nm.substr(0, nm.find(".convs1")) + " (packed)", flops);
+  const std::string nm = v->convs[v->rb_c1[i][j0][0]].name;
+  timed_begin(v, st, nm.substr(0, nm.find(".convs1")) + (n_br > 1 ? " (packed x" + std::to_string(n_br) + ")" : " (packed)"), flops);
   const int ctas = g_knobs.max_ctas > 0 ? (int)g_knobs.max_ctas : v->num_sms;
   cudaError_t e = launch_respk_tc(P, maps, ctas, st);
   timed_end(v, st);
@@ -697,7 +718,16 @@ int run_chain(l2s_vocoder* v, cudaStream_t st, const Workspace& ws, int batch, i
     // output, so fused stages ping-pong the activated buffers (xa -> ya -> ta -> ...); the fp32
     // residual is updated in place (each element is read and written by the same thread).
     if (whole) {
-      for (int j = 0; j < c.n_rk; ++j) {
+      PkGeom fg;
+      bool done = false;
+      if (stage_pk_fused(v, i, (int)len, batch, &fg)) {
+        // every kernel-size branch of the stage in ONE launch: the branches run back to back on each tile
+        rc = run_respk(v, i, 0, c.n_rk, st, batch, (int)len, ws.x, want_raw ? ws.acc : nullptr, last_stage ? nullptr : ws.ma[cur ^ 1],
+                       nullptr, ws.acc, (float)c.n_rk, 0.1f);
+        if (rc == L2S_OK) done = true;
+        else if (rc != L2S_ERR_UNSUPPORTED) return rc;
+      }
+      for (int j = 0; !done && j < c.n_rk; ++j) {
         float* o_raw;
         void* o_act = nullptr;
         const float* a_in = nullptr;
@@ -709,7 +739,7 @@ int run_chain(l2s_vocoder* v, cudaStream_t st, const Workspace& ws, int batch, i
           a_in = c.n_rk == 1 ? nullptr : ws.acc;
           dv = (float)c.n_rk;
         }
-        rc = run_respk(v, i, j, st, batch, (int)len, ws.x, o_raw, o_act, a_in, dv, 0.1f);
+        rc = run_respk(v, i, j, 1, st, batch, (int)len, ws.x, o_raw, o_act, a_in, nullptr, dv, 0.1f);
         if (rc == L2S_ERR_UNSUPPORTED) rc = run_res(v, i, j, st, batch, (int)len, ws.x, o_raw, o_act, a_in, dv, 0.1f);
         if (rc == L2S_ERR_UNSUPPORTED) return fail(v, L2S_ERR_STATE, "whole-ResBlock plan vanished");
         if (rc) return rc;
@@ -1019,11 +1049,14 @@ int l2s_finalize(l2s_vocoder* v, int device) {
   }
   // time-packed whole-ResBlock kernel: block-Toeplitz weights and per-column bias constants of the C <= 64 stages
   v->pk_bias.assign((size_t)c.n_ups, std::vector<float*>((size_t)c.n_rk, nullptr));
-  for (int i = 0; bf && i < c.n_ups; ++i) {
+  v->pk_bias_stage.assign((size_t)c.n_ups, nullptr);
+  v->pk_bias_host.assign((size_t)c.n_ups, std::vector<std::vector<float>>((size_t)c.n_rk));
+  for (int i = 0; bf && i < c.n_ups && c.n_dil <= kPkMaxDil; ++i) {
     const int ch = v->stage_ch[i];
     if (ch != 16 && ch != 32 && ch != 64) continue;
+    std::vector<float> stage_cols;
     for (int j = 0; j < c.n_rk; ++j) {
-      std::vector<float> cols((size_t)(2 * c.n_dil + 1) * 128, 0.f), run((size_t)ch, 0.f);
+      std::vector<float> cols((size_t)kPkBiasRows * 128, 0.f), run((size_t)ch, 0.f);
       for (int m = 0; m < c.n_dil; ++m) {
         for (int which = 0; which < 2; ++which) {
           ConvLayer& L = v->convs[which ? v->rb_c2[i][j][m] : v->rb_c1[i][j][m]];
@@ -1039,10 +1072,17 @@ int l2s_finalize(l2s_vocoder* v, int device) {
           for (int col = 0; col < 128; ++col) cols[(size_t)(2 * m + which) * 128 + col] = which ? run[col % ch] : b[col % ch];
         }
       }
-      for (int col = 0; col < 128; ++col) cols[(size_t)(2 * c.n_dil) * 128 + col] = run[col % ch];   // output epilogue: all c2 biases
+      for (int col = 0; col < 128; ++col) cols[(size_t)(2 * kPkMaxDil) * 128 + col] = run[col % ch];   // output epilogue: all c2 biases
       v->pk_bias[i][j] = dev_upload<float>(v, cols.data(), cols.size(), &e);
       if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, cudaGetErrorString(e));
+      stage_cols.insert(stage_cols.end(), cols.begin(), cols.end());
+      std::vector<float>& hb = v->pk_bias_host[i][j];
+      hb.assign((size_t)kPkBiasRows * 64, 0.f);
+      for (int row = 0; row < kPkBiasRows; ++row)
+        for (int q = 0; q < ch; ++q) hb[(size_t)row * 64 + q] = cols[(size_t)row * 128 + q];
     }
+    v->pk_bias_stage[i] = dev_upload<float>(v, stage_cols.data(), stage_cols.size(), &e);
+    if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, cudaGetErrorString(e));
   }
   {
     const std::vector<float>& d = v->weights["dict.weight"];
@@ -1153,7 +1193,11 @@ int32_t l2s_launch_count(l2s_vocoder* v, int32_t batch, int32_t frames) {
   long long len = frames;
   for (int i = 0; i < c.n_ups; ++i) {
     len *= c.up_rates[i];
-    if (batch > 0 && frames > 0 && stage_branch_fused(v, i, (int)len, batch)) n -= c.n_rk * (c.n_dil - 1);   // one per ResBlock
+    if (batch > 0 && frames > 0 && stage_branch_fused(v, i, (int)len, batch)) {
+      n -= c.n_rk * (c.n_dil - 1);   // one per ResBlock
+      PkGeom fg;
+      if (stage_pk_fused(v, i, (int)len, batch, &fg)) n -= c.n_rk - 1;   // one per stage
+    }
   }
   if (c.variant == L2S_VARIANT_MULTI_INPUT && c.multispkr) n += 1;
   return n;
@@ -1270,6 +1314,8 @@ int l2s_debug_set(const char* key, int64_t value) {
   else if (k == "pk_mode") g_pk_mode = (int)value;
   else if (k == "pk_cg2") g_pk_cg2 = (int)value;
   else if (k == "pk_single_pct") g_pk_single_pct = (int)value;
+  else if (k == "pk_fuse") g_pk_fuse_br = (int)value;
+  else if (k == "pk_chan") g_pk_chan_mask = (int)value;
   else if (k == "cluster") g_knobs.cluster = value;
   else if (k == "alias_at") g_knobs.alias_at = value;
   else if (k == "epi_tma") g_knobs.epi_tma = value;

@@ -276,7 +276,7 @@ def test_whole_resblock_kernels_match_steps(pkg, weights, frames):
         lib.l2s_debug_set(b"stop_after_stage", -1)
         lib.l2s_debug_set(b"fuse_branch", 1)
         y = g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV)).cpu()
-        assert g.launch_count(2, frames, DEV) == 36
+        assert g.launch_count(2, frames, DEV) == 34
     finally:
         lib.l2s_debug_set(b"stop_after_stage", -1)
         lib.l2s_debug_set(b"fuse_branch", 1)
@@ -308,23 +308,27 @@ def test_whole_resblock_tilings_agree(pkg, weights, knob, value):
     assert torch.equal(a, b), float((a - b).abs().max())
 
 
-@pytest.mark.parametrize("knob,value", [("pk_mode", 1), ("pk_mode", 2), ("pk_cg2", 0)])
+@pytest.mark.parametrize("knob,value", [("pk_mode", 1), ("pk_mode", 2), ("pk_cg2", 0), ("pk_fuse", 0)])
 @pytest.mark.parametrize("batch,frames", [(3, 150), (1, 34)])
 def test_packed_resblock_variants_agree(pkg, weights, knob, value, batch, frames):
     """Time-packed whole-ResBlock kernel (respk_tc.cuh): tile size / CTAs per SM (pk_mode) and CTA pairs (pk_cg2) change
     where an output element sits in a tile and which phase-major block holds it, not its arithmetic (the same offset
-    MMAs in the same order): the waveform must not change by a bit."""
+    MMAs in the same order); running the three kernel-size branches of a stage in one launch (pk_fuse) or in three
+    changes only where the running branch sum waits: the waveform must not change by a bit."""
     h, sds = weights
     code, mel, spkr = vo.synthetic_inputs(batch, frames, seed=33)
     g = make_gen(pkg, h, sds["trained"], "bf16")
     lib = pkg._cabi.load()
     try:
+        lib.l2s_debug_set(b"pk_chan", 16 | 32 | 64)     # the time-packed kernel on every narrow stage
         a = g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV)).clone()
         lib.l2s_debug_set(knob.encode(), value)
         b = g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV)).clone()
     finally:
+        lib.l2s_debug_set(b"pk_chan", 32)
         lib.l2s_debug_set(b"pk_mode", 0)
         lib.l2s_debug_set(b"pk_cg2", 1)
+        lib.l2s_debug_set(b"pk_fuse", 1)
     assert torch.isfinite(a).all()
     assert torch.equal(a, b), float((a - b).abs().max())
 
@@ -341,6 +345,7 @@ def test_packed_vs_tap_by_tap_whole_resblock(pkg, weights, batch, frames):
     chans, rates = [256, 128, 64, 32, 16], [5, 20, 40, 80, 160]
     outs = []
     try:
+        lib.l2s_debug_set(b"pk_chan", 16 | 32 | 64)
         for stage in (2, 3, 4):
             taps = []
             for pack in (0, 1):
@@ -359,6 +364,7 @@ def test_packed_vs_tap_by_tap_whole_resblock(pkg, weights, batch, frames):
     finally:
         lib.l2s_debug_set(b"stop_after_stage", -1)
         lib.l2s_debug_set(b"pack", 1)
+        lib.l2s_debug_set(b"pk_chan", 32)
     ref = vo.mel_code_generator_forward(vo.fold_weight_norm(sds["trained"]), h, code, mel, spkr)
     check(ref, outs[0], "bf16", f"tap-by-tap whole-ResBlock {batch}x{frames}")
     check(ref, outs[1], "bf16", f"time-packed whole-ResBlock {batch}x{frames}")
@@ -518,10 +524,14 @@ def test_odd_shapes_whole_resblock_vs_steps(pkg, weights, batch, frames):
         for fb in (0, 1):
             lib.l2s_debug_set(b"fuse_branch", fb)
             outs.append(g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV)).cpu())
+        lib.l2s_debug_set(b"pk_chan", 16 | 32 | 64)     # and with the time-packed kernel on every narrow stage
+        outs.append(g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV)).cpu())
     finally:
         lib.l2s_debug_set(b"fuse_branch", 1)
-    assert torch.isfinite(outs[1]).all()
+        lib.l2s_debug_set(b"pk_chan", 32)
+    assert torch.isfinite(outs[1]).all() and torch.isfinite(outs[2]).all()
     assert vo.snr_db(outs[0], outs[1]) >= 40.0, vo.snr_db(outs[0], outs[1])
+    assert vo.snr_db(outs[0], outs[2]) >= 40.0, vo.snr_db(outs[0], outs[2])
     if frames <= 600:
         ref = vo.mel_code_generator_forward(vo.fold_weight_norm(sds["trained"]), h, code, mel, spkr)
         check(ref, outs[1], "bf16", f"odd shape {batch}x{frames}")

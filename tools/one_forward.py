@@ -12,6 +12,9 @@ from oracle import vocoder_oracle as vo  # noqa: E402  (weights + synthetic inpu
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 pkg = ge.load_package()
+for kv in sys.argv[2:]:                      # debug knobs k=v (tools only)
+    k, v = kv.split("=")
+    assert pkg._cabi.load().l2s_debug_set(k.encode(), int(v)) == 0, kv
 dev = torch.device("cuda:0")
 h = vo.shipped_config()
 g = pkg.MelCodeGenerator(pkg.AttrDict(h))
