@@ -107,11 +107,13 @@ int32_t l2s_hop(l2s_vocoder* v);
 
 /* Replaces MelCodeGenerator.forward(**kwargs) / CodeGenerator.forward(**kwargs).
  *   code  int64 (B,U) device
- *   mel   (B,num_mels,T) device, dtype mel_dtype (L2S_F32 / L2S_F16); NULL for unit-only
+ *   mel   (B,num_mels,T) device, dtype mel_dtype (L2S_F32 / L2S_F16 / L2S_BF16); NULL for unit-only
  *   spkr  float32 (B,spk_dim) device, or int64 (B) speaker ids when spk_dim == 0
  *   out   float32 (B,1,hop*T) device
  * Launches on `stream` (a cudaStream_t); does not synchronise.  Out-of-range
- * ids are clamped on the device and reported by l2s_poll_index_error. */
+ * ids are clamped on the device and recorded in a sticky flag: the NEXT l2s_forward on this handle (or
+ * l2s_poll_index_error) returns L2S_ERR_INDEX -- late rather than never, without a device synchronisation.
+ * Thread safety: calls on one handle are serialised by the handle; different handles run concurrently. */
 int l2s_forward(l2s_vocoder* v, void* stream, const int64_t* code, const void* mel, int32_t mel_dtype,
                 const void* spkr, int32_t batch, int32_t units, int32_t frames, float* out,
                 void* workspace, int64_t workspace_bytes);
@@ -124,8 +126,9 @@ int l2s_forward_i16(l2s_vocoder* v, void* stream, const int64_t* code, const voi
                     int16_t* out_i16, void* workspace, int64_t workspace_bytes);
 
 /* Reads (and clears) the sticky out-of-range-id flag the front-end kernel sets.
- * The flag lives in host-mapped memory; call after the stream has been
- * synchronised.  Returns L2S_ERR_INDEX if an id was out of range since the last poll. */
+ * The flag lives in host-mapped memory, so this never synchronises: after the stream has been synchronised it
+ * covers every forward issued so far, otherwise those that have already run.  Returns L2S_ERR_INDEX if an id was
+ * out of range since the last poll. */
 int l2s_poll_index_error(l2s_vocoder* v);
 
 /* Number of kernels l2s_forward launches for this batch shape (for bench accounting). */
@@ -133,47 +136,6 @@ int32_t l2s_launch_count(l2s_vocoder* v, int32_t batch, int32_t frames);
 
 const char* l2s_last_error(l2s_vocoder* v);
 const char* l2s_version(void);
-
-/* ---- test hooks (used by tests/ only) ---------------------------------- */
-
-/* Copy an intermediate buffer of the most recent forward to the host as fp32.
- * Names: "cond", "embed" (needs knob embed_tap), "conv_pre_act", and -- when the
- * forward was stopped with knob stop_after_stage = i -- "ups" (ups[i] output) and
- * "mrf" (stage i MRF mean).  Channels-last (B, L, C).  Synchronises. */
-int l2s_debug_tap(l2s_vocoder* v, const char* name, float* host_dst, int64_t numel);
-
-/* Run ONE generic tap-offset convolution (the building block every layer maps
- * onto) on caller-provided device buffers.  impl: 0 = CUDA-core kernel,
- * 1 = tcgen05 kernel (halo slab + row-shifted shared-memory descriptors),
- * 2 = retired probe (descriptor base-offset field filled in: measured WRONG on sm_100a,
- *     row-shifted descriptors need base_offset = 0),
- * 3 = one TMA-loaded A tile per tap, no row-shifted descriptors (probe / fallback).
- * `scale` is the divisor applied in the epilogue.  See csrc/conv_common.cuh. */
-typedef struct l2s_conv_desc {
-  const void* in;        /* [B][lin][cin_pad] channels-last, fp32 or bf16                */
-  const void* w;         /* [ntaps][ntot][cin_pad] same dtype                            */
-  const float* bias;     /* [ntot]                                                       */
-  float* out_raw;        /* fp32, flat per-utterance index, may be NULL                  */
-  void* out_act;         /* leaky-relu'd copy in the activation dtype, may be NULL       */
-  const float* res;      /* fp32 residual, same indexing as out, may be NULL             */
-  const float* acc_in;   /* fp32 running branch sum, may be NULL                         */
-  int32_t act_bf16;      /* 1: in / w / out_act are bf16, 0: fp32                         */
-  int32_t batch, lin, cin_pad, ntaps, ntot, mrows;
-  int32_t tap_off[16];
-  int64_t out_shift, out_valid;
-  float scale, slope;
-} l2s_conv_desc;
-int l2s_debug_conv(const l2s_conv_desc* d, int32_t impl, int32_t device, void* stream, char* err, int32_t err_len);
-
-/* With knob layer_events = 1 every launch of a forward is bracketed by a CUDA event
- * pair; this reads launch `idx` of the most recent forward (ms, algorithmic flops,
- * layer name).  L2S_ERR_INVALID past the last launch.  Synchronises on the event. */
-int l2s_debug_layer_time(l2s_vocoder* v, int32_t idx, float* ms, double* flops, char* name, int32_t name_len);
-
-/* Override a tuning / descriptor knob (tests and probes only): force_simt,
- * stop_after_stage, stop_after_pre, per_tap, sa_min, dual, cluster, alias_at, epi_tma, pdl, use_graph, fuse_pairs, trace_launch, span_ptr, plan_report, trace_ptr, max_msub, slab_cap, max_ctas,
- * embed_tap, layer_events. */
-int l2s_debug_set(const char* key, int64_t value);
 
 #ifdef __cplusplus
 }

@@ -9,10 +9,12 @@
 
 #include <map>
 #include <mutex>
+#include <shared_mutex>
 #include <string>
 #include <vector>
 
 #include "../../include/l2s_vocoder.h"
+#include "../../include/l2s_debug.h"
 #include "conv_common.cuh"
 #include "conv_simt.cuh"
 #include "conv_tc.cuh"
@@ -62,6 +64,7 @@ struct Knobs {
   long long layer_events = 0;      // record a cudaEvent pair around every launch of the next forwards
 };
 Knobs g_knobs;
+std::shared_mutex g_knob_mu;   // forwards hold it shared, l2s_debug_set exclusively: a knob never changes under a running forward
 
 inline uint16_t f2bf(float f) {  // round to nearest even
   uint32_t u;
@@ -115,6 +118,7 @@ struct l2s_vocoder {
   float* d_zero_bias = nullptr;                // 256 zeros: output epilogue of the whole-ResBlock kernel
   std::vector<std::vector<float*>> pk_bias;    // [stage][branch]: [kPkBiasRows][128] per-column constants of the time-packed kernel
   std::vector<float*> pk_bias_stage;           // [stage]: the same for all branches back to back, [n_rk][kPkBiasRows][128]
+  std::vector<char> pk_ok;                     // [stage]: config-only: the time-packed kernel can run this stage (set by l2s_create)
   std::vector<std::vector<std::vector<float>>> pk_bias_host;   // [stage][branch]: [kPkBiasRows][64] per-channel copy handed to the kernel by value
   bool finalized = false;
   int device = -1, num_sms = 0;
@@ -215,6 +219,7 @@ int build_layers(l2s_vocoder* v) {
   int ch = c.up_init_ch;
   if (ch % 16 != 0) return fail(v, L2S_ERR_UNSUPPORTED, "upsample_initial_channel must be a multiple of 16");
   v->convs.clear();
+  v->pk_ok.clear();
   v->convs.push_back(make_conv("conv_pre", in_dim, ch, 7, 1));
   v->conv_pre = 0;
   v->expected["conv_pre.weight"] = (long long)ch * in_dim * 7;
@@ -232,6 +237,7 @@ int build_layers(l2s_vocoder* v) {
     v->expected[std::string(nm) + ".bias"] = ch / 2;
     ch /= 2;
     v->stage_ch.push_back(ch);
+    v->pk_ok.push_back(c.precision == L2S_PREC_BF16 && c.n_dil <= kPkMaxDil && (ch == 16 || ch == 32 || ch == 64) ? 1 : 0);
     std::vector<std::vector<int>> s1, s2;
     for (int j = 0; j < c.n_rk; ++j) {
       const int rk = c.rk_sizes[j];
@@ -360,7 +366,8 @@ int run_conv(l2s_vocoder* v, ConvLayer& L, cudaStream_t st, int batch, int lin, 
   p.cin_pad = L.cin_pad;
   p.ntaps = L.ntaps;
   p.ntot = L.ntot;
-  p.mrows = L.transposed ? lin + 1 : lin;
+  // polyphase ConvTranspose1d: output n = q u + r - p; the last output (n = lin u - 1, r = 0) sits in row q = lin + ceil(p / u) - 1
+  p.mrows = L.transposed ? lin + (L.pad + L.up - 1) / L.up : lin;
   for (int j = 0; j < L.ntaps; ++j) p.tap_off[j] = L.tap_off[j];
   p.out_shift = L.out_shift;
   p.out_valid = (long long)lin * L.up * L.cout;
@@ -494,16 +501,16 @@ bool branch_geom(const l2s_vocoder* v, int i, int j, int lin, int batch, ResGeom
 bool branch_pk_geom(const l2s_vocoder* v, int i, int j0, int n_br, int lin, int batch, PkGeom* g) {
   const l2s_config& c = v->cfg;
   int dil[kPkMaxDil], ks[kPkMaxBr];
-  if (c.n_dil > kPkMaxDil || n_br < 1 || n_br > kPkMaxBr) return false;
+  if (c.n_dil > kPkMaxDil || n_br < 1 || n_br > kPkMaxBr || !v->pk_ok[i]) return false;
   const int ch = v->stage_ch[i];
   for (int j = j0; j < j0 + n_br; ++j) {
     const ConvLayer& a = v->convs[v->rb_c1[i][j][0]];
-    if (a.cin != a.cout || a.cin_pad != a.cin || a.cin != ch || !v->pk_bias[i][j]) return false;
+    if (a.cin != a.cout || a.cin_pad != a.cin || a.cin != ch) return false;
     ks[j - j0] = a.k;
     for (int m = 0; m < c.n_dil; ++m) {
       const ConvLayer& a1 = v->convs[v->rb_c1[i][j][m]];
       const ConvLayer& a2 = v->convs[v->rb_c2[i][j][m]];
-      if (a1.k != a.k || a2.k != a.k || a2.dil != 1 || !a1.wpk_dev || !a2.wpk_dev) return false;
+      if (a1.k != a.k || a2.k != a.k || a2.dil != 1) return false;
       if (j == j0) dil[m] = a1.dil;
       else if (dil[m] != a1.dil) return false;              // fused branches share the phase-major layouts
     }
@@ -513,8 +520,7 @@ bool branch_pk_geom(const l2s_vocoder* v, int i, int j0, int n_br, int lin, int 
 
 // All branches of stage i in one time-packed launch?
 bool stage_pk_fused(const l2s_vocoder* v, int i, int lin, int batch, PkGeom* g) {
-  return g_pk_fuse_br && v->cfg.n_rk >= 2 && v->cfg.n_rk <= kPkMaxBr && v->pk_bias_stage[i] &&
-         branch_pk_geom(v, i, 0, v->cfg.n_rk, lin, batch, g);
+  return g_pk_fuse_br && v->cfg.n_rk >= 2 && v->cfg.n_rk <= kPkMaxBr && branch_pk_geom(v, i, 0, v->cfg.n_rk, lin, batch, g);
 }
 
 // Every ResBlock of stage i runs as one whole-ResBlock kernel (bf16 mode, C <= 64, a plan exists for each branch).
@@ -537,7 +543,7 @@ int run_respk(l2s_vocoder* v, int i, int j0, int n_br, cudaStream_t st, int batc
   PkParams P{};
   if (!branch_pk_geom(v, i, j0, n_br, lin, batch, &P.g)) return L2S_ERR_UNSUPPORTED;
   if (!pk_mode_supported(((acc_in || div != 1.0f) ? kEpiAcc : 0) | (out_raw ? kEpiRaw : 0) | (out_act ? kEpiAct : 0))) return L2S_ERR_UNSUPPORTED;
-  if (n_br > 1 && (j0 != 0 || !v->pk_bias_stage[i] || !acc_buf)) return L2S_ERR_UNSUPPORTED;
+  if (!v->finalized || !v->pk_bias[i][j0] || (n_br > 1 && (j0 != 0 || !v->pk_bias_stage[i] || !acc_buf))) return L2S_ERR_UNSUPPORTED;
   const PkGeom& g = P.g;
   PkMaps maps;
   double flops = 0.0;
@@ -804,8 +810,17 @@ int forward_impl(l2s_vocoder* v, void* stream, const int64_t* code, const void* 
                  int32_t batch, int32_t units, int32_t frames, float* out, int16_t* out_i16, void* workspace,
                  int64_t workspace_bytes) {
   if (!v) return L2S_ERR_INVALID;
+  std::shared_lock<std::shared_mutex> knobs(g_knob_mu);
   std::lock_guard<std::mutex> lock(v->mu);
   if (!v->finalized) return fail(v, L2S_ERR_STATE, "l2s_finalize has not been called");
+  if (v->err_host && *(volatile int*)v->err_host) {
+    // An EARLIER forward on this handle clamped an out-of-range id (the reference raises IndexError on the CPU and
+    // device-asserts on CUDA): report it now, late rather than never, without synchronising.  This call does no work.
+    const int f = *(volatile int*)v->err_host;
+    *(volatile int*)v->err_host = 0;
+    return fail(v, L2S_ERR_INDEX, (f & 1) ? "index out of range in self (a unit id outside the dict table, seen by an earlier forward)"
+                                          : "index out of range in self (a speaker id outside the table, seen by an earlier forward)");
+  }
   const l2s_config& c = v->cfg;
   const bool multi = c.variant == L2S_VARIANT_MULTI_INPUT;
   if (batch < 1 || units < 1 || frames < 1) return fail(v, L2S_ERR_SHAPE, "empty batch / sequence");
@@ -1051,9 +1066,9 @@ int l2s_finalize(l2s_vocoder* v, int device) {
   v->pk_bias.assign((size_t)c.n_ups, std::vector<float*>((size_t)c.n_rk, nullptr));
   v->pk_bias_stage.assign((size_t)c.n_ups, nullptr);
   v->pk_bias_host.assign((size_t)c.n_ups, std::vector<std::vector<float>>((size_t)c.n_rk));
-  for (int i = 0; bf && i < c.n_ups && c.n_dil <= kPkMaxDil; ++i) {
+  for (int i = 0; i < c.n_ups; ++i) {
     const int ch = v->stage_ch[i];
-    if (ch != 16 && ch != 32 && ch != 64) continue;
+    if (!v->pk_ok[i]) continue;
     std::vector<float> stage_cols;
     for (int j = 0; j < c.n_rk; ++j) {
       std::vector<float> cols((size_t)kPkBiasRows * 128, 0.f), run((size_t)ch, 0.f);
@@ -1187,6 +1202,7 @@ int l2s_poll_index_error(l2s_vocoder* v) {
 
 int32_t l2s_launch_count(l2s_vocoder* v, int32_t batch, int32_t frames) {
   if (!v) return -1;
+  std::shared_lock<std::shared_mutex> knobs(g_knob_mu);
   const l2s_config& c = v->cfg;
   int n = (int)v->convs.size() + 1 /* post */ + 1 /* cond */;
   if (pairs_fused(v)) n -= c.n_ups * c.n_rk * c.n_dil;   // one launch per (c1, c2) step
@@ -1238,6 +1254,7 @@ int l2s_debug_conv(const l2s_conv_desc* d, int32_t impl, int32_t device, void* s
     if (err && err_len > 0) snprintf(err, (size_t)err_len, "%s", m);
   };
   if (!d) { say("null desc"); return L2S_ERR_INVALID; }
+  std::shared_lock<std::shared_mutex> knobs(g_knob_mu);
   if (d->ntaps < 1 || d->ntaps > kMaxTaps) { say("ntaps"); return L2S_ERR_INVALID; }
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) { say(cudaGetErrorString(e)); return L2S_ERR_CUDA; }
@@ -1294,6 +1311,7 @@ int l2s_debug_layer_time(l2s_vocoder* v, int32_t idx, float* ms, double* flops, 
 
 int l2s_debug_set(const char* key, int64_t value) {
   if (!key) return L2S_ERR_INVALID;
+  std::unique_lock<std::shared_mutex> knobs(g_knob_mu);
   const std::string k(key);
   ++g_knobs.epoch;
   if (k == "use_graph") { g_knobs.use_graph = value; return L2S_OK; }

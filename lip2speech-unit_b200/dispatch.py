@@ -67,10 +67,12 @@ class HostPipeline:
 
         pipe = HostPipeline(generator, "cuda:0")
         for (code_h, mel_h, spk_h), out_h in zip(batches, pinned_outputs):
-            pipe.submit(code_h, mel_h, spk_h, out_h)        # asynchronous; out_h is a pinned float32 (B,1,L) tensor
+            pipe.submit(code_h, mel_h, spk_h, out_h)        # asynchronous; out_h: pinned float32 (B,1,L) or int16 (B,L)
         pipe.finish()                                       # every out_h is complete
 
-    The forward itself runs on the stream that is current when submit() is called."""
+    An int16 `out_h` gets the device-side int16 waveform (what every reference caller derives on the host,
+    inference.py:79-81): half the device->host bytes.  The forward itself runs on the stream that is current when
+    submit() is called."""
 
     def __init__(self, generator, device="cuda"):
         self.g = generator
@@ -82,19 +84,35 @@ class HostPipeline:
         self.out_free = [None, None]     # event: the device->host copy of slot s's waveform has finished
         self.bufs = [None, None]         # per slot: (shapes, code, mel, spk, out) device buffers, allocated once per shape
 
+    def _allocate(self, s, shapes, code_h, mel_h, spk_h, out_h, main):
+        if self.bufs[s] is not None:
+            torch.cuda.synchronize(self.device)               # a new shape: retire the old buffers first
+        with torch.cuda.device(self.device):
+            bufs = (torch.empty_like(code_h, device=self.device), torch.empty_like(mel_h, device=self.device),
+                    torch.empty_like(spk_h, device=self.device), torch.empty(out_h.shape, dtype=out_h.dtype, device=self.device))
+        # The blocks come from the allocating (main) stream's pool but are written on s_in and read on s_out: tell the
+        # caching allocator, and make both copy streams wait until main has reached the allocation point (a recycled
+        # block may still be in use by kernels queued on main).
+        born = torch.cuda.Event()
+        born.record(main)
+        self.s_in.wait_event(born)
+        self.s_out.wait_event(born)
+        for t in bufs[:3]:
+            t.record_stream(self.s_in)
+        bufs[3].record_stream(self.s_out)
+        self.bufs[s] = (shapes,) + bufs
+        self.in_free[s] = self.out_free[s] = None
+
     @torch.no_grad()
     def submit(self, code_h, mel_h, spk_h, out_h):
         s = self.slot
         self.slot ^= 1
         main = torch.cuda.current_stream(self.device)
-        shapes = (tuple(code_h.shape), tuple(mel_h.shape), tuple(spk_h.shape), mel_h.dtype, tuple(out_h.shape))
+        if out_h.dtype not in (torch.float32, torch.int16):
+            raise TypeError("out_h must be float32 (B,1,L) or int16 (B,L)")
+        shapes = (tuple(code_h.shape), tuple(mel_h.shape), tuple(spk_h.shape), mel_h.dtype, tuple(out_h.shape), out_h.dtype)
         if self.bufs[s] is None or self.bufs[s][0] != shapes:
-            if self.bufs[s] is not None:
-                torch.cuda.synchronize(self.device)               # a new shape: retire the old buffers first
-            self.bufs[s] = (shapes, torch.empty_like(code_h, device=self.device), torch.empty_like(mel_h, device=self.device),
-                            torch.empty_like(spk_h, device=self.device),
-                            torch.empty(out_h.shape, dtype=torch.float32, device=self.device))
-            self.in_free[s] = self.out_free[s] = None
+            self._allocate(s, shapes, code_h, mel_h, spk_h, out_h, main)
         _, code, mel, spk, out = self.bufs[s]
         with torch.cuda.stream(self.s_in):
             if self.in_free[s] is not None:
@@ -107,7 +125,10 @@ class HostPipeline:
         main.wait_event(ready)
         if self.out_free[s] is not None:
             main.wait_event(self.out_free[s])                  # the slot's previous waveform has left the device
-        self.g.forward_into(out, code=code, mel=mel, spkr=spk)
+        if out.dtype == torch.int16:
+            self.g.forward_int16_into(out, code=code, mel=mel, spkr=spk)
+        else:
+            self.g.forward_into(out, code=code, mel=mel, spkr=spk)
         done = torch.cuda.Event()
         done.record(main)
         self.in_free[s] = done
@@ -119,4 +140,12 @@ class HostPipeline:
         self.out_free[s] = copied
 
     def finish(self):
+        """Wait until every submitted waveform is in its pinned host buffer."""
         self.s_out.synchronize()
+        self.s_in.synchronize()
+
+    def __del__(self):
+        try:
+            self.finish()           # the device buffers must not return to the pool while a copy is in flight
+        except Exception:
+            pass

@@ -154,10 +154,17 @@ class _GeneratorBase(nn.Module):
         self.conv_post = _WeightNormed((1, ch, 7), 1, 0.01)
         self.dict = _Plain((h.num_embeddings, h.embedding_dim), normal=True)
         self.multispkr = h.get("multispkr", None)
+        # bf16 tensor-core mode is the default (the path this library exists for: ~46 dB SNR / <= 2e-2 max-abs against the
+        # fp32 reference).  "tf32" matches what the reference itself computes on an Ampere-or-later
+        # GPU (cuDNN TF32 convolutions are on by default in torch), "fp32" is the CUDA-core reference mode.
         self.precision = os.environ.get("L2S_PRECISION", h.get("precision", "bf16"))
+        # Out-of-range ids: always detected (sticky device flag).  Default: the NEXT forward (or check_index_errors())
+        # raises IndexError -- late, like the asynchronous device assert of the CUDA reference, and without a
+        # synchronisation; strict: synchronise after every forward and raise immediately, like the CPU reference.
         self.strict_index_check = bool(int(os.environ.get("L2S_STRICT_INDEX", "0")))
         self._engines = {}
-        self._lock = threading.Lock()
+        self._lock = threading.Lock()          # guards the engine table only
+        self._dev_locks = {}                   # one lock per device: forwards on different GPUs run concurrently
         self._folded = False
 
     # ------------------------------------------------------------ reference surface
@@ -245,7 +252,8 @@ class _GeneratorBase(nn.Module):
 
     def _engine(self, device: torch.device) -> _Engine:
         key = (device.index if device.index is not None else torch.cuda.current_device(), self.precision)
-        eng = self._engines.get(key)
+        with self._lock:
+            eng = self._engines.get(key)
         if eng is not None:
             return eng
         lib = _cabi.load()
@@ -269,7 +277,8 @@ class _GeneratorBase(nn.Module):
             lib.l2s_destroy(handle)
             raise
         eng = _Engine(lib, handle, key[0], self.precision)
-        self._engines[key] = eng
+        with self._lock:
+            self._engines[key] = eng
         return eng
 
     def _check_device(self, t, name):
@@ -278,7 +287,7 @@ class _GeneratorBase(nn.Module):
         if not t.is_cuda:
             raise RuntimeError(f"{name} is on {t.device}: this generator runs on a B200 only (no CPU fallback)")
 
-    def _run(self, code, mel, spkr, frames, want_i16=False, out=None):
+    def _run(self, code, mel, spkr, frames, want_i16=False, out=None, out16=None):
         if self.training:
             raise NotImplementedError("the accelerated generator is inference-only: call .eval() first")
         device = code.device
@@ -296,7 +305,11 @@ class _GeneratorBase(nn.Module):
                 eng.workspaces[wkey] = None
                 ws = torch.empty(int(need), dtype=torch.uint8, device=device)
                 eng.workspaces[wkey] = ws
-            if out is None:
+            if out16 is not None:
+                if (out16.dtype != torch.int16 or not out16.is_cuda or not out16.is_contiguous()
+                        or out16.numel() != batch * eng.hop * frames):
+                    raise RuntimeError(f"out16 must be a contiguous int16 CUDA tensor of {batch * eng.hop * frames} samples")
+            elif out is None:
                 out = torch.empty((batch, 1, eng.hop * frames), dtype=torch.float32, device=device)
             elif (out.dtype != torch.float32 or not out.is_cuda or not out.is_contiguous()
                   or tuple(out.shape) != (batch, 1, eng.hop * frames)):
@@ -307,6 +320,14 @@ class _GeneratorBase(nn.Module):
                 mel_ptr = mel.data_ptr()
             spk_ptr = spkr.data_ptr() if spkr is not None else None
             with torch.cuda.device(device):
+                if out16 is not None:              # int16 only, into the caller's buffer (no fp32 copy is written)
+                    st = lib.l2s_forward_i16(eng.handle, stream.cuda_stream, code.data_ptr(), mel_ptr, mel_tag, spk_ptr,
+                                             batch, units, frames, None, out16.data_ptr(), ws.data_ptr(), ws.numel())
+                    _cabi.raise_for(lib, eng.handle, st)
+                    if self.strict_index_check:
+                        stream.synchronize()
+                        _cabi.raise_for(lib, eng.handle, lib.l2s_poll_index_error(eng.handle))
+                    return out16
                 if want_i16:
                     out16 = torch.empty((batch, eng.hop * frames), dtype=torch.int16, device=device)
                     st = lib.l2s_forward_i16(eng.handle, stream.cuda_stream, code.data_ptr(), mel_ptr, mel_tag, spk_ptr,
@@ -323,7 +344,24 @@ class _GeneratorBase(nn.Module):
         return (out, out16) if want_i16 else out
 
     def _lock_for(self, device):
-        return self._lock
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        with self._lock:
+            lk = self._dev_locks.get(idx)
+            if lk is None:
+                lk = self._dev_locks[idx] = threading.Lock()
+        return lk
+
+    def check_index_errors(self, device=None):
+        """Synchronise `device` and raise IndexError if any forward so far saw an out-of-range unit / speaker id
+        (what the reference raises on the CPU; on CUDA it device-asserts).  Without this call the error surfaces at the
+        next forward on the same device."""
+        device = torch.device(device if device is not None else "cuda")
+        torch.cuda.synchronize(device)
+        with self._lock:
+            engines = [e for (idx, _), e in self._engines.items()
+                       if idx == (device.index if device.index is not None else torch.cuda.current_device())]
+        for eng in engines:
+            _cabi.raise_for(eng.lib, eng.handle, eng.lib.l2s_poll_index_error(eng.handle))
 
     def launch_count(self, batch, frames, device=None):
         device = torch.device(device if device is not None else "cuda")
@@ -413,6 +451,13 @@ class MelCodeGenerator(_GeneratorBase):
         pipelined caller wants, see dispatch.HostPipeline).  Returns out."""
         code, mel, spkr, frames = self._prepare(kwargs)
         return self._run(code, mel, spkr, frames, out=out)
+
+    @torch.no_grad()
+    def forward_int16_into(self, out16, **kwargs):
+        """int16 waveform only (inference.py:79-81 on the device), written into a caller-owned int16 device tensor of
+        B * hop * T samples: half the device->host bytes of the float waveform, no allocation per call."""
+        code, mel, spkr, frames = self._prepare(kwargs)
+        return self._run(code, mel, spkr, frames, out16=out16)
 
     @torch.no_grad()
     def forward_int16(self, **kwargs):

@@ -15,8 +15,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol(pkg):
     lib = pkg._cabi.load()
-    with open(os.path.join(ROOT, "include", "l2s_vocoder.h")) as f:
-        text = f.read()
+    text = ""
+    for name in ("l2s_vocoder.h", "l2s_debug.h"):       # the drop-in boundary + the test hooks
+        with open(os.path.join(ROOT, "include", name)) as f:
+            text += f.read()
     declared = set(re.findall(r"\b(l2s_[a-z0-9_]+)\s*\(", text))
     assert declared, "no prototypes found in the header"
     assert declared == set(pkg._cabi.EXPORTS)

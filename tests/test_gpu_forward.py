@@ -198,6 +198,73 @@ def test_error_conventions(pkg, weights):
     g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV))   # flag was cleared
 
 
+def test_out_of_range_ids_are_reported_by_default(pkg, weights):
+    """Default (non-strict) mode: an out-of-range unit id is never silent (IndexError / device assert).  The
+    forward that saw it does not synchronise; the error surfaces at check_index_errors(), or -- late -- at the next
+    forward on the same device, which then does no work.  After that the generator is usable again."""
+    h, sds = weights
+    g = make_gen(pkg, h, sds["trained"], "fp32")
+    code, mel, spkr = vo.synthetic_inputs(1, 20, seed=1)
+    bad = code.clone()
+    bad[0, 5] = -7
+    assert not g.strict_index_check
+    y = g(code=bad.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV))          # clamped, flagged, no sync
+    assert torch.isfinite(y).all()
+    with pytest.raises(IndexError):
+        g.check_index_errors(DEV)
+    g.check_index_errors(DEV)                                              # cleared by the report
+    g(code=bad.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV))
+    torch.cuda.synchronize()
+    with pytest.raises(IndexError):                                        # reported late by the next forward
+        g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV))
+    want = vo.mel_code_generator_forward(vo.fold_weight_norm(sds["trained"]), h, code, mel, spkr)
+    check(want, g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV)), "fp32", "forward after a reported index error")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_upsampler_kernel_wider_than_three_strides(pkg, precision):
+    """Edge config: ConvTranspose1d with k > 3u (u = 2, k = 8, padding 3 > u): the last output positions
+    come from polyphase row lin + 1, which the launch must cover.  Against the oracle."""
+    h = vo.shipped_config(upsample_rates=[2, 4, 2], upsample_kernel_sizes=[8, 16, 4], upsample_initial_channel=128,
+                          resblock_kernel_sizes=[3, 7], resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5]])
+    sd = vo.init_state_dict(h, seed=7, style="trained")
+    code, mel, spkr = vo.synthetic_inputs(2, 26, seed=17)
+    ref = vo.mel_code_generator_forward(vo.fold_weight_norm(sd), h, code, mel, spkr)
+    g = make_gen(pkg, h, sd, precision)
+    y = g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV))
+    assert y.shape == (2, 1, 16 * 26)
+    check(ref, y, precision, "k > 3u upsamplers")
+
+
+def test_concurrent_forwards_from_two_threads(pkg, weights):
+    """inference_server.py runs Flask's threaded dev server: /vocoder handlers may call the shared generator from any
+    thread.  Two threads hammering one generator (each on its own stream) must get exactly the single-threaded bits."""
+    import threading
+    h, sds = weights
+    g = make_gen(pkg, h, sds["trained"], "bf16")
+    jobs = [vo.synthetic_inputs(2, 40 + 8 * (i % 3), seed=200 + i) for i in range(8)]
+    want = [g(code=c.to(DEV), mel=m.to(DEV), spkr=s.to(DEV)).cpu() for c, m, s in jobs]
+    got, errs = [None] * len(jobs), []
+
+    def worker(ids):
+        try:
+            st = torch.cuda.Stream(DEV)
+            with torch.cuda.stream(st):
+                for _ in range(3):
+                    for i in ids:
+                        c, m, s = jobs[i]
+                        got[i] = g(code=c.to(DEV), mel=m.to(DEV), spkr=s.to(DEV)).cpu()
+        except Exception as e:                      # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=worker, args=(range(k, len(jobs), 2),)) for k in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    for a, b in zip(want, got):
+        assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_batch_invariance(pkg, weights, precision):
     """Utterances are independent: a batched forward equals the per-utterance forwards bit for bit."""
@@ -457,6 +524,14 @@ def test_host_pipeline_equals_direct_forward(pkg, weights):
     pipe.finish()
     for (c, m, s), o in zip(batches, outs):
         assert torch.equal(o, g(code=c.to(DEV), mel=m.to(DEV), spkr=s.to(DEV)).cpu())
+    # int16 pinned outputs: the device-side int16 waveform (inference.py:79-81), half the device->host bytes
+    outs16 = [torch.empty((2, o.shape[-1]), dtype=torch.int16).pin_memory() for o in outs]
+    for (c, m, s), o in zip(batches, outs16):
+        pipe.submit(c, m, s, o)
+    pipe.finish()
+    for o32, o16 in zip(outs, outs16):
+        expect = (o32.squeeze(1) * 32768.0).clamp(-32768, 32767).numpy().astype("int16")
+        assert np.array_equal(o16.numpy(), expect)
 
 
 def test_stage1_outputs_straight_into_the_vocoder(pkg, weights):
