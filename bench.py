@@ -418,10 +418,11 @@ def main():
             yu = gen_u(code=cu, spkr=su)
         sync_all()
         u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        yu_h = torch.empty((n5, 300 * 320), dtype=torch.int16).pin_memory()
         u0.record()
         for _ in range(5):
             yu = gen_u(code=cu, spkr=su)
-            yu16 = (yu * 32768.0).clamp_(-32768, 32767).to(torch.int16).cpu()    # unit-only: the reference callers' own int16 flow
+            yu_h.copy_((yu.view(n5, -1) * 32768.0).clamp_(-32768, 32767).to(torch.int16), non_blocking=True)   # inference.py:79-81
         u1.record()
         sync_all()
         msu = max_over_ranks([u0.elapsed_time(u1) / 5])[0]

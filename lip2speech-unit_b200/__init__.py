@@ -8,7 +8,7 @@ MelCodeGenerator`` exactly like the reference's inference scripts do.
 """
 from . import _cabi  # noqa: F401
 from .models_multi_input import AttrDict, CodeGenerator, MelCodeGenerator  # noqa: F401
-from .dispatch import shard_utterances, chunk_plan, vocode_long, HostPipeline  # noqa: F401
+from .dispatch import shard_utterances, chunk_plan, vocode_long, HostPipeline, MultiGpuVocoder  # noqa: F401
 from . import hand_off  # noqa: F401
 
-__all__ = ["MelCodeGenerator", "CodeGenerator", "AttrDict", "shard_utterances", "chunk_plan", "vocode_long", "HostPipeline", "hand_off"]
+__all__ = ["MelCodeGenerator", "CodeGenerator", "AttrDict", "shard_utterances", "chunk_plan", "vocode_long", "HostPipeline", "MultiGpuVocoder", "hand_off"]

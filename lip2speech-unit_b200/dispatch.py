@@ -1,8 +1,11 @@
 """Host-side work partitioning around the generator forward: utterance sharding
 across GPUs (no collective: utterances are independent) and the
 halo-exact chunk plan for long streams."""
-from typing import List, Sequence, Tuple
+import threading
+from concurrent.futures import ThreadPoolExecutor
+from typing import Dict, List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 
 # An output sample depends on conditioning within +-21.6 mel frames;
@@ -85,8 +88,11 @@ class HostPipeline:
         self.bufs = [None, None]         # per slot: (shapes, code, mel, spk, out) device buffers, allocated once per shape
 
     def _allocate(self, s, shapes, code_h, mel_h, spk_h, out_h, main):
-        if self.bufs[s] is not None:
-            torch.cuda.synchronize(self.device)               # a new shape: retire the old buffers first
+        # a new shape: retire the old buffers first.  Only this pipeline's own work is waited for -- a device-wide
+        # synchronize here could collide with another host thread that is capturing a CUDA graph on the same device.
+        for ev in (self.in_free[s], self.out_free[s]):
+            if ev is not None:
+                ev.synchronize()
         with torch.cuda.device(self.device):
             bufs = (torch.empty_like(code_h, device=self.device), torch.empty_like(mel_h, device=self.device),
                     torch.empty_like(spk_h, device=self.device), torch.empty(out_h.shape, dtype=out_h.dtype, device=self.device))
@@ -138,6 +144,7 @@ class HostPipeline:
             copied = torch.cuda.Event()
             copied.record(self.s_out)
         self.out_free[s] = copied
+        return copied                                          # completes when out_h holds this batch's waveform
 
     def finish(self):
         """Wait until every submitted waveform is in its pinned host buffer."""
@@ -149,3 +156,75 @@ class HostPipeline:
             self.finish()           # the device buffers must not return to the pool while a copy is in flight
         except Exception:
             pass
+
+
+def _pinned_stack(arrays, dtype):
+    t = torch.empty((len(arrays),) + tuple(arrays[0].shape), dtype=dtype).pin_memory()
+    for i, a in enumerate(arrays):
+        t[i].copy_(a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a)))
+    return t
+
+
+class MultiGpuVocoder:
+    """One PROCESS, every GPU of the box ("one host thread or process per GPU", no collective):
+    the utterance list is dealt longest-first across the devices (shard_utterances), each device has its own engine
+    (weights replicated, 28 MB), its own stream, its own HostPipeline and a host thread that feeds it; utterances of
+    equal length share a forward, int16 waveforms come back through pinned memory (half the PCIe bytes of fp32).
+    Results are bit-identical to vocoding every utterance alone on one GPU (batch invariance of the kernels).
+
+        mg = MultiGpuVocoder(generator)                       # all visible GPUs
+        wavs = mg.vocode(feats)                               # feats[i] = {"code": (U,), "mel": (80, 2U), "spkr": (256,)} host arrays
+                                                              # -> list of int16 numpy arrays (160 * 2U samples), input order
+    A service process keeps one instance; vocode() may be called from any thread (calls are serialised per instance)."""
+
+    def __init__(self, generator, devices: Optional[Sequence] = None, max_batch: int = 32):
+        if devices is None:
+            devices = list(range(torch.cuda.device_count()))
+        if not devices:
+            raise RuntimeError("MultiGpuVocoder needs at least one CUDA device (there is no CPU fallback)")
+        self.g = generator
+        self.devices = [torch.device("cuda", d) if isinstance(d, int) else torch.device(d) for d in devices]
+        self.max_batch = max_batch
+        self._streams = [torch.cuda.Stream(d) for d in self.devices]
+        self._pipes = [None] * len(self.devices)
+        self._pool = ThreadPoolExecutor(max_workers=len(self.devices), thread_name_prefix="l2s-gpu")
+        self._call = threading.Lock()
+
+    def _worker(self, k: int, feats, mine: List[int], out: list):
+        dev = self.devices[k]
+        torch.cuda.set_device(dev)
+        by_len: Dict[int, List[int]] = {}
+        for i in mine:
+            by_len.setdefault(int(feats[i]["mel"].shape[1]), []).append(i)
+        batches = [idxs[s:s + self.max_batch] for _, idxs in sorted(by_len.items(), reverse=True)
+                   for s in range(0, len(idxs), self.max_batch)]
+        with torch.no_grad(), torch.cuda.stream(self._streams[k]):
+            if self._pipes[k] is None:
+                self._pipes[k] = HostPipeline(self.g, dev)
+            pipe, pending = self._pipes[k], []
+            for grp in batches:
+                code = _pinned_stack([feats[i]["code"] for i in grp], torch.int64)
+                mel = _pinned_stack([feats[i]["mel"] for i in grp], torch.float32)
+                spk = _pinned_stack([feats[i]["spkr"] for i in grp], torch.float32)
+                wav = torch.empty((len(grp), mel.shape[2] * 160), dtype=torch.int16).pin_memory()
+                pending.append((grp, wav, pipe.submit(code, mel, spk, wav), (code, mel, spk)))
+            for grp, wav, done, _keep in pending:
+                done.synchronize()
+                for j, i in enumerate(grp):
+                    out[i] = wav[j].numpy().copy()
+            pipe.finish()
+            self.g.check_index_errors(dev)          # synchronises this worker's stream only
+
+    def vocode(self, feats: Sequence[dict]) -> List[np.ndarray]:
+        with self._call:
+            lengths = [int(f["mel"].shape[1]) for f in feats]
+            out: list = [None] * len(feats)
+            n = len(self.devices)
+            futs = [self._pool.submit(self._worker, k, feats, shard_utterances(lengths, n, k), out) for k in range(n)]
+            for f in futs:
+                f.result()
+            return out
+
+    def close(self):
+        self._pool.shutdown(wait=True)
+        self._pipes = [None] * len(self.devices)

@@ -352,11 +352,12 @@ class _GeneratorBase(nn.Module):
         return lk
 
     def check_index_errors(self, device=None):
-        """Synchronise `device` and raise IndexError if any forward so far saw an out-of-range unit / speaker id
-        (what the reference raises on the CPU; on CUDA it device-asserts).  Without this call the error surfaces at the
-        next forward on the same device."""
+        """Synchronise the current stream of `device` and raise IndexError if a forward issued on it saw an out-of-range
+        unit / speaker id (what the reference raises on the CPU; on CUDA it device-asserts).  Without this call the
+        error surfaces at the next forward on the same device.  (Stream, not device: a device-wide synchronize could
+        collide with another host thread capturing a CUDA graph.)"""
         device = torch.device(device if device is not None else "cuda")
-        torch.cuda.synchronize(device)
+        torch.cuda.current_stream(device).synchronize()
         with self._lock:
             engines = [e for (idx, _), e in self._engines.items()
                        if idx == (device.index if device.index is not None else torch.cuda.current_device())]

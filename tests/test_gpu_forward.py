@@ -624,3 +624,51 @@ def test_cfg2_shape_bf16_vs_fp32_device_reference(pkg, weights):
     snr = vo.snr_db(a.cpu(), b.cpu())
     print(f"[parity] cfg2 bf16 vs fp32-device: snr {snr:.2f} dB max-abs {vo.max_abs(a.cpu(), b.cpu()):.3e}")
     assert snr >= 43.0
+
+
+@pytest.mark.parametrize("devices", ["twice_gpu0", "all"])
+def test_in_process_multi_gpu_dispatcher_equals_single_gpu(pkg, weights, devices):
+    """one process, one engine + HostPipeline + host thread per GPU, utterances dealt
+    longest-first, int16 back.  The waveforms must equal the per-utterance single-GPU flow bit for bit.  "twice_gpu0"
+    runs two workers on cuda:0 (exercises the threading on a one-GPU box); "all" needs >= 2 GPUs."""
+    h, sds = weights
+    if devices == "all" and torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    devs = [0, 0] if devices == "twice_gpu0" else list(range(torch.cuda.device_count()))
+    g = make_gen(pkg, h, sds["trained"], "bf16")
+    feats, want = [], []
+    for i, frames in enumerate([60, 84, 60, 30, 84, 60, 84, 30, 60, 12, 84]):
+        code, mel, spkr = vo.synthetic_inputs(1, frames, seed=400 + i)
+        feats.append({"code": code[0].numpy(), "mel": mel[0].numpy(), "spkr": spkr[0].numpy()})
+        y = g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV))
+        want.append((y.squeeze() * 32768.0).clamp(-32768, 32767).to(torch.int16).cpu().numpy())
+    mg = pkg.MultiGpuVocoder(g, devices=devs, max_batch=2)
+    try:
+        for _ in range(2):                                   # second call reuses engines, pipelines, graphs
+            got = mg.vocode(feats)
+            assert len(got) == len(want)
+            for a, b in zip(got, want):
+                assert a.dtype == np.int16 and np.array_equal(a, b)
+    finally:
+        mg.close()
+
+
+def test_serve_vocoder_request_equals_per_utterance_flow(pkg, weights, tmp_path):
+    """the batched, I/O-overlapped /vocoder request handler against the reference's per-utterance flow
+    (forward, * 32768, astype int16 on the host, scipy wav) on the shipped sample rows: identical files."""
+    from scipy.io import wavfile
+    h, sds = weights
+    g = make_gen(pkg, h, sds["trained"], "fp32")
+    fix = os.path.join(GOLDEN, "lrs3_handoff")
+    ho = pkg.hand_off
+    paths = ho.serve_vocoder_request(g, fix, str(tmp_path), device=DEV, max_batch=4, io_threads=4)
+    _, rows = ho.parse_manifest(os.path.join(fix, "label", "test.tsv"))
+    code_dict = ho.load_code_dict(os.path.join(fix, "label", "dict.unt.txt"))
+    assert len(paths) == 5
+    for r, pth in zip(rows, paths):
+        feats, n = ho.load_item(fix, r, code_dict)
+        y = g(**{k: torch.from_numpy(v).to(DEV).unsqueeze(0) for k, v in feats.items()})
+        expect = (y.squeeze() * 32768.0).clamp(-32768, 32767).cpu().numpy().astype("int16")
+        ref_path = os.path.join(str(tmp_path), "ref.wav")
+        wavfile.write(ref_path, 16000, expect[:n])
+        assert open(pth, "rb").read() == open(ref_path, "rb").read()

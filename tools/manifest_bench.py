@@ -62,8 +62,12 @@ with tempfile.TemporaryDirectory() as root:
     def batched(out_dir):
         ho.vocode_manifest(g, manifest, out_dir, root=root, device=dev)
 
+    def service(out_dir, io_threads=None):
+        ho.serve_vocoder_request(g, root, out_dir, device=dev, **({} if io_threads is None else {"io_threads": io_threads}))
+
     res = {"utterances": n_utts, "audio_s": total_s}
-    for name, fn in (("per_utterance_like_inference_py", per_utterance), ("batched_vocode_manifest", batched)):
+    for name, fn in (("per_utterance_like_inference_py", per_utterance), ("batched_vocode_manifest", batched),
+                     ("serve_vocoder_request", service)):
         with tempfile.TemporaryDirectory() as out:
             fn(out)                                   # warm-up: plans, graphs, file cache
         with tempfile.TemporaryDirectory() as out:
@@ -71,4 +75,16 @@ with tempfile.TemporaryDirectory() as root:
             fn(out)
             torch.cuda.synchronize(); dt = time.perf_counter() - t0
         res[name] = {"seconds": round(dt, 4), "audio_s_per_s": round(total_s / dt, 1)}
+    sweep = {}
+    for nt in (2, 3, 4, 6, 8, 16):
+        with tempfile.TemporaryDirectory() as out:
+            service(out, nt)
+        best = 1e9
+        for _ in range(3):
+            with tempfile.TemporaryDirectory() as out:
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                service(out, nt)
+                torch.cuda.synchronize(); best = min(best, time.perf_counter() - t0)
+        sweep[str(nt)] = round(total_s / best, 1)
+    res["serve_vocoder_request_io_threads_sweep_audio_s_per_s"] = sweep
     print(json.dumps(res))
