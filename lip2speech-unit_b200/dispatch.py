@@ -159,7 +159,7 @@ class HostPipeline:
 
 
 def _pinned_stack(arrays, dtype):
-    t = torch.empty((len(arrays),) + tuple(arrays[0].shape), dtype=dtype).pin_memory()
+    t = torch.empty((len(arrays),) + tuple(arrays[0].shape), dtype=dtype, pin_memory=True)
     for i, a in enumerate(arrays):
         t[i].copy_(a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a)))
     return t
@@ -206,7 +206,7 @@ class MultiGpuVocoder:
                 code = _pinned_stack([feats[i]["code"] for i in grp], torch.int64)
                 mel = _pinned_stack([feats[i]["mel"] for i in grp], torch.float32)
                 spk = _pinned_stack([feats[i]["spkr"] for i in grp], torch.float32)
-                wav = torch.empty((len(grp), mel.shape[2] * 160), dtype=torch.int16).pin_memory()
+                wav = torch.empty((len(grp), mel.shape[2] * 160), dtype=torch.int16, pin_memory=True)
                 pending.append((grp, wav, pipe.submit(code, mel, spk, wav), (code, mel, spk)))
             for grp, wav, done, _keep in pending:
                 done.synchronize()

@@ -132,7 +132,7 @@ def vocode_batched(generator, feats: Sequence[dict], device="cuda", max_batch: i
         ts = [as_tensor(v) for v in vals]
         if ts[0].is_cuda:
             return torch.stack([t.to(device) for t in ts])
-        pinned = torch.empty((len(ts),) + tuple(ts[0].shape), dtype=ts[0].dtype).pin_memory()
+        pinned = torch.empty((len(ts),) + tuple(ts[0].shape), dtype=ts[0].dtype, pin_memory=True)
         torch.stack(ts, out=pinned)
         return pinned.to(device, non_blocking=True)
 
@@ -251,7 +251,7 @@ def _load_group(dataset_dir: str, rows, idxs, code_dict, pin: bool = True):
     out = []
     for t, grp in by_t.items():
         n = len(grp)
-        mk = (lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()) if pin else (lambda shape, dt: torch.empty(shape, dtype=dt))
+        mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=pin)      # noqa: E731
         code = mk((n, grp[0][1].shape[0]), torch.int64)
         mel = mk((n, grp[0][2].shape[1], t), torch.float32)
         spk = mk((n, grp[0][3].shape[0]), torch.float32)
