@@ -62,6 +62,8 @@ struct Knobs {
   long long max_ctas = 0;
   long long embed_tap = 0;
   long long layer_events = 0;      // record a cudaEvent pair around every launch of the next forwards
+  long long branch_par = 1;        // C >= 128 stages: the kernel-size branches of a stage run on parallel streams (graph branches); only the
+                                   // last step of a branch waits for the previous branch (running sum).  Fills the wave-quantisation tails.
 };
 Knobs g_knobs;
 std::shared_mutex g_knob_mu;   // forwards hold it shared, l2s_debug_set exclusively: a knob never changes under a running forward
@@ -147,6 +149,8 @@ struct l2s_vocoder {
   struct ChainGraph { int batch, frames; void* workspace; long long epoch; int seen; cudaGraphExec_t exec; };
   std::vector<ChainGraph> graphs;
   cudaStream_t capture_stream = nullptr;
+  cudaStream_t br_stream[L2S_MAX_RK] = {nullptr};   // parallel branches of a stage (index 0 unused: branch 0 stays on the caller's stream)
+  cudaEvent_t ev_fork = nullptr, ev_acc[L2S_MAX_RK] = {nullptr}, ev_join[L2S_MAX_RK] = {nullptr};
 };
 
 namespace {
@@ -651,8 +655,10 @@ int run_res(l2s_vocoder* v, int i, int j, cudaStream_t st, int batch, int lin, c
 struct Workspace {
   void* cond;
   void* ma[2];
-  float *x, *y, *acc;
-  void *xa, *ya, *ta;
+  float *x, *acc;
+  void* xa;
+  float* y[L2S_MAX_RK];            // per branch: fp32 residual stream between the steps of a ResBlock
+  void *ya[L2S_MAX_RK], *ta[L2S_MAX_RK];   // per branch: activated copies (ping-pong)
   float* spk_vec;
   float* embed;
   size_t bytes;
@@ -681,11 +687,15 @@ Workspace carve(const l2s_vocoder* v, int batch, int frames, uint8_t* base) {
   w.ma[0] = take((size_t)batch * ma_elems * as);
   w.ma[1] = take((size_t)batch * ma_elems * as);
   w.x = (float*)take((size_t)batch * max_stage * 4);
-  w.y = (float*)take((size_t)batch * max_stage * 4);
   w.acc = (float*)take((size_t)batch * max_stage * 4);
   w.xa = take((size_t)batch * max_stage * as);
-  w.ya = take((size_t)batch * max_stage * as);
-  w.ta = take((size_t)batch * max_stage * as);
+  for (int j = 0; j < L2S_MAX_RK; ++j) {
+    if (j < c.n_rk) {
+      w.y[j] = (float*)take((size_t)batch * max_stage * 4);
+      w.ya[j] = take((size_t)batch * max_stage * as);
+      w.ta[j] = take((size_t)batch * max_stage * as);
+    } else { w.y[j] = w.y[0]; w.ya[j] = w.ya[0]; w.ta[j] = w.ta[0]; }
+  }
   w.spk_vec = (float*)take((size_t)batch * c.embedding_dim * 4);
   const int units = c.variant == L2S_VARIANT_MULTI_INPUT ? frames / 2 : frames;
   w.embed = (float*)take((size_t)batch * units * c.embedding_dim * 4);
@@ -761,20 +771,30 @@ int run_chain(l2s_vocoder* v, cudaStream_t st, const Workspace& ws, int batch, i
             !pair_plan(a1.cin, a1.k, a1.dil, (int)len, batch, (int)g_knobs.pair_smem, g_knobs.dual != 0, g_knobs.cluster != 0, g_knobs.alias_at != 0, false, false, &pg))
           stage_fused = false;
       }
+    // Branch-parallel streams: the steps of different branches are independent except that a branch's LAST step adds to the
+    // running sum the previous branch's last step wrote.  Branch 0 stays on st, the others fork off it and join back.
+    const bool par = !whole && stage_fused && g_knobs.branch_par && c.n_rk > 1 && !g_knobs.layer_events && !g_knobs.span_ptr &&
+                     !g_knobs.trace_ptr && v->ev_fork;
+    if (par) {
+      cudaEventRecord(v->ev_fork, st);
+      for (int j = 1; j < c.n_rk; ++j) cudaStreamWaitEvent(v->br_stream[j], v->ev_fork, 0);
+    }
     for (int j = 0; !whole && j < c.n_rk; ++j) {
+      cudaStream_t sj = (par && j > 0) ? v->br_stream[j] : st;
+      const int bj = par ? j : 0;                              // serial: every branch reuses buffer set 0
       for (int m = 0; m < c.n_dil; ++m) {
         ConvLayer& c1 = v->convs[v->rb_c1[i][j][m]];
         ConvLayer& c2 = v->convs[v->rb_c2[i][j][m]];
-        void* act_pp[2] = {ws.ya, ws.ta};
-        const void* in1 = m == 0 ? ws.xa : (stage_fused ? act_pp[(m - 1) & 1] : ws.ya);
-        void* mid_act = stage_fused ? act_pp[m & 1] : ws.ya;     // activated output of a non-final step
-        const float* res = m == 0 ? ws.x : ws.y;
+        void* act_pp[2] = {ws.ya[bj], ws.ta[bj]};
+        const void* in1 = m == 0 ? ws.xa : (stage_fused ? act_pp[(m - 1) & 1] : ws.ya[bj]);
+        void* mid_act = stage_fused ? act_pp[m & 1] : ws.ya[bj];     // activated output of a non-final step
+        const float* res = m == 0 ? ws.x : ws.y[bj];
         // per (j, m): which outputs the step produces
         float* o_raw;
         void* o_act;
         const float* a_in = nullptr;
         float dv = 1.f;
-        if (m < c.n_dil - 1) { o_raw = ws.y; o_act = mid_act; }
+        if (m < c.n_dil - 1) { o_raw = ws.y[bj]; o_act = mid_act; }
         else if (j < c.n_rk - 1) { o_raw = ws.acc; o_act = nullptr; a_in = j == 0 ? nullptr : ws.acc; }
         else {
           // last branch: mean over branches (true division by num_kernels, models.py:109)
@@ -783,17 +803,24 @@ int run_chain(l2s_vocoder* v, cudaStream_t st, const Workspace& ws, int batch, i
           a_in = c.n_rk == 1 ? nullptr : ws.acc;
           dv = (float)c.n_rk;
         }
+        if (par && m == c.n_dil - 1 && j > 0) cudaStreamWaitEvent(sj, v->ev_acc[j - 1], 0);   // the running sum of the previous branch
         if (stage_fused) {
-          rc = run_pair(v, c1, c2, st, batch, (int)len, in1, res, o_raw, o_act, a_in, dv, 0.1f);
+          rc = run_pair(v, c1, c2, sj, batch, (int)len, in1, res, o_raw, o_act, a_in, dv, 0.1f);
           if (rc == L2S_ERR_UNSUPPORTED) return fail(v, L2S_ERR_STATE, "fused plan vanished for " + c1.name);
         } else {
-          rc = run_conv(v, c1, st, batch, (int)len, in1, nullptr, ws.ta, nullptr, nullptr, 1.f, 0.1f);
+          rc = run_conv(v, c1, sj, batch, (int)len, in1, nullptr, ws.ta[bj], nullptr, nullptr, 1.f, 0.1f);
           if (rc) return rc;
-          rc = run_conv(v, c2, st, batch, (int)len, ws.ta, o_raw, o_act, res, a_in, dv, 0.1f);
+          rc = run_conv(v, c2, sj, batch, (int)len, ws.ta[bj], o_raw, o_act, res, a_in, dv, 0.1f);
         }
         if (rc) return rc;
+        if (par && m == c.n_dil - 1 && j < c.n_rk - 1) cudaEventRecord(v->ev_acc[j], sj);
       }
     }
+    if (par)
+      for (int j = 1; j < c.n_rk; ++j) {
+        cudaEventRecord(v->ev_join[j], v->br_stream[j]);
+        cudaStreamWaitEvent(st, v->ev_join[j], 0);
+      }
     cur ^= 1;
     if (g_knobs.stop_after_stage == i) {
       v->taps["ups"] = {ws.x, numel, false};
@@ -993,6 +1020,12 @@ void l2s_destroy(l2s_vocoder* v) {
     if (dev != v->device) cudaSetDevice(v->device);
     for (auto& gph : v->graphs) if (gph.exec) cudaGraphExecDestroy(gph.exec);
     if (v->capture_stream) cudaStreamDestroy(v->capture_stream);
+    for (int j = 0; j < L2S_MAX_RK; ++j) {
+      if (v->br_stream[j]) cudaStreamDestroy(v->br_stream[j]);
+      if (v->ev_acc[j]) cudaEventDestroy(v->ev_acc[j]);
+      if (v->ev_join[j]) cudaEventDestroy(v->ev_join[j]);
+    }
+    if (v->ev_fork) cudaEventDestroy(v->ev_fork);
     for (void* p : v->dev_allocs) cudaFree(p);
     if (v->err_host) cudaFreeHost(v->err_host);
     if (dev >= 0 && dev != v->device) cudaSetDevice(dev);
@@ -1160,6 +1193,12 @@ int l2s_finalize(l2s_vocoder* v, int device) {
     if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, cudaGetErrorString(e));
     v->post_bias = v->weights["conv_post.bias"][0];
   }
+  for (int j = 1; j < c.n_rk && j < L2S_MAX_RK; ++j) {
+    if ((e = cudaStreamCreateWithFlags(&v->br_stream[j], cudaStreamNonBlocking)) != cudaSuccess) return fail(v, L2S_ERR_CUDA, cudaGetErrorString(e));
+    cudaEventCreateWithFlags(&v->ev_join[j], cudaEventDisableTiming);
+  }
+  for (int j = 0; j < L2S_MAX_RK; ++j) cudaEventCreateWithFlags(&v->ev_acc[j], cudaEventDisableTiming);
+  if ((e = cudaEventCreateWithFlags(&v->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail(v, L2S_ERR_CUDA, cudaGetErrorString(e));
   if ((e = cudaHostAlloc((void**)&v->err_host, sizeof(int), cudaHostAllocMapped)) != cudaSuccess)
     return fail(v, L2S_ERR_CUDA, cudaGetErrorString(e));
   *v->err_host = 0;
@@ -1353,6 +1392,7 @@ int l2s_debug_set(const char* key, int64_t value) {
   else if (k == "max_ctas") g_knobs.max_ctas = value;
   else if (k == "embed_tap") g_knobs.embed_tap = value;
   else if (k == "layer_events") g_knobs.layer_events = value;
+  else if (k == "branch_par") g_knobs.branch_par = value;
   else return L2S_ERR_INVALID;
   return L2S_OK;
 }

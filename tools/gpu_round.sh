@@ -1,22 +1,18 @@
 #!/bin/bash
-# One GPU-box session: parity tests, smoke, bench, ncu launch list, per-kernel metrics, two full captures.
-# Everything lands in gpurun_out/ (keep it under 64 MiB: --set full for two launches only).
+# One GPU-box session for the ncu evidence of a round: launch list of one forward, per-kernel metrics of the fused
+# launches, full captures of the heaviest kernel of every family.  Everything lands in gpurun_out/ (< 64 MiB).
 set +e
 mkdir -p gpurun_out
-python -m pytest tests -q -s -m gpu > gpurun_out/pytest_all.log 2>&1
-grep "\[parity\]" gpurun_out/pytest_all.log > gpurun_out/parity.txt
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
-python bench.py --steps 50 --warmup 5 --layers > gpurun_out/bench_bf16.json 2> gpurun_out/bench_bf16.err
-python bench.py --impl reference --steps 2 --warmup 3 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
-# launch list of one forward (36 launches per forward in bf16 mode; the third forward of the process is listed)
-python tools/one_forward.py 3 > gpurun_out/plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -s 72 -c 36 --csv --log-file gpurun_out/launches_final.csv python tools/one_forward.py 3 > gpurun_out/ncu_launch.log 2>&1
-# metrics of the 18 fused-step + 9 whole-ResBlock launches of the second forward
-python tools/one_forward.py 2 > gpurun_out/plain2.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,lts__t_bytes.sum,smsp__inst_executed.sum,launch__registers_per_thread,launch__shared_mem_per_block_dynamic,launch__grid_size --clock-control none -k "regex:pair_tc_kernel|res_tc_kernel" -s 27 -c 27 --csv --log-file gpurun_out/fused_metrics.csv python tools/one_forward.py 2 > gpurun_out/ncu_pairs.log 2>&1
-# full captures: the heaviest fused step (stage 1, k = 11) and the heaviest whole-ResBlock launch (stage 2, k = 11)
-ncu --set full --clock-control none --import-source on -k regex:pair_tc_kernel -s 33 -c 1 -o gpurun_out/prof_pair_stage1 python tools/one_forward.py 2 > gpurun_out/ncu_full.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:res_tc_kernel -s 11 -c 1 -o gpurun_out/prof_res_stage2 python tools/one_forward.py 2 > gpurun_out/ncu_full2.log 2>&1
-du -sh gpurun_out
-tail -n 3 gpurun_out/pytest_all.log; tail -n 2 gpurun_out/smoke.log
-cat gpurun_out/bench_bf16.json
+python tools/one_forward.py 3 > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain.log; exit 1; }
+# launch list of the third forward (34 launches per forward in bf16 mode)
+ncu --metrics gpu__time_duration.sum --clock-control none -s 68 -c 34 --csv --log-file gpurun_out/launches.csv python tools/one_forward.py 3 > gpurun_out/ncu_launch.log 2>&1
+# metrics of the 18 fused-step + 6 whole-ResBlock + 1 time-packed stage launches of the second forward
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,lts__t_bytes.sum,smsp__inst_executed.sum,sm__issue_active.avg.pct_of_peak_sustained_elapsed,launch__registers_per_thread,launch__shared_mem_per_block_dynamic,launch__grid_size --clock-control none -k "regex:pair_tc_kernel|res_tc_kernel|respk_tc_kernel" -s 25 -c 25 --csv --log-file gpurun_out/fused_metrics.csv python tools/one_forward.py 2 > gpurun_out/ncu_fused.log 2>&1
+# small kernels: front end, upsamplers, head
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,lts__t_bytes.sum,sm__issue_active.avg.pct_of_peak_sustained_elapsed,launch__registers_per_thread,launch__grid_size --clock-control none -k "regex:conv_tc_kernel|post_kernel|cond_multi_kernel|spk_project_kernel" -s 9 -c 9 --csv --log-file gpurun_out/small_metrics.csv python tools/one_forward.py 2 > gpurun_out/ncu_small.log 2>&1
+# full captures: heaviest fused step (stage 1, k = 11), the time-packed stage kernel (C = 32), an upsampler (ups.1), the head
+ncu --set full --clock-control none --import-source on -k regex:pair_tc_kernel -s 33 -c 1 -o gpurun_out/prof_pair_stage1 python tools/one_forward.py 2 > gpurun_out/ncu_full1.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:respk_tc_kernel -s 1 -c 1 -o gpurun_out/prof_respk_stage3 python tools/one_forward.py 2 > gpurun_out/ncu_full2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 8 -c 1 -o gpurun_out/prof_conv_ups1 python tools/one_forward.py 2 > gpurun_out/ncu_full3.log 2>&1
+ncu --set full --clock-control none -k regex:post_kernel -s 1 -c 1 -o gpurun_out/prof_post python tools/one_forward.py 2 > gpurun_out/ncu_full4.log 2>&1
+du -sh gpurun_out; ls gpurun_out
