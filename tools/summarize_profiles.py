@@ -9,7 +9,7 @@ import shutil
 import subprocess
 import sys
 
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
 G, P = "gpurun_out", "profiles"
 
 
@@ -26,48 +26,80 @@ def metric_rows(path):
 
 
 # 1. launch list of one forward
-shutil.copy(os.path.join(G, "launches_final.csv"), os.path.join(P, f"{tag}_launches_one_forward_cfg2_final.csv"))
+shutil.copy(os.path.join(G, "launches.csv"), os.path.join(P, f"{tag}_launches_one_forward_cfg2.csv"))
 
 # 2. per-launch metrics of the fused kernels
 rows = metric_rows(os.path.join(G, "fused_metrics.csv"))
-chans = [256] * 9 + [128] * 9 + [64] * 3 + [32] * 3 + [16] * 3
-ks = [3, 3, 3, 7, 7, 7, 11, 11, 11] * 2 + [3, 7, 11] * 3
-per_launch, per_stage = [], {}
-for r, c, k in zip(rows, chans, ks):
+
+
+def entry(r, **extra):
     t = r["gpu__time_duration.sum"] / 1e3
-    e = {"kernel": r["kernel"], "C": c, "k": k, "us": round(t, 1), "dram_read_MB": round(r["dram__bytes_read.sum"] / 1e6, 1),
+    e = {"kernel": r["kernel"], **extra, "us": round(t, 1), "dram_read_MB": round(r["dram__bytes_read.sum"] / 1e6, 1),
          "dram_write_MB": round(r["dram__bytes_write.sum"] / 1e6, 1), "l2_MB": round(r["lts__t_bytes.sum"] / 1e6, 1),
          "tensor_pipe_active_pct": round(r["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"], 1),
-         "inst_M": round(r["smsp__inst_executed.sum"] / 1e6, 1), "regs": int(r["launch__registers_per_thread"]),
-         "smem_KB": round(r["launch__shared_mem_per_block_dynamic"] / 1024, 1), "grid": int(r["launch__grid_size"])}
+         "issue_active_pct": round(r.get("sm__issue_active.avg.pct_of_peak_sustained_elapsed", 0.0), 1),
+         "regs": int(r["launch__registers_per_thread"]), "grid": int(r["launch__grid_size"])}
+    if "launch__shared_mem_per_block_dynamic" in r:
+        e["smem_KB"] = round(r["launch__shared_mem_per_block_dynamic"] / 1024, 1)
+    return e
+
+
+# launch order of the second forward: with branch-parallel streams the C >= 128 steps interleave across branches, so the
+# (C, k) label comes from the kernel family + order within the family
+per_launch, per_stage = [], {}
+n_pair = 0
+n_res = 0
+for r in rows:
+    kn = r["kernel"]
+    if "pair_tc_kernel" in kn:
+        c = 256 if n_pair < 9 else 128
+        n_pair += 1
+        e = entry(r, C=c, what="fused ResBlock step")
+    elif "respk_tc_kernel" in kn:
+        c = 32
+        e = entry(r, C=c, what="time-packed stage kernel (3 ResBlocks)")
+    else:
+        c = 64 if n_res < 3 else 16
+        k = [3, 7, 11][n_res % 3]
+        n_res += 1
+        e = entry(r, C=c, k=k, what="whole ResBlock")
     per_launch.append(e)
-    s = per_stage.setdefault(f"C={c}", {"launches": 0, "sum_us": 0.0, "dram_read_MB": 0.0, "dram_write_MB": 0.0, "l2_MB": 0.0, "tw": 0.0})
-    s["launches"] += 1; s["sum_us"] += t; s["dram_read_MB"] += e["dram_read_MB"]; s["dram_write_MB"] += e["dram_write_MB"]
-    s["l2_MB"] += e["l2_MB"]; s["tw"] += e["tensor_pipe_active_pct"] * t
-for s in per_stage.values():
-    s["tensor_pipe_active_pct"] = round(s.pop("tw") / s["sum_us"], 1)
-    s["dram_TBps"] = round((s["dram_read_MB"] + s["dram_write_MB"]) / s["sum_us"], 2)   # MB / us = TB/s
+    s_ = per_stage.setdefault(f"C={c}", {"launches": 0, "sum_us": 0.0, "dram_read_MB": 0.0, "dram_write_MB": 0.0, "l2_MB": 0.0, "tw": 0.0})
+    s_["launches"] += 1; s_["sum_us"] += e["us"]; s_["dram_read_MB"] += e["dram_read_MB"]; s_["dram_write_MB"] += e["dram_write_MB"]
+    s_["l2_MB"] += e["l2_MB"]; s_["tw"] += e["tensor_pipe_active_pct"] * e["us"]
+for s_ in per_stage.values():
+    s_["tensor_pipe_active_pct"] = round(s_.pop("tw") / s_["sum_us"], 1)
+    s_["dram_TBps"] = round((s_["dram_read_MB"] + s_["dram_write_MB"]) / s_["sum_us"], 2)   # MB / us = TB/s
     for k in ("sum_us", "dram_read_MB", "dram_write_MB", "l2_MB"):
-        s[k] = round(s[k], 1)
-json.dump({"note": "ncu metrics pass over the 18 fused ResBlock-step launches (C = 256, 128) and the 9 whole-ResBlock launches (C = 64, 32, 16) "
-                   "of one cfg2 forward (16 x 4 s, bf16); cold-cache serialized durations",
+        s_[k] = round(s_[k], 1)
+json.dump({"note": "ncu metrics pass over the 18 fused ResBlock-step launches (C = 256, 128), the 6 whole-ResBlock launches (C = 64, 16) and the "
+                   "time-packed stage launch (C = 32) of one cfg2 forward (16 x 4 s, bf16); cold-cache serialized durations",
            "per_stage": per_stage, "per_launch": per_launch}, open(os.path.join(P, f"{tag}_fused_steps_metrics.json"), "w"), indent=1)
 tot_r = sum(e["dram_read_MB"] for e in per_launch) * 1e6
 tot_w = sum(e["dram_write_MB"] for e in per_launch) * 1e6
-json.dump({"kernel": "pair_tc_kernel + res_tc_kernel (27 launches of one cfg2 forward)", "dram_bytes_read_sum": tot_r, "dram_bytes_write_sum": tot_w,
-           "traffic_bytes_per_launch_avg": (tot_r + tot_w) / len(per_launch),
-           "source": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum over the 27 fused launches (profiles/{tag}_fused_steps_metrics.json); "
-                     f"--set full captures of two of them: profiles/{tag}_ncu_full_pair_stage1.json, profiles/{tag}_ncu_full_res_stage2.json"},
+json.dump({"kernel": f"pair_tc_kernel + res_tc_kernel + respk_tc_kernel ({len(per_launch)} launches of one cfg2 forward)", "dram_bytes_read_sum": tot_r,
+           "dram_bytes_write_sum": tot_w, "traffic_bytes_per_launch_avg": (tot_r + tot_w) / len(per_launch),
+           "source": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum over the {len(per_launch)} fused launches (profiles/{tag}_fused_steps_metrics.json); "
+                     f"--set full captures: profiles/{tag}_ncu_full_pair_stage1.json, profiles/{tag}_ncu_full_respk_stage3.json"},
           open(os.path.join(P, f"{tag}_traffic.json"), "w"), indent=1)
+if os.path.exists(os.path.join(G, "small_metrics.csv")):
+    small = [entry(r) for r in metric_rows(os.path.join(G, "small_metrics.csv"))]
+    for e in small:
+        e["dram_GBps"] = round((e["dram_read_MB"] + e["dram_write_MB"]) / e["us"] * 1e3, 1)
+    json.dump({"note": "front end (spk_project_kernel, cond_multi_kernel), conv_pre + 5 upsamplers (conv_tc_kernel) and the head (post_kernel) of one cfg2 forward",
+               "per_launch": small}, open(os.path.join(P, f"{tag}_small_kernels_metrics.json"), "w"), indent=1)
 
 # 3. the two full captures: headline metrics + hottest instructions
-KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+KEEP = ["sm__issue_active.avg.pct_of_peak_sustained_elapsed", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__inst_executed.avg.per_cycle_elapsed", "smsp__inst_executed.sum",
         "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__grid_size", "launch__occupancy_limit_registers",
         "launch__occupancy_limit_shared_mem", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
-for rep, what in (("prof_pair_stage1", "fused ResBlock step of stage 1 (C=128, k=11, d=1: first step of branch 2)"),
-                  ("prof_res_stage2", "whole-ResBlock kernel of stage 2 (C=64, k=11, dilations 1/3/5)")):
+for rep, what in (("prof_pair_stage1", "a fused ResBlock step of stage 1 (C=128)"),
+                  ("prof_respk_stage3", "time-packed stage kernel of stage 3 (C=32, three ResBlocks k=3/7/11, dilations 1/3/5)"),
+                  ("prof_conv_ups1", "polyphase ConvTranspose1d ups.1 (256 -> 128, k=8, u=4) in conv_tc_kernel"),
+                  ("prof_post", "post_kernel: leaky-ReLU(0.01) -> conv_post -> tanh"),
+                  ("prof_pk16k3", "time-packed kernel, one ResBlock per launch (pk_fuse=0, pk_chan=112): C=16, k=3")):
     path = os.path.join(G, rep + ".ncu-rep")
     if not os.path.exists(path):
         continue
