@@ -159,9 +159,15 @@ class HostPipeline:
 
 
 def _pinned_stack(arrays, dtype):
-    t = torch.empty((len(arrays),) + tuple(arrays[0].shape), dtype=dtype, pin_memory=True)
-    for i, a in enumerate(arrays):
-        t[i].copy_(a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a)))
+    """One pinned (n, ...) tensor from n equal-shaped host arrays: a single torch.stack into pinned memory (the copy runs
+    without the GIL, so the per-GPU host threads do not serialise on it)."""
+    ts = [a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a)) for a in arrays]
+    t = torch.empty((len(ts),) + tuple(ts[0].shape), dtype=dtype, pin_memory=True)
+    if ts[0].dtype == dtype:
+        torch.stack(ts, out=t)
+    else:
+        for i, a in enumerate(ts):
+            t[i].copy_(a)
     return t
 
 
@@ -210,8 +216,9 @@ class MultiGpuVocoder:
                 pending.append((grp, wav, pipe.submit(code, mel, spk, wav), (code, mel, spk)))
             for grp, wav, done, _keep in pending:
                 done.synchronize()
+                w = wav.numpy()                      # views of the pinned result buffer (kept alive by the views)
                 for j, i in enumerate(grp):
-                    out[i] = wav[j].numpy().copy()
+                    out[i] = w[j]
             pipe.finish()
             self.g.check_index_errors(dev)          # synchronises this worker's stream only
 
@@ -220,7 +227,38 @@ class MultiGpuVocoder:
             lengths = [int(f["mel"].shape[1]) for f in feats]
             out: list = [None] * len(feats)
             n = len(self.devices)
-            futs = [self._pool.submit(self._worker, k, feats, shard_utterances(lengths, n, k), out) for k in range(n)]
+            order = sorted(range(len(lengths)), key=lambda i: (-lengths[i], i))     # shard_utterances for every rank at once
+            futs = [self._pool.submit(self._worker, k, feats, sorted(order[k::n]), out) for k in range(n)]
+            for f in futs:
+                f.result()
+            return out
+
+    def _batch_worker(self, k: int, code, mel, spk, wav, lo: int, hi: int):
+        dev = self.devices[k]
+        torch.cuda.set_device(dev)
+        with torch.no_grad(), torch.cuda.stream(self._streams[k]):
+            if self._pipes[k] is None:
+                self._pipes[k] = HostPipeline(self.g, dev)
+            pipe = self._pipes[k]
+            for s in range(lo, hi, self.max_batch):
+                e = min(hi, s + self.max_batch)
+                pipe.submit(code[s:e], mel[s:e], spk[s:e], wav[s:e])
+            pipe.finish()
+            self.g.check_index_errors(dev)
+
+    def vocode_batch(self, code: torch.Tensor, mel: torch.Tensor, spkr: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Equal-length utterances already stacked on the host: code (B,U) int64, mel (B,80,T) float32, spkr (B,256)
+        float32 (pinned memory makes the copies asynchronous).  Utterances [k B / n, (k + 1) B / n) go to device k as
+        batches of <= max_batch, straight from slices of the caller's tensors: no host staging at all.  Returns the
+        int16 waveforms (B, 160 T) in a pinned tensor (or `out`)."""
+        with self._call:
+            b = code.shape[0]
+            n = len(self.devices)
+            if out is None:
+                out = torch.empty((b, mel.shape[2] * 160), dtype=torch.int16, pin_memory=True)
+            bounds = [(b * k) // n for k in range(n + 1)]
+            futs = [self._pool.submit(self._batch_worker, k, code, mel, spkr, out, bounds[k], bounds[k + 1])
+                    for k in range(n) if bounds[k + 1] > bounds[k]]
             for f in futs:
                 f.result()
             return out

@@ -649,6 +649,12 @@ def test_in_process_multi_gpu_dispatcher_equals_single_gpu(pkg, weights, devices
             assert len(got) == len(want)
             for a, b in zip(got, want):
                 assert a.dtype == np.int16 and np.array_equal(a, b)
+        # equal-length utterances already stacked on the host: straight from slices of the caller's pinned tensors
+        code, mel, spkr = vo.synthetic_inputs(7, 60, seed=77)
+        wav = mg.vocode_batch(code.pin_memory(), mel.pin_memory(), spkr.pin_memory())
+        for i in range(7):
+            y = g(code=code[i:i + 1].to(DEV), mel=mel[i:i + 1].to(DEV), spkr=spkr[i:i + 1].to(DEV))
+            assert torch.equal(wav[i], (y.squeeze() * 32768.0).clamp(-32768, 32767).to(torch.int16).cpu())
     finally:
         mg.close()
 
