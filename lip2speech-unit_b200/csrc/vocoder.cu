@@ -62,6 +62,8 @@ struct Knobs {
   long long max_ctas = 0;
   long long embed_tap = 0;
   long long layer_events = 0;      // record a cudaEvent pair around every launch of the next forwards
+  long long par_share = 0;         // experiment: with branch_par, two-CTAs-per-SM step kernels launch ONE CTA per SM each, so CTAs of two
+                                   // different branches (k = 3 epilogue-bound, k = 11 MMA-bound) share an SM
   long long branch_par = 1;        // C >= 128 stages: the kernel-size branches of a stage run on parallel streams (graph branches); only the
                                    // last step of a branch waits for the previous branch (running sum).  Fills the wave-quantisation tails.
 };
@@ -462,7 +464,8 @@ int run_pair(l2s_vocoder* v, ConvLayer& c1, ConvLayer& c2, cudaStream_t st, int 
   p.slope = slope;
   p.pf = (int)g_knobs.epi_pf;
   timed_begin(v, st, c1.name + "+c2", 4.0 * c1.cin * c1.cout * c1.k * (double)batch * lin);
-  const int ctas = g_knobs.max_ctas > 0 ? (int)g_knobs.max_ctas : v->num_sms;
+  int ctas = g_knobs.max_ctas > 0 ? (int)g_knobs.max_ctas : v->num_sms;
+  if (g_knobs.par_share && g_knobs.branch_par && g.dual) ctas = (ctas + 1) / 2;   // launch_pair_tc doubles it for dual plans
   PairEpiMaps em{};
   if (g.epi_tma) {
     const int tail_rows = 32 - 2 * g.h2 > 0 ? 32 - 2 * g.h2 : 32;
@@ -1393,6 +1396,7 @@ int l2s_debug_set(const char* key, int64_t value) {
   else if (k == "embed_tap") g_knobs.embed_tap = value;
   else if (k == "layer_events") g_knobs.layer_events = value;
   else if (k == "branch_par") g_knobs.branch_par = value;
+  else if (k == "par_share") g_knobs.par_share = value;
   else return L2S_ERR_INVALID;
   return L2S_OK;
 }
