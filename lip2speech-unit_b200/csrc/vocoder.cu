@@ -1262,7 +1262,7 @@ int32_t l2s_launch_count(l2s_vocoder* v, int32_t batch, int32_t frames) {
 }
 
 const char* l2s_last_error(l2s_vocoder* v) { return v ? v->err.c_str() : "null handle"; }
-const char* l2s_version(void) { return "l2s_vocoder 0.1 (sm_100a)"; }
+const char* l2s_version(void) { return "l2s_vocoder 0.2 (sm_100a)"; }
 
 int l2s_debug_tap(l2s_vocoder* v, const char* name, float* host_dst, int64_t numel) {
   if (!v || !name || !host_dst) return L2S_ERR_INVALID;

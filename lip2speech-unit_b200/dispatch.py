@@ -86,8 +86,9 @@ class HostPipeline:
         self.in_free = [None, None]      # event: the forward that read slot s's device inputs has finished
         self.out_free = [None, None]     # event: the device->host copy of slot s's waveform has finished
         self.bufs = [None, None]         # per slot: (shapes, code, mel, spk, out) device buffers, allocated once per shape
+        self.mel_cm = [None, None]       # per slot: channel-major mel when the caller hands time-major frames
 
-    def _allocate(self, s, shapes, code_h, mel_h, spk_h, out_h, main):
+    def _allocate(self, s, shapes, code_h, mel_h, spk_h, out_h, main, time_major=False):
         # a new shape: retire the old buffers first.  Only this pipeline's own work is waited for -- a device-wide
         # synchronize here could collide with another host thread that is capturing a CUDA graph on the same device.
         for ev in (self.in_free[s], self.out_free[s]):
@@ -96,6 +97,9 @@ class HostPipeline:
         with torch.cuda.device(self.device):
             bufs = (torch.empty_like(code_h, device=self.device), torch.empty_like(mel_h, device=self.device),
                     torch.empty_like(spk_h, device=self.device), torch.empty(out_h.shape, dtype=out_h.dtype, device=self.device))
+            # time-major mel (n, T, 80), the layout of the .npy hand-off files: transposed on the device, not by the host
+            self.mel_cm[s] = torch.empty((mel_h.shape[0], mel_h.shape[2], mel_h.shape[1]), dtype=torch.float32,
+                                         device=self.device) if time_major else None
         # The blocks come from the allocating (main) stream's pool but are written on s_in and read on s_out: tell the
         # caching allocator, and make both copy streams wait until main has reached the allocation point (a recycled
         # block may still be in use by kernels queued on main).
@@ -110,15 +114,17 @@ class HostPipeline:
         self.in_free[s] = self.out_free[s] = None
 
     @torch.no_grad()
-    def submit(self, code_h, mel_h, spk_h, out_h):
+    def submit(self, code_h, mel_h, spk_h, out_h, mel_time_major: bool = False):
+        """mel_time_major: mel_h is (B, T, num_mels) as the hand-off files store it; the (B, num_mels, T) the generator takes
+        is made on the device (a 4 MB transpose kernel instead of a strided host copy per utterance)."""
         s = self.slot
         self.slot ^= 1
         main = torch.cuda.current_stream(self.device)
         if out_h.dtype not in (torch.float32, torch.int16):
             raise TypeError("out_h must be float32 (B,1,L) or int16 (B,L)")
-        shapes = (tuple(code_h.shape), tuple(mel_h.shape), tuple(spk_h.shape), mel_h.dtype, tuple(out_h.shape), out_h.dtype)
+        shapes = (tuple(code_h.shape), tuple(mel_h.shape), tuple(spk_h.shape), mel_h.dtype, tuple(out_h.shape), out_h.dtype, mel_time_major)
         if self.bufs[s] is None or self.bufs[s][0] != shapes:
-            self._allocate(s, shapes, code_h, mel_h, spk_h, out_h, main)
+            self._allocate(s, shapes, code_h, mel_h, spk_h, out_h, main, mel_time_major)
         _, code, mel, spk, out = self.bufs[s]
         with torch.cuda.stream(self.s_in):
             if self.in_free[s] is not None:
@@ -131,6 +137,9 @@ class HostPipeline:
         main.wait_event(ready)
         if self.out_free[s] is not None:
             main.wait_event(self.out_free[s])                  # the slot's previous waveform has left the device
+        if mel_time_major:
+            self.mel_cm[s].copy_(mel.transpose(1, 2))
+            mel = self.mel_cm[s]
         if out.dtype == torch.int16:
             self.g.forward_int16_into(out, code=code, mel=mel, spkr=spk)
         else:

@@ -232,7 +232,7 @@ def _plan_groups(rows, max_batch: int, first: int = 8):
 
 def _load_group(dataset_dir: str, rows, idxs, code_dict, pin: bool = True):
     """Read the .npy files of rows[idxs], apply the trimming rule, and stack rows of equal exact length into (pinned)
-    batch tensors: [(items, code (n,U) int64, mel (n,80,T) float32, spkr (n,256) float32, wav (n,160 T) int16 buffer)]
+    batch tensors: [(items, code (n,U) int64, mel (n,T,80) float32 TIME-MAJOR, spkr (n,256) float32, wav (n,160 T) int16 buffer)]
     with items[k] = (row index, ..., samples to keep)."""
     items = []
     for i in idxs:
@@ -253,12 +253,12 @@ def _load_group(dataset_dir: str, rows, idxs, code_dict, pin: bool = True):
         n = len(grp)
         mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=pin)      # noqa: E731
         code = mk((n, grp[0][1].shape[0]), torch.int64)
-        mel = mk((n, grp[0][2].shape[1], t), torch.float32)
+        mel = mk((n, t, grp[0][2].shape[1]), torch.float32)      # time-major as on disk; (80, T) (dataset_multi_input.py:243) is made on the device
         spk = mk((n, grp[0][3].shape[0]), torch.float32)
         code_np, mel_np, spk_np = code.numpy(), mel.numpy(), spk.numpy()
         for k, (_, c, m, s_, _) in enumerate(grp):
             code_np[k] = c
-            mel_np[k] = m.T                            # (T, 80) on disk -> (80, T), dataset_multi_input.py:243
+            mel_np[k] = m
             spk_np[k] = s_
         wav = mk((n, t * 160), torch.int16)
         out.append((grp, code, mel, spk, wav))
@@ -267,7 +267,7 @@ def _load_group(dataset_dir: str, rows, idxs, code_dict, pin: bool = True):
 
 @torch.no_grad()
 def serve_vocoder_request(generator, dataset_dir: str, out_dir: str, split: str = "test", device="cuda", max_batch: int = 32,
-                          io_threads: int = 2, code_dict_path: Optional[str] = None) -> List[str]:
+                          io_threads: int = 2, code_dict_path: Optional[str] = None, first_group: int = 8) -> List[str]:
     """One /vocoder request of the stage-2 service, batched and overlapped.
 
     The reference handler (multi_input_vocoder/inference_server.py:207-213) re-parses <dataset_dir>/label/<split>.tsv,
@@ -305,14 +305,14 @@ def serve_vocoder_request(generator, dataset_dir: str, out_dir: str, split: str 
             with open(paths[i], "wb") as f:
                 f.write(_wav_header(n) + w[k, :n].tobytes())
 
-    groups = _plan_groups(rows, max_batch)
+    groups = _plan_groups(rows, max_batch, first_group)
     pipe = HostPipeline(generator, dev)
     with ThreadPoolExecutor(max_workers=max(2, io_threads)) as pool:
         loads = [pool.submit(load_group, g_) for g_ in groups]               # later groups load while earlier ones run
         writers = []
         for fut in loads:
             for grp, code, mel, spk, wav in fut.result():
-                done = pipe.submit(code, mel, spk, wav)
+                done = pipe.submit(code, mel, spk, wav, mel_time_major=True)
                 writers.append(pool.submit(write_group, done, wav, grp))     # wav files written while later groups run
         for w in writers:
             w.result()

@@ -87,4 +87,18 @@ with tempfile.TemporaryDirectory() as root:
                 torch.cuda.synchronize(); best = min(best, time.perf_counter() - t0)
         sweep[str(nt)] = round(total_s / best, 1)
     res["serve_vocoder_request_io_threads_sweep_audio_s_per_s"] = sweep
+    sweep2 = {}
+    for mb, fg, nt in ((32, 8, 2), (64, 8, 2), (64, 16, 2), (32, 4, 2), (16, 8, 2), (64, 8, 3), (32, 32, 2)):
+        def run(out):
+            ho.serve_vocoder_request(g, root, out, device=dev, max_batch=mb, first_group=fg, io_threads=nt)
+        with tempfile.TemporaryDirectory() as out:
+            run(out)
+        best = 1e9
+        for _ in range(4):
+            with tempfile.TemporaryDirectory() as out:
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                run(out)
+                torch.cuda.synchronize(); best = min(best, time.perf_counter() - t0)
+        sweep2[f"max_batch={mb},first={fg},threads={nt}"] = round(total_s / best, 1)
+    res["serve_vocoder_request_sweep_audio_s_per_s"] = sweep2
     print(json.dumps(res))
