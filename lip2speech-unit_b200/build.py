@@ -8,8 +8,8 @@ link.  nvcc cross-compiles without a GPU; the built .so travels to the GPU box w
 git-ignored, not gpurun-ignored).
 """
 import concurrent.futures
+import hashlib
 import os
-import re
 import subprocess
 import sys
 
@@ -40,19 +40,52 @@ def _deps_of(src):
     return [p for p in files if not p.startswith(("/usr/", "/opt/"))] + [src, os.path.abspath(__file__)]
 
 
+def _digest(src, deps):
+    """Content hash of everything the object depends on (sources, headers, flags, this script): a copied tree whose
+    modification times were not preserved (a snapshot sent to the GPU box, a fresh checkout next to cached objects) must
+    not trigger -- or miss -- a rebuild."""
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for d in sorted(set(os.path.abspath(x) for x in deps)):
+        h.update(os.path.relpath(d, HERE).encode())
+        try:
+            with open(d, "rb") as f:
+                h.update(f.read())
+        except OSError:
+            h.update(b"<missing>")
+    return h.hexdigest()
+
+
+def _stamp(src):
+    return _obj(src)[:-2] + ".stamp"
+
+
 def _stale(src) -> bool:
     deps = _deps_of(src)
-    if deps is None:
+    if deps is None or not os.path.exists(_stamp(src)):
         return True
-    t = os.path.getmtime(_obj(src))
-    return any((not os.path.exists(d)) or os.path.getmtime(d) > t for d in deps)
+    with open(_stamp(src)) as f:
+        return f.read().strip() != _digest(src, deps)
+
+
+def _lib_stamp():
+    return os.path.join(OBJ_DIR, "lib.stamp")
+
+
+def _lib_digest():
+    h = hashlib.sha256()
+    for s_ in _sources():
+        with open(_stamp(s_)) as f:
+            h.update(f.read().encode())
+    return h.hexdigest()
 
 
 def needs_build() -> bool:
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(LIB_PATH) or not os.path.exists(_lib_stamp()):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    return any(_stale(s) or os.path.getmtime(_obj(s)) > t for s in _sources())
+    if any(_stale(s) for s in _sources()):
+        return True
+    with open(_lib_stamp()) as f:
+        return f.read().strip() != _lib_digest()
 
 
 def _compile(src, nvcc, verbose):
@@ -71,12 +104,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
         for src, cmd, proc in pool.map(lambda s: _compile(s, nvcc, verbose), todo):
             if proc.returncode != 0:
                 raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+            with open(_stamp(src), "w") as f:
+                f.write(_digest(src, _deps_of(src)))
             if verbose:
                 sys.stderr.write(proc.stderr)
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + [_obj(s) for s in _sources()]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    with open(_lib_stamp(), "w") as f:
+        f.write(_lib_digest())
     return LIB_PATH
 
 
