@@ -45,12 +45,18 @@ def _digest(src, deps):
     modification times were not preserved (a snapshot sent to the GPU box, a fresh checkout next to cached objects) must
     not trigger -- or miss -- a rebuild."""
     h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
-    for d in sorted(set(os.path.abspath(x) for x in deps)):
-        h.update(os.path.relpath(d, HERE).encode())
-        try:
-            with open(d, "rb") as f:
-                h.update(f.read())
-        except OSError:
+    # the .d file holds the absolute paths of the build that wrote it; the tree may since have moved (the GPU box runs a
+    # copy under another root): files are looked up by NAME under csrc/ and include/
+    names = sorted(set(os.path.basename(x) for x in deps))
+    for name in names:
+        h.update(name.encode())
+        for base in (CSRC, os.path.join(HERE, "..", "include"), HERE):
+            path = os.path.join(base, name)
+            if os.path.exists(path):
+                with open(path, "rb") as f:
+                    h.update(f.read())
+                break
+        else:
             h.update(b"<missing>")
     return h.hexdigest()
 
