@@ -678,3 +678,26 @@ def test_serve_vocoder_request_equals_per_utterance_flow(pkg, weights, tmp_path)
         ref_path = os.path.join(str(tmp_path), "ref.wav")
         wavfile.write(ref_path, 16000, expect[:n])
         assert open(pth, "rb").read() == open(ref_path, "rb").read()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("pk_chan", [0, 16 | 32 | 64])
+def test_unusual_resblock_config(pkg, precision, pk_chan):
+    """A config far from the shipped one: kernel sizes 5 / 9 (the run-time MMA issue path of the time-packed kernel: its
+    immediate-operand path covers k = 3 / 7 / 11), two dilations per ResBlock, even dilations (phase-major layouts with
+    d = 2 / 4), different dilation lists per branch (so the branches of a stage cannot share one launch), rates [4,4,2].
+    With and without the time-packed kernel, against the oracle."""
+    h = vo.shipped_config(upsample_rates=[4, 4, 2], upsample_kernel_sizes=[8, 8, 4], upsample_initial_channel=128,
+                          resblock_kernel_sizes=[5, 9], resblock_dilation_sizes=[[1, 2], [2, 4]])
+    sd = vo.init_state_dict(h, seed=11, style="trained")
+    code, mel, spkr = vo.synthetic_inputs(3, 46, seed=19)
+    ref = vo.mel_code_generator_forward(vo.fold_weight_norm(sd), h, code, mel, spkr)
+    g = make_gen(pkg, h, sd, precision)
+    lib = pkg._cabi.load()
+    try:
+        lib.l2s_debug_set(b"pk_chan", pk_chan)
+        y = g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV))
+    finally:
+        lib.l2s_debug_set(b"pk_chan", 32)
+    assert y.shape == (3, 1, 32 * 46)
+    check(ref, y, precision, f"k = 5 / 9, dilations [1,2] / [2,4], pk_chan {pk_chan}")
