@@ -335,8 +335,10 @@ __device__ __forceinline__ void res_issue_stage(bool leader, int msub, uint32_t 
 // thread issues cta_group::2 MMAs (M = 256: both tiles), each CTA loads HALF of every weight stage and keeps its own
 // X / D1 / S; barriers the MMA thread waits on live in the leader and collect both CTAs' arrivals, its commits are
 // multicast to both.  (Own instantiation: a kernel that contains cta_group::2 code cannot be launched without a cluster.)
-template <int MODE, bool DUAL, bool CG2 = false>
-__global__ void __maxnreg__(DUAL ? 80 : 168)
+// WIDE: one CTA per SM with SIXTEEN epilogue warps (four per TMEM lane quadrant, 576 threads, 96 registers: 18 warps put five on one scheduler, whose 16 K registers then bound the count): MMA and
+// epilogue phases of a one-CTA-per-SM plan strictly alternate, so halving every phase's latency shortens the tile's chain.
+template <int MODE, bool DUAL, bool CG2 = false, bool WIDE = false>
+__global__ void __maxnreg__(DUAL ? 80 : (WIDE ? 96 : 168))
 res_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
   extern __shared__ uint8_t smem_raw[];
   const ConvParams& p = P.c;
@@ -541,8 +543,8 @@ res_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
       }
       // ---- output: X -> global (rows [q0, q0 + r_out) of the tile only)
       const int row_lim = dummy ? 0 : min(p.lin, q0 + g.r_out);
-      if (g.c % CW == 0) res_output<CW, MODE, !DUAL>(p, tile, x_quad, b, t_row0, q0, row_lim, g.msub, g.c, w, d_full, pd);
-      else res_output<16, MODE, !DUAL>(p, tile, x_quad, b, t_row0, q0, row_lim, g.msub, g.c, w, d_full, pd);
+      if (g.c % CW == 0) res_output<CW, MODE, !DUAL && !WIDE>(p, tile, x_quad, b, t_row0, q0, row_lim, g.msub, g.c, w, d_full, pd);
+      else res_output<16, MODE, !DUAL && !WIDE>(p, tile, x_quad, b, t_row0, q0, row_lim, g.msub, g.c, w, d_full, pd);
       pd ^= 1u;
       L2S_RTRACE(0, ntr);
       tc_fence_before();
@@ -560,6 +562,7 @@ res_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
 
 // ------------------------------------------------------------------ host side
 
+inline int g_res_wide = 1;  // knob res_wide: one-CTA-per-SM plans use sixteen epilogue warps (WIDE kernels)
 inline int g_res_cg2 = 4;   // whole-ResBlock plans run as CTA pairs issuing cta_group::2 MMAs (knob res_cg2: 0 off, 1 one-CTA-per-SM
                             // plans only, 2 + dual, 3 + quad, 4 + C = 16)
 
@@ -594,7 +597,7 @@ inline bool res_plan_with(int c, int k, int n_dil, const int* dil, int lin, int 
   while (cols < 2 * msub * c) cols <<= 1;
   if (cols > (kind == 2 ? 128 : (dual ? 256 : 512))) return false;
   g.tmem_cols = cols;
-  g.ne = kind == 2 ? 4 : kTcEpiWarps;
+  g.ne = kind == 2 ? 4 : ((kind == 0 && g_res_wide) ? 16 : kTcEpiWarps);
   g.ctas_per_sm = kind == 2 ? 4 : (dual ? 2 : 1);
   int tb = 1;
   while (tb < k && tb < 16 && (tb * 2) * c * g.rb <= 16384) tb *= 2;
@@ -658,15 +661,15 @@ inline bool res_plan(int c, int k, int n_dil, const int* dil, int lin, int batch
   return true;
 }
 
-template <int MODE, bool DUAL, bool CG2 = false>
+template <int MODE, bool DUAL, bool CG2 = false, bool WIDE = false>
 inline cudaError_t launch_res_mode(const ResParams& P, const ResMaps& maps, int grid, cudaStream_t stream) {
   static bool configured[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(res_tc_kernel<MODE, DUAL, CG2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(res_tc_kernel<MODE, DUAL, CG2, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(res_tc_kernel<MODE, DUAL, CG2>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(res_tc_kernel<MODE, DUAL, CG2, WIDE>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     configured[dev] = true;
@@ -683,7 +686,7 @@ inline cudaError_t launch_res_mode(const ResParams& P, const ResMaps& maps, int 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CG2 ? 1u : 0u;
-  return cudaLaunchKernelEx(&cfg, res_tc_kernel<MODE, DUAL, CG2>, maps, P);
+  return cudaLaunchKernelEx(&cfg, res_tc_kernel<MODE, DUAL, CG2, WIDE>, maps, P);
 }
 
 // Defined in tu_res_tc.cu (the only translation unit that instantiates res_tc_kernel); declared everywhere else.
@@ -706,6 +709,7 @@ cudaError_t launch_res_tc(const ResParams& P, const ResMaps& maps, int num_ctas,
   switch (mode) {
 #define L2S_RMODE(m)                                                                                        \
   case m:                                                                                                   \
+    if (g.ne == 16) return g.cg2 ? launch_res_mode<m, false, true, true>(P, maps, grid, stream) : launch_res_mode<m, false, false, true>(P, maps, grid, stream); \
     if (g.cg2) return g.dual ? launch_res_mode<m, true, true>(P, maps, grid, stream) : launch_res_mode<m, false, true>(P, maps, grid, stream); \
     return g.dual ? launch_res_mode<m, true>(P, maps, grid, stream) : launch_res_mode<m, false>(P, maps, grid, stream);
     L2S_RMODE(4) L2S_RMODE(6) L2S_RMODE(8) L2S_RMODE(10) L2S_RMODE(12) L2S_RMODE(14)

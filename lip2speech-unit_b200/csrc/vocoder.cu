@@ -1370,6 +1370,7 @@ int l2s_debug_set(const char* key, int64_t value) {
   else if (k == "res_single_pct") g_res_single_pct = (int)value;
   else if (k == "res_quad_pct") g_res_quad_pct = (int)value;
   else if (k == "res_cg2") g_res_cg2 = (int)value;
+  else if (k == "res_wide") g_res_wide = (int)value;
   else if (k == "pack") g_pk_on = (int)value;
   else if (k == "pk_mode") g_pk_mode = (int)value;
   else if (k == "pk_cg2") g_pk_cg2 = (int)value;
