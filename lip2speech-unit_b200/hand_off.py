@@ -26,6 +26,11 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 import torch
 
+try:
+    from . import _cabi
+except ImportError:                                       # top-level module use (see models_multi_input.py)
+    import _cabi
+
 CODE_HOP, MEL_HOP, SAMPLE_RATE = 320, 160, 16000
 
 
@@ -230,21 +235,8 @@ def _plan_groups(rows, max_batch: int, first: int = 8):
     return groups
 
 
-def _load_group(dataset_dir: str, rows, idxs, code_dict, pin: bool = True):
-    """Read the .npy files of rows[idxs], apply the trimming rule, and stack rows of equal exact length into (pinned)
-    batch tensors: [(items, code (n,U) int64, mel (n,T,80) float32 TIME-MAJOR, spkr (n,256) float32, wav (n,160 T) int16 buffer)]
-    with items[k] = (row index, ..., samples to keep)."""
-    items = []
-    for i in idxs:
-        row = rows[i]
-        audio_path = os.path.join(dataset_dir, row.audio_rel)
-        mel = _read_npy(audio_path.replace("/audio/", "/mel/")[:-4] + ".npy")
-        spk = _read_npy(audio_path.replace("/audio/", "/spk_emb/")[:-4] + ".npy")
-        if spk.shape != (256,) or spk.dtype != np.float32:      # helpers.py:194 / create_dataset.py:229
-            raise ValueError(f"{row.uid}: speaker embedding must be (256,) float32, got {spk.shape} {spk.dtype}")
-        code = np.asarray(code_to_sequence(row.units.split(), code_dict), dtype=np.int64)
-        u, t, cut = trim_lengths(row.n_audio, code.shape[0], mel.shape[0])
-        items.append((i, code[:u], mel[:t], spk, cut))
+def _stack_group(items, pin: bool):
+    """items = [(row index, code, mel (t, bins), spk, cut)] -> one batch per exact length (see _load_group)."""
     by_t: Dict[int, list] = {}
     for it in items:                                  # exact lengths may differ inside a group: split it
         by_t.setdefault(it[2].shape[0], []).append(it)
@@ -265,9 +257,94 @@ def _load_group(dataset_dir: str, rows, idxs, code_dict, pin: bool = True):
     return out
 
 
+def _load_group_python(dataset_dir: str, rows, idxs, code_dict, pin: bool = True):
+    """_load_group through numpy, one file at a time: the path for anything the native reader declines (Fortran order,
+    other dtypes, wrong shapes -- with the reference's own error messages)."""
+    items = []
+    for i in idxs:
+        row = rows[i]
+        audio_path = os.path.join(dataset_dir, row.audio_rel)
+        mel = _read_npy(audio_path.replace("/audio/", "/mel/")[:-4] + ".npy")
+        spk = _read_npy(audio_path.replace("/audio/", "/spk_emb/")[:-4] + ".npy")
+        if spk.shape != (256,) or spk.dtype != np.float32:      # helpers.py:194 / create_dataset.py:229
+            raise ValueError(f"{row.uid}: speaker embedding must be (256,) float32, got {spk.shape} {spk.dtype}")
+        code = np.asarray(code_to_sequence(row.units.split(), code_dict), dtype=np.int64)
+        u, t, cut = trim_lengths(row.n_audio, code.shape[0], mel.shape[0])
+        items.append((i, code[:u], mel[:t], spk, cut))
+    return _stack_group(items, pin)
+
+
+def _c_paths(paths):
+    import ctypes as C
+    return (C.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
+
+
+def _load_group(dataset_dir: str, rows, idxs, code_dict, pin: bool = True, num_mels: int = 80, native_threads: int = 4):
+    """Read the .npy files of rows[idxs], apply the trimming rule, and stack rows of equal exact length into (pinned)
+    batch tensors: [(items, code (n,U) int64, mel (n,T,80) float32 TIME-MAJOR, spkr (n,256) float32, wav (n,160 T) int16 buffer)]
+    with items[k] = (row index, ..., samples to keep).
+
+    The files of the group are read by ONE native call each for mel/ and spk_emb/ (l2s_io_read_npy_f32: native_threads
+    host threads, straight into the pinned batch tensors, float16 widened on the fly); a file the native reader declines
+    sends the whole group through _load_group_python."""
+    import ctypes as C
+    lib = _cabi.load()
+    n = len(idxs)
+    if n == 0:
+        return []
+    audio = [os.path.join(dataset_dir, rows[i].audio_rel) for i in idxs]
+    cap = np.asarray([rows[i].n_audio // MEL_HOP for i in idxs], dtype=np.int32)      # frames the trimming rule can keep at most
+    t_max = int(cap.max())
+    mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=pin)      # noqa: E731
+    mel = mk((n, max(t_max, 1), num_mels), torch.float32)
+    spk = mk((n, 256), torch.float32)
+    got = np.zeros(n, dtype=np.int32)
+    one = np.ones(n, dtype=np.int32)
+    ip = C.POINTER(C.c_int32)
+    st = lib.l2s_io_read_npy_f32(_c_paths([a.replace("/audio/", "/mel/")[:-4] + ".npy" for a in audio]), n, mel.data_ptr(),
+                                 mel.stride(0), cap.ctypes.data_as(ip), num_mels, _cabi.IO_REQUIRE_2D, got.ctypes.data_as(ip),
+                                 native_threads, None)
+    if st == _cabi.IO_OK:
+        got1 = np.zeros(n, dtype=np.int32)
+        st = lib.l2s_io_read_npy_f32(_c_paths([a.replace("/audio/", "/spk_emb/")[:-4] + ".npy" for a in audio]), n, spk.data_ptr(),
+                                     spk.stride(0), one.ctypes.data_as(ip), 256, _cabi.IO_REQUIRE_1D | _cabi.IO_REQUIRE_F32,
+                                     got1.ctypes.data_as(ip), native_threads, None)
+    if st != _cabi.IO_OK:
+        return _load_group_python(dataset_dir, rows, idxs, code_dict, pin)
+    codes, keep = [], []
+    for k, i in enumerate(idxs):
+        ids = code_to_sequence(rows[i].units.split(), code_dict)
+        u, t, cut = trim_lengths(rows[i].n_audio, len(ids), int(got[k]))
+        codes.append(ids[:u])
+        keep.append((u, t, cut))
+    if all(kp[:2] == keep[0][:2] for kp in keep) and keep[0][1] == t_max and t_max > 0:
+        # the usual case: every row of the group keeps the same number of frames -- the tensors just read ARE the batch
+        code = mk((n, keep[0][0]), torch.int64)
+        code.numpy()[:] = np.asarray(codes, dtype=np.int64).reshape(n, keep[0][0])
+        wav = mk((n, t_max * MEL_HOP), torch.int16)
+        grp = [(i, None, None, None, keep[k][2]) for k, i in enumerate(idxs)]
+        return [(grp, code, mel, spk, wav)]
+    mel_np, spk_np = mel.numpy(), spk.numpy()
+    items = [(i, np.asarray(codes[k], dtype=np.int64), mel_np[k, :keep[k][1]], spk_np[k], keep[k][2]) for k, i in enumerate(idxs)]
+    return _stack_group(items, pin)
+
+
+def _write_group_native(paths, wav: torch.Tensor, n_samples, native_threads: int = 4):
+    """wav (n, S) int16 host tensor -> n RIFF files (l2s_io_write_wav_i16; bytes as scipy.io.wavfile.write, inference.py:164)."""
+    import ctypes as C
+    lib = _cabi.load()
+    ns = np.asarray(n_samples, dtype=np.int32)
+    bad = C.c_int32(-1)
+    st = lib.l2s_io_write_wav_i16(_c_paths(paths), len(paths), wav.data_ptr(), wav.stride(0), ns.ctypes.data_as(C.POINTER(C.c_int32)),
+                                  SAMPLE_RATE, native_threads, C.byref(bad))
+    if st != _cabi.IO_OK:
+        raise OSError(f"could not write {paths[bad.value] if 0 <= bad.value < len(paths) else 'wav files'} (status {st})")
+
+
 @torch.no_grad()
 def serve_vocoder_request(generator, dataset_dir: str, out_dir: str, split: str = "test", device="cuda", max_batch: int = 32,
-                          io_threads: int = 2, code_dict_path: Optional[str] = None, first_group: int = 8) -> List[str]:
+                          io_threads: int = 2, code_dict_path: Optional[str] = None, first_group: int = 8,
+                          native_threads: int = 4) -> List[str]:
     """One /vocoder request of the stage-2 service, batched and overlapped.
 
     The reference handler (multi_input_vocoder/inference_server.py:207-213) re-parses <dataset_dir>/label/<split>.tsv,
@@ -276,8 +353,10 @@ def serve_vocoder_request(generator, dataset_dir: str, out_dir: str, split: str 
       * the manifest and the unit dictionary are parsed once;
       * rows are grouped by the frame count the manifest implies (<= max_batch per group); io_threads host threads read
         the .npy files of the NEXT groups while the GPU works on the current one, and write the wav files of finished
-        groups (the file I/O was 58 % of the job when done inline).  Two threads measured best on the B200 box (the
-        per-file work is interpreter-bound: 16.5 k audio-s/s with 2 threads, 12.3 k with 16);
+        groups (the file I/O was 58 % of the job when done inline).  The per-file work itself is native: each of those
+        threads hands a whole group to l2s_io_read_npy_f32 / l2s_io_write_wav_i16 (include/l2s_hand_off.h), which run it
+        on native_threads host threads outside the interpreter (done per file in Python the job was interpreter-bound:
+        16.5 k audio-s/s with 2 Python threads, 12.3 k with 16);
       * rows of a group whose exact lengths agree share a forward; inputs and int16 waveforms move through
         dispatch.HostPipeline (copies overlapped with the forward, int16 made on the device).
     `dataset_dir` replaces the absolute root in the manifest's first line (create_dataset.vocoder() writes the dataset
@@ -295,15 +374,14 @@ def serve_vocoder_request(generator, dataset_dir: str, out_dir: str, split: str 
     for d in {os.path.dirname(p) for p in paths}:
         os.makedirs(d, exist_ok=True)
 
+    num_mels = int(getattr(getattr(generator, "h", None), "num_mels", 80) or 80)
+
     def load_group(idxs):
-        return _load_group(dataset_dir, rows, idxs, code_dict, pin=True)
+        return _load_group(dataset_dir, rows, idxs, code_dict, pin=True, num_mels=num_mels, native_threads=native_threads)
 
     def write_group(done, wav, grp):
         done.synchronize()
-        w = wav.numpy()
-        for k, (i, _, _, _, n) in enumerate(grp):
-            with open(paths[i], "wb") as f:
-                f.write(_wav_header(n) + w[k, :n].tobytes())
+        _write_group_native([paths[it[0]] for it in grp], wav, [it[4] for it in grp], native_threads)
 
     groups = _plan_groups(rows, max_batch, first_group)
     pipe = HostPipeline(generator, dev)

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_exports_every_declared_symbol(pkg):
     lib = pkg._cabi.load()
     text = ""
-    for name in ("l2s_vocoder.h", "l2s_debug.h"):       # the drop-in boundary + the test hooks
+    for name in ("l2s_vocoder.h", "l2s_debug.h", "l2s_hand_off.h"):       # the drop-in boundary, the test hooks, the hand-off file I/O
         with open(os.path.join(ROOT, "include", name)) as f:
             text += f.read()
     declared = set(re.findall(r"\b(l2s_[a-z0-9_]+)\s*\(", text))

@@ -69,3 +69,123 @@ def test_stage1_mel_deinterleave_matches_reference_expression(pkg):
     y = pkg.hand_off.stage1_mel_to_frames(x)
     assert y.shape == (2, 6, 80)
     assert torch.equal(y[:, 0::2], x[:, :, 0::2]) and torch.equal(y[:, 1::2], x[:, :, 1::2])
+
+
+def _groups_equal(a, b):
+    assert len(a) == len(b)
+    for (ga, ca, ma, sa, wa), (gb, cb, mb, sb, wb) in zip(a, b):
+        assert [it[0] for it in ga] == [it[0] for it in gb] and [it[4] for it in ga] == [it[4] for it in gb]
+        assert ca.dtype == cb.dtype and ma.dtype == mb.dtype and sa.dtype == sb.dtype
+        assert np.array_equal(ca.numpy(), cb.numpy()) and np.array_equal(ma.numpy(), mb.numpy()) and np.array_equal(sa.numpy(), sb.numpy())
+        assert wa.shape == wb.shape and wa.dtype == wb.dtype
+
+
+def test_native_group_loader_matches_numpy_on_the_lrs3_rows(pkg):
+    """l2s_io_read_npy_f32 (include/l2s_hand_off.h) against np.load + the Python collate, on the shipped sample rows:
+    one group per row (lengths differ) and all rows in one group (the loader must split it by exact length)."""
+    ho = pkg.hand_off
+    _, rows = ho.parse_manifest(os.path.join(FIX, "label", "test.tsv"))
+    cd = ho.load_code_dict(os.path.join(FIX, "label", "dict.unt.txt"))
+    for idxs in ([0], [1], [4], [0, 1, 2, 3, 4]):
+        nat = ho._load_group(FIX, rows, idxs, cd, pin=False)
+        ref = ho._load_group_python(FIX, rows, idxs, cd, pin=False)
+        _groups_equal(sorted(nat, key=lambda g: g[2].shape[1]), sorted(ref, key=lambda g: g[2].shape[1]))
+    one = ho._load_group(FIX, rows, [0], cd, pin=False)[0]
+    assert tuple(one[2].shape) == (1, 428, 80) and tuple(one[1].shape) == (1, 214) and one[0][0][4] == 68480
+
+
+def _write_dataset(root, specs, mel_dtype=np.float32, spk=None, fortran=False):
+    """specs = [(frames on disk, n_audio)] -> a dataset in the reference's layout under root; returns the mel arrays."""
+    os.makedirs(os.path.join(root, "label"))
+    with open(os.path.join(root, "label", "dict.unt.txt"), "w") as f:
+        f.writelines(f"{i} 1\n" for i in range(200))
+    rng = np.random.default_rng(3)
+    tsv, unt, mels = [root + "\n"], [], []
+    for i, (frames, n_audio) in enumerate(specs):
+        rel = f"audio/test/s{i % 2}/{i:03d}.wav"
+        mel = rng.standard_normal((frames, 80)).astype(mel_dtype)
+        emb = rng.standard_normal(256).astype(np.float32) if spk is None else spk
+        for sub, arr in (("mel", np.asfortranarray(mel) if fortran else mel), ("spk_emb", emb)):
+            path = os.path.join(root, rel.replace("audio/", sub + "/")[:-4] + ".npy")
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            np.save(path, arr)
+        nv = n_audio // 640
+        tsv.append(f"test/s{i % 2}/{i:03d}\tv.mp4\t{rel}\t{nv}\t{n_audio}\n")
+        unt.append(" ".join(str(int(c)) for c in rng.integers(0, 200, 2 * nv)) + "\n")
+        mels.append(mel)
+    open(os.path.join(root, "label", "test.tsv"), "w").writelines(tsv)
+    open(os.path.join(root, "label", "test.unt"), "w").writelines(unt)
+    return mels
+
+
+def test_native_group_loader_equal_lengths_fp16_and_fallbacks(pkg, tmp_path):
+    ho = pkg.hand_off
+    # equal lengths: the tensors the native reader filled are the batch itself; longer files are cut at n_audio // 160
+    root = str(tmp_path / "a")
+    mels = _write_dataset(root, [(400, 64000), (403, 64000), (400, 64000)])
+    _, rows = ho.parse_manifest(os.path.join(root, "label", "test.tsv"))
+    cd = ho.load_code_dict(os.path.join(root, "label", "dict.unt.txt"))
+    nat = ho._load_group(root, rows, [0, 1, 2], cd, pin=False)
+    assert len(nat) == 1 and tuple(nat[0][2].shape) == (3, 400, 80)
+    assert np.array_equal(nat[0][2].numpy()[1], mels[1][:400])
+    _groups_equal(nat, ho._load_group_python(root, rows, [0, 1, 2], cd, pin=False))
+    # float16 on disk is widened exactly (including subnormals, zeros, infinities)
+    root = str(tmp_path / "b")
+    mels = _write_dataset(root, [(200, 32000), (200, 32000)], mel_dtype=np.float16)
+    special = np.asarray([0.0, -0.0, 5.96e-8, -6.1e-5, 65504.0, np.inf, -np.inf, 1.0009765625], dtype=np.float16)
+    m0 = mels[0].copy(); m0[0, :8] = special
+    np.save(os.path.join(root, "mel", "test", "s0", "000.npy"), m0)
+    _, rows = ho.parse_manifest(os.path.join(root, "label", "test.tsv"))
+    nat = ho._load_group(root, rows, [0, 1], cd, pin=False)
+    assert nat[0][2].dtype.is_floating_point and nat[0][2].element_size() == 4
+    assert np.array_equal(nat[0][2].numpy()[0], m0.astype(np.float32)) and np.array_equal(nat[0][2].numpy()[1], mels[1].astype(np.float32))
+    # Fortran-order files are declined by the native reader and read through numpy: same result
+    root = str(tmp_path / "c")
+    mels = _write_dataset(root, [(100, 16000), (100, 16000)], fortran=True)
+    _, rows = ho.parse_manifest(os.path.join(root, "label", "test.tsv"))
+    nat = ho._load_group(root, rows, [0, 1], cd, pin=False)
+    assert np.array_equal(nat[0][2].numpy()[0], mels[0]) and np.array_equal(nat[0][2].numpy()[1], mels[1])
+    # a speaker embedding of the wrong shape raises the reference's check (helpers.py:194), a missing file raises too
+    root = str(tmp_path / "d")
+    _write_dataset(root, [(100, 16000)], spk=np.zeros((1, 256), np.float32))
+    _, rows = ho.parse_manifest(os.path.join(root, "label", "test.tsv"))
+    with pytest.raises(ValueError, match="speaker embedding"):
+        ho._load_group(root, rows, [0], cd, pin=False)
+    os.remove(os.path.join(root, "mel", "test", "s0", "000.npy"))
+    with pytest.raises(OSError):
+        ho._load_group(root, rows, [0], cd, pin=False)
+
+
+def test_native_wav_writer_matches_scipy(pkg, tmp_path):
+    """l2s_io_write_wav_i16: n files per call, bytes equal scipy.io.wavfile.write (inference.py:164)."""
+    import torch
+    from scipy.io import wavfile
+    rng = np.random.default_rng(1)
+    x = torch.from_numpy(rng.integers(-32768, 32767, (5, 4000), dtype=np.int16))
+    ns = [4000, 1, 0, 3999, 1234]
+    paths = [str(tmp_path / f"{i}.wav") for i in range(5)]
+    pkg.hand_off._write_group_native(paths, x, ns, native_threads=3)
+    for i, (p, n) in enumerate(zip(paths, ns)):
+        buf = io.BytesIO()
+        wavfile.write(buf, 16000, x[i, :n].numpy())
+        assert open(p, "rb").read() == buf.getvalue()
+    with pytest.raises(OSError):
+        pkg.hand_off._write_group_native([str(tmp_path / "missing_dir" / "x.wav")], x, [10])
+
+
+def test_native_io_argument_checks(pkg):
+    import ctypes as C
+    cabi = pkg._cabi
+    lib = cabi.load()
+    assert lib.l2s_io_read_npy_f32(None, 1, None, 0, None, 80, 0, None, 1, None) == cabi.IO_ERR_ARG
+    assert lib.l2s_io_read_npy_f32(None, 0, None, 0, None, 80, 0, None, 1, None) == cabi.IO_OK
+    assert lib.l2s_io_write_wav_i16(None, 1, None, 0, None, 16000, 1, None) == cabi.IO_ERR_ARG
+    buf = np.zeros(80, np.float32)
+    rows, cap, bad = np.zeros(1, np.int32), np.asarray([2], np.int32), C.c_int32(-1)
+    ip = C.POINTER(C.c_int32)
+    paths = (C.c_char_p * 1)(b"/nonexistent/x.npy")
+    # the slot is too small for max_rows * cols
+    assert lib.l2s_io_read_npy_f32(paths, 1, buf.ctypes.data, 80, cap.ctypes.data_as(ip), 80, 0, rows.ctypes.data_as(ip), 1, C.byref(bad)) == cabi.IO_ERR_ARG
+    cap[0] = 1
+    assert lib.l2s_io_read_npy_f32(paths, 1, buf.ctypes.data, 80, cap.ctypes.data_as(ip), 80, 0, rows.ctypes.data_as(ip), 1, C.byref(bad)) == cabi.IO_ERR_OPEN
+    assert bad.value == 0

@@ -101,4 +101,44 @@ with tempfile.TemporaryDirectory() as root:
                 torch.cuda.synchronize(); best = min(best, time.perf_counter() - t0)
         sweep2[f"max_batch={mb},first={fg},threads={nt}"] = round(total_s / best, 1)
     res["serve_vocoder_request_sweep_audio_s_per_s"] = sweep2
+    sweep3 = {}
+    for nt, nn in ((2, 1), (2, 2), (2, 4), (2, 8), (3, 4), (4, 4), (3, 8)):
+        def run(out):
+            ho.serve_vocoder_request(g, root, out, device=dev, io_threads=nt, native_threads=nn)
+        with tempfile.TemporaryDirectory() as out:
+            run(out)
+        best = 1e9
+        for _ in range(4):
+            with tempfile.TemporaryDirectory() as out:
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                run(out)
+                torch.cuda.synchronize(); best = min(best, time.perf_counter() - t0)
+        sweep3[f"io_threads={nt},native_threads={nn}"] = round(total_s / best, 1)
+    res["serve_vocoder_request_native_threads_sweep_audio_s_per_s"] = sweep3
+    # host-only cost of the file I/O of the whole request, native batch calls against one numpy / Python call per file
+    _, rows = ho.parse_manifest(manifest)
+    cd = ho.load_code_dict(os.path.join(root, "label", "dict.unt.txt"))
+    groups = ho._plan_groups(rows, 32, 8)
+    host = {}
+    for name, fn in (("native", ho._load_group), ("python", ho._load_group_python)):
+        best = 1e9
+        for _ in range(3):
+            t0 = time.perf_counter()
+            loaded = [fn(root, rows, g_, cd, pin=True) for g_ in groups]
+            best = min(best, time.perf_counter() - t0)
+        host["load_ms_" + name] = round(best * 1e3, 2)
+    with tempfile.TemporaryDirectory() as out:
+        paths = [os.path.join(out, f"{i}.wav") for i in range(len(rows))]
+        t0 = time.perf_counter()
+        for lg in loaded:
+            for grp, code, mel, spk, wav in lg:
+                ho._write_group_native([paths[it[0]] for it in grp], wav, [it[4] for it in grp], 4)
+        host["write_ms_native"] = round((time.perf_counter() - t0) * 1e3, 2)
+        t0 = time.perf_counter()
+        for lg in loaded:
+            for grp, code, mel, spk, wav in lg:
+                for k, it in enumerate(grp):
+                    ho.write_wav_int16(paths[it[0]], wav[k, :it[4]].numpy())
+        host["write_ms_python"] = round((time.perf_counter() - t0) * 1e3, 2)
+    res["host_file_io_of_the_request"] = host
     print(json.dumps(res))
