@@ -53,6 +53,10 @@ struct CondParams {
   const void* mel;         // (B,num_mels,T)
   int mel_dtype;
   const float* spk_vec;    // (B,E) projected speaker vectors (multi) or null
+  const float* spk_raw;    // (B,spk_dim) raw speaker embeddings: when set, every block projects its utterance's embedding itself
+  const float* spk_w;      //   (spkr Linear, [E][spk_dim] + spk_b) in the arithmetic order of spk_project_kernel, and spk_vec is
+  const float* spk_b;      //   not read: one launch less in front of conv_pre
+  int spk_dim;
   const float* dict;       // (num_embeddings,E)
   const float* tab;        // unit table folded through the ConvTranspose1d taps at load: [4][num_embeddings][E], tab[j][id] = W_j^T dict[id]
   const float* wt;         // unit ConvT weights repacked [4][E_in][E_out] (only used to build the table)
@@ -65,7 +69,9 @@ struct CondParams {
   int batch, units, frames, e, num_mels, num_embeddings, cin_pad, has_spk;
 };
 
-constexpr int kCondFrames = 8;   // frames per block (even start)
+constexpr int kCondFrames = 8;   // frames per pass (even start)
+constexpr int kCondPasses = 2;   // passes per block: the in-block speaker projection (128 KB of weights from L2) is shared by 16 frames
+constexpr int kCondMaxSpk = 512; // largest spk_dim the in-block projection stages in shared memory
 constexpr int kCondE = 128;      // embedding_dim this kernel is specialised for
 constexpr int kCondSplit = 4;    // K (input channel) split: 4 thread groups of 128 each own a quarter of the reduction
 constexpr int kCondThreads = kCondE * kCondSplit;
@@ -77,17 +83,42 @@ template <typename Ta>
 __global__ void __launch_bounds__(kCondThreads) cond_multi_kernel(const CondParams p) {
   __shared__ float s_act[kCondFrames][kCondE];
   __shared__ float s_part[kCondSplit][kCondFrames][kCondE];
+  __shared__ float s_sv[kCondE];
+  __shared__ int s_id[kCondFrames / 2 + 2];
   const int b = blockIdx.y;
-  const int t0 = blockIdx.x * kCondFrames;
-  const int i0 = t0 >> 1;
   const int c = threadIdx.x & (kCondE - 1);
   const int g = threadIdx.x >> 7;
   constexpr int KQ = kCondE / kCondSplit;                 // input channels per group
   constexpr int FPG = kCondFrames / kCondSplit;           // frames each group finishes
   Ta* cond = reinterpret_cast<Ta*>(p.cond) + ((long long)b * p.frames) * p.cin_pad;
 
-  // (1) unit ids of this block: i0-1 .. i0+4 (clamped, sticky error flag like the reference's device assert)
-  __shared__ int s_id[kCondFrames / 2 + 2];
+  // (0) speaker projection of this utterance (models_multi_input.py:70-72), one warp per output channel at a time, lanes
+  //     over the input channels, shuffle reduction: the arithmetic of spk_project_kernel, bit for bit
+  if (p.has_spk) {
+    if (p.spk_raw) {
+      float* s_in = &s_part[0][0][0];                       // kCondMaxSpk floats fit the partial-sum buffer (not yet in use)
+      for (int k = threadIdx.x; k < p.spk_dim; k += kCondThreads) s_in[k] = p.spk_raw[(long long)b * p.spk_dim + k];
+      __syncthreads();
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      for (int ch = warp; ch < kCondE; ch += kCondThreads / 32) {
+        const float* wr = p.spk_w + (long long)ch * p.spk_dim;
+        float acc = 0.f;
+        for (int k = lane; k < p.spk_dim; k += 32) acc = fmaf(s_in[k], wr[k], acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) s_sv[ch] = acc + p.spk_b[ch];
+      }
+    } else if (threadIdx.x < kCondE) {
+      s_sv[threadIdx.x] = p.spk_vec[(long long)b * kCondE + threadIdx.x];
+    }
+  }
+  __syncthreads();
+
+  for (int pass = 0; pass < kCondPasses; ++pass) {
+  const int t0 = (blockIdx.x * kCondPasses + pass) * kCondFrames;
+  if (t0 >= p.frames) break;
+  const int i0 = t0 >> 1;
+  // (1) unit ids of this pass: i0-1 .. i0+4 (clamped, sticky error flag like the reference's device assert)
   if (threadIdx.x < kCondFrames / 2 + 2) {
     const int i = i0 - 1 + (int)threadIdx.x;
     int id = -1;                                            // -1: outside the utterance (contributes zero)
@@ -144,7 +175,7 @@ __global__ void __launch_bounds__(kCondThreads) cond_multi_kernel(const CondPara
   __syncthreads();
   // (5) reduce + concat: [mel | code feats | speaker | zero pad]
   const float fb = p.fc_bias[c];
-  const float sv = p.has_spk ? p.spk_vec[(long long)b * kCondE + c] : 0.f;
+  const float sv = p.has_spk ? s_sv[c] : 0.f;
   const int spk_base = p.num_mels + kCondE;
 #pragma unroll
   for (int j = 0; j < FPG; ++j) {
@@ -167,6 +198,8 @@ __global__ void __launch_bounds__(kCondThreads) cond_multi_kernel(const CondPara
     if (t < p.frames)
       cond[(long long)t * p.cin_pad + m] =
           to_act<Ta>(load_mel(p.mel, p.mel_dtype, ((long long)b * p.num_mels + m) * p.frames + t));
+  }
+  __syncthreads();                                          // s_id / s_act / s_part are rewritten by the next pass
   }
 }
 
@@ -230,13 +263,18 @@ constexpr int kPostTile = 256;
 // pitch (floats) of a staged row: a multiple of 4 (float4 reads) that spreads 8 consecutive rows over all banks
 __host__ __device__ inline int post_pitch(int c) { return c + 4; }
 
+// CC > 0: the channel count as a compile-time constant (the index arithmetic of the staging loop and the tap loops
+// unroll: the run-time version spent two thirds of its 22.6 M warp instructions on divisions and loop control and was
+// issue-bound at 31 us for cfg2; 0 = any C <= kPostMaxC.
+template <int CC>
 __global__ void __launch_bounds__(kPostTile) post_kernel(const PostParams p) {
   extern __shared__ __align__(16) float s_x[];   // [(kPostTile + 6)][post_pitch(C)]
   const int b = blockIdx.y;
   const int l0 = blockIdx.x * kPostTile;
-  const int c = p.c, pitch = post_pitch(c), c4 = c >> 2;
+  const int c = CC > 0 ? CC : p.c, pitch = post_pitch(c), c4 = c >> 2;
   const float4* in4 = reinterpret_cast<const float4*>(p.in + (long long)b * p.len * c);
   const int n4 = (kPostTile + 6) * c4;
+#pragma unroll 2
   for (int i = threadIdx.x; i < n4; i += kPostTile) {
     const int r = i / c4, q = i - r * c4;
     const int l = l0 - 3 + r;
@@ -257,10 +295,20 @@ __global__ void __launch_bounds__(kPostTile) post_kernel(const PostParams p) {
   for (int j = 0; j < 7; ++j) {
     const float4* xr = reinterpret_cast<const float4*>(s_x + (threadIdx.x + j) * pitch);
     const float* wr = p.wc + j * c;
-    for (int q = 0; q < c4; ++q) {
-      const float4 x = xr[q];
-      acc = fmaf(x.x, wr[4 * q], acc); acc = fmaf(x.y, wr[4 * q + 1], acc);
-      acc = fmaf(x.z, wr[4 * q + 2], acc); acc = fmaf(x.w, wr[4 * q + 3], acc);
+#pragma unroll
+    for (int q = 0; q < (CC > 0 ? CC / 4 : 1); ++q) {
+      if (CC > 0) {
+        const float4 x = xr[q];
+        acc = fmaf(x.x, wr[4 * q], acc); acc = fmaf(x.y, wr[4 * q + 1], acc);
+        acc = fmaf(x.z, wr[4 * q + 2], acc); acc = fmaf(x.w, wr[4 * q + 3], acc);
+      }
+    }
+    if (CC == 0) {
+      for (int q = 0; q < c4; ++q) {
+        const float4 x = xr[q];
+        acc = fmaf(x.x, wr[4 * q], acc); acc = fmaf(x.y, wr[4 * q + 1], acc);
+        acc = fmaf(x.z, wr[4 * q + 2], acc); acc = fmaf(x.w, wr[4 * q + 3], acc);
+      }
     }
   }
   const float y = tanhf(acc);

@@ -51,6 +51,11 @@ struct ResGeom {
   int cg2;                  // 1: CTA pairs (cluster of 2) issue cta_group::2 MMAs; a CTA keeps half of every weight stage
   uint32_t idesc;
   int smem_bytes;
+  // skewed schedule (resq_tc.cuh): two S slabs, per-granule barriers, weight-stage groups walked granule by granule
+  int skew;                 // 1: run by resq_tc_kernel
+  int gran, ng;             // granule = gran 128-row accumulators (32 TMEM columns at least), ng granules per tile
+  int gh, gt, head_fwd;     // first gh / last gt weight stages of a conv are walked granule-outer; head_fwd: the head group
+                            // holds a tap right of the centre (its MMAs on granule i read S rows of granule i + 1)
 };
 
 struct ResParams {
@@ -261,7 +266,7 @@ __device__ __forceinline__ void res_output(const ConvParams& p, float* tile, uin
     EpiChunk ca{}, cb{};
     float4 ava[CW / 4], avb[CW / 4];
     if (idx < n_chunks) { ca = locate(idx); epi_load_acc<CW, MODE>(p, ca, ava); }
-    mbar_wait(bar, parity);
+    if (bar) mbar_wait(bar, parity);            // nullptr: the caller has already waited for the accumulators
     tc_fence_after();
     while (idx < n_chunks) {
       const int idx2 = skip(next_after(idx));
@@ -289,7 +294,7 @@ __device__ __forceinline__ void res_output(const ConvParams& p, float* tile, uin
       }
     };
     prefetch_acc(idx);
-    mbar_wait(bar, parity);
+    if (bar) mbar_wait(bar, parity);
     tc_fence_after();
     while (idx < n_chunks) {
       const EpiChunk ca = locate(idx);
@@ -569,8 +574,12 @@ inline int g_res_cg2 = 4;   // whole-ResBlock plans run as CTA pairs issuing cta
 // kind: 0 = one CTA per SM (168 registers, 32-column epilogue chunks), 1 = two (80 registers, <= 112 KB, <= 256 TMEM
 // columns), 2 = four CTAs per SM with four epilogue warps each (<= 55 KB, <= 128 TMEM columns): more independent
 // tiles in flight for the MMA-light ResBlocks, whose epilogue warps otherwise idle while their own tile's MMAs run.
-inline bool res_plan_with(int c, int k, int n_dil, const int* dil, int lin, int batch, int kind, int msub, ResGeom* out) {
+inline int g_res_ng = 2;         // knob res_ng: granules per tile of the skewed schedule (each with its own barrier pair)
+inline int g_res_skew = 0;       // knob res_skew: one-CTA-per-SM plans run the skewed schedule of resq_tc.cuh where its two S slabs fit
+
+inline bool res_plan_with(int c, int k, int n_dil, const int* dil, int lin, int batch, int kind, int msub, ResGeom* out, bool skew = false) {
   const bool dual = kind != 0;
+  if (skew && kind != 0) return false;
   ResGeom g{};
   if ((c != 16 && c != 32 && c != 64) || k < 1 || k > kMaxTaps || (k & 1) == 0 || n_dil < 1 || n_dil > kResMaxDil) return false;
   g.c = c; g.k = k; g.n_dil = n_dil;
@@ -587,7 +596,8 @@ inline bool res_plan_with(int c, int k, int n_dil, const int* dil, int lin, int 
   g.k16 = g.rb / 32;
   g.lc = c == 16 ? 4 : (c == 32 ? 5 : 6);
   g.dual = dual ? 1 : 0;
-  g.cw = (!dual && c % 32 == 0) ? 32 : 16;
+  const bool wide = kind == 0 && g_res_wide;
+  g.cw = (!dual && c % 32 == 0 && !(skew && wide)) ? 32 : 16;   // skewed + sixteen warps: 16-column output chunks (half the tile memory)
   g.tile_words = 32 * g.cw;
   g.msub = msub;
   g.mt = 128 * msub;
@@ -613,7 +623,16 @@ inline bool res_plan_with(int c, int k, int n_dil, const int* dil, int lin, int 
   g.bstage_bytes = tb * (g.cg2 ? c / 2 : c) * g.rb;
   g.s_bytes = ((g.mt + 2 * g.pad) * g.rb + 1023) & ~1023;
   if ((msub * c) % 32 != 0) return false;   // the phases walk the TMEM region in 32-column units
-  const int fixed = 1024 + 192 + 2 * kResMaxDil * 64 * 4 + g.ne * g.tile_words * 4 + g.s_bytes;   // slack, barriers, biases, tiles, S
+  if (skew) {
+    g.skew = 1;
+    const int gmin = c >= 32 ? 1 : 32 / c;      // a granule is a whole number of 32-column units
+    if (msub % gmin != 0) return false;
+    int ngr = g_res_ng < 1 ? 1 : (g_res_ng > 8 ? 8 : g_res_ng);
+    while ((msub / gmin) % ngr != 0) --ngr;
+    g.ng = ngr;
+    g.gran = msub / ngr;
+  }
+  const int fixed = 1024 + (skew ? 448 : 192) + 2 * kResMaxDil * 64 * 4 + g.ne * g.tile_words * 4 + (skew ? 2 : 1) * g.s_bytes;   // slack, barriers, biases, tiles, S
   const int budget = kind == 2 ? 55 * 1024 : (dual ? 112 * 1024 : 220 * 1024);
   int sb = 2;
   if (fixed + sb * g.bstage_bytes > budget) return false;
@@ -621,6 +640,23 @@ inline bool res_plan_with(int c, int k, int n_dil, const int* dil, int lin, int 
          (sb + 1) * g.bstage_bytes <= 64 * 1024)
     ++sb;
   g.sb = sb;
+  if (skew) {
+    // head group: the leading stages whose taps all lie at or left of the centre (their MMAs on a granule read no S row of
+    // the next granule); tail group: the trailing stages; both at most half the ring (the producer keeps loading ahead)
+    int gmax = sb / 2 > 1 ? sb / 2 : 1;
+    if (gmax > 4) gmax = 4;                       // kResqMaxGroup
+    const int nts = g.n_tstages;
+    if (nts == 1) { g.gh = 0; g.gt = 1; }
+    else {
+      int gh = ((k - 1) / 2 + 1) / tb;
+      if (gh > gmax) gh = gmax;
+      if (gh > nts - 1) gh = nts - 1;
+      if (gh < 1) gh = 1;
+      g.gh = gh;
+      g.gt = nts - gh < gmax ? nts - gh : gmax;
+    }
+    g.head_fwd = (g.gh * tb - 1 > (k - 1) / 2) ? 1 : 0;
+  }
   g.smem_bytes = fixed + sb * g.bstage_bytes;
   g.idesc = umma_idesc_bf16(128u, (uint32_t)c);
   *out = g;
@@ -631,6 +667,7 @@ inline bool res_plan_with(int c, int k, int n_dil, const int* dil, int lin, int 
 // halo eats too much of the smaller tile.  mode: 0 auto, 1 force dual, 2 force single, 3 force quad.
 inline int g_res_single_pct = 85;   // planner: score discount (percent) of a one-CTA-per-SM plan (knob res_single_pct)
 
+inline int g_res_skew_pct = 100;    // planner: score weight (percent) of a skewed one-CTA-per-SM plan (knob res_skew_pct)
 inline int g_res_quad_pct = 115;    // planner: score weight (percent) of a four-CTAs-per-SM plan, 0 = never (knob res_quad_pct).  Measured on
                                     // cfg2: C=32 k=3 92 -> 84 us, C=16 k=7 117 -> 107 us; 200 (quad everywhere it fits) is slower.
 
@@ -644,13 +681,15 @@ inline bool res_plan(int c, int k, int n_dil, const int* dil, int lin, int batch
     double kind_best = 0.0;
     for (int msub = max_msub < 8 ? max_msub : 8; msub >= 1; --msub) {
       ResGeom g;
-      if (!res_plan_with(c, k, n_dil, dil, lin, batch, kind, msub, &g)) continue;
+      if (!(kind == 0 && g_res_skew && res_plan_with(c, k, n_dil, dil, lin, batch, kind, msub, &g, true)) &&
+          !res_plan_with(c, k, n_dil, dil, lin, batch, kind, msub, &g))
+        continue;
       // useful rows per computed row, weighted by how well the kind overlaps MMA and epilogue phases (from the
       // measured sweeps); tiles much longer than the utterance waste the rest.  One CTA per SM is discounted less
       // when two CTAs only fit 256-row tiles (C = 64, k = 7: 171 -> 160 us as one 512-row tile per SM).
       const int covered = g.m_items * g.r_out;
       const double single_w = 0.01 * g_res_single_pct + ((dual_mt > 0 && dual_mt <= 256) ? 0.10 : 0.0);
-      const double w = kind == 2 ? 0.01 * (g_res_quad_pct > 0 ? g_res_quad_pct : 100) : (kind == 1 ? 1.0 : single_w);
+      const double w = kind == 2 ? 0.01 * (g_res_quad_pct > 0 ? g_res_quad_pct : 100) : (kind == 1 ? 1.0 : (g.skew ? 0.01 * g_res_skew_pct : single_w));
       const double score = (double)g.r_out / g.mt * ((double)lin / covered) * w;
       if (kind == 1 && score > kind_best) { kind_best = score; dual_mt = g.mt; }
       if (score > best_score) { best_score = score; best = g; }
@@ -689,6 +728,8 @@ inline cudaError_t launch_res_mode(const ResParams& P, const ResMaps& maps, int 
   return cudaLaunchKernelEx(&cfg, res_tc_kernel<MODE, DUAL, CG2, WIDE>, maps, P);
 }
 
+cudaError_t launch_resq_tc(const ResParams& P, const ResMaps& maps, int grid, int mode, cudaStream_t stream);   // resq_tc.cuh / tu_resq_tc.cu
+
 // Defined in tu_res_tc.cu (the only translation unit that instantiates res_tc_kernel); declared everywhere else.
 #ifndef L2S_TU_RES_TC
 cudaError_t launch_res_tc(const ResParams& P, const ResMaps& maps, int num_ctas, cudaStream_t stream);
@@ -706,6 +747,7 @@ cudaError_t launch_res_tc(const ResParams& P, const ResMaps& maps, int num_ctas,
     grid = 2 * pairs;
   }
   const int mode = ((c.acc_in || c.div != 1.0f) ? kEpiAcc : 0) | (c.out_raw ? kEpiRaw : 0) | (c.out_act ? kEpiAct : 0);
+  if (g.skew) return launch_resq_tc(P, maps, grid, mode, stream);
   switch (mode) {
 #define L2S_RMODE(m)                                                                                        \
   case m:                                                                                                   \

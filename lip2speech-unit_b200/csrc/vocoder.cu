@@ -64,6 +64,7 @@ struct Knobs {
   long long layer_events = 0;      // record a cudaEvent pair around every launch of the next forwards
   long long par_share = 0;         // experiment: with branch_par, two-CTAs-per-SM step kernels launch ONE CTA per SM each, so CTAs of two
                                    // different branches (k = 3 epilogue-bound, k = 11 MMA-bound) share an SM
+  long long front_fuse = 1;        // the speaker projection runs inside the conditioning kernel (0: its own launch in front of it)
   long long branch_par = 1;        // C >= 128 stages: the kernel-size branches of a stage run on parallel streams (graph branches); only the
                                    // last step of a branch waits for the previous branch (running sum).  Fills the wave-quantisation tails.
 };
@@ -889,11 +890,15 @@ int forward_impl(l2s_vocoder* v, void* stream, const int64_t* code, const void* 
   timed_begin(v, st, "front_end", 0.0);
   float* embed_tap = g_knobs.embed_tap ? ws.embed : nullptr;
   if (multi) {
-    if (c.multispkr) {
+    // the speaker projection runs inside the conditioning kernel (every block projects its utterance's embedding: one launch
+    // and one kernel boundary less in front of conv_pre); knob front_fuse = 0 or an oversized spk_dim: the separate kernel
+    const bool spk_in_block = c.multispkr && g_knobs.front_fuse && c.spk_dim <= kCondMaxSpk;
+    if (c.multispkr && !spk_in_block) {
       spk_project_kernel<<<batch, 512, c.spk_dim * sizeof(float), st>>>((const float*)spkr, v->d_spk_w, v->d_spk_b, ws.spk_vec,
                                                                         c.spk_dim, E);
     }
     CondParams cp{};
+    if (spk_in_block) { cp.spk_raw = (const float*)spkr; cp.spk_w = v->d_spk_w; cp.spk_b = v->d_spk_b; cp.spk_dim = c.spk_dim; }
     cp.code = (const long long*)code;
     cp.mel = mel;
     cp.mel_dtype = mel_dtype;
@@ -909,7 +914,7 @@ int forward_impl(l2s_vocoder* v, void* stream, const int64_t* code, const void* 
     cp.err_flag = v->err_dev;
     cp.batch = batch; cp.units = units; cp.frames = frames; cp.e = E; cp.num_mels = c.num_mels;
     cp.num_embeddings = c.num_embeddings; cp.cin_pad = pre.cin_pad; cp.has_spk = c.multispkr ? 1 : 0;
-    dim3 grid((frames + kCondFrames - 1) / kCondFrames, batch);
+    dim3 grid((frames + kCondFrames * kCondPasses - 1) / (kCondFrames * kCondPasses), batch);
     if (bf) cond_multi_kernel<__nv_bfloat16><<<grid, kCondThreads, 0, st>>>(cp);
     else cond_multi_kernel<float><<<grid, kCondThreads, 0, st>>>(cp);
   } else {
@@ -993,7 +998,9 @@ int forward_impl(l2s_vocoder* v, void* stream, const int64_t* code, const void* 
   pp.c = v->stage_ch.back();
   dim3 grid((unsigned)((len + kPostTile - 1) / kPostTile), batch);
   timed_begin(v, st, "conv_post", 2.0 * pp.c * 7 * (double)batch * len);
-  post_kernel<<<grid, kPostTile, (kPostTile + 6) * post_pitch(pp.c) * sizeof(float), st>>>(pp);
+  if (pp.c == 16) post_kernel<16><<<grid, kPostTile, (kPostTile + 6) * post_pitch(pp.c) * sizeof(float), st>>>(pp);
+  else if (pp.c == 32) post_kernel<32><<<grid, kPostTile, (kPostTile + 6) * post_pitch(pp.c) * sizeof(float), st>>>(pp);
+  else post_kernel<0><<<grid, kPostTile, (kPostTile + 6) * post_pitch(pp.c) * sizeof(float), st>>>(pp);
   timed_end(v, st);
   if ((e = cudaGetLastError()) != cudaSuccess) return fail(v, L2S_ERR_CUDA, std::string("post: ") + cudaGetErrorString(e));
   return L2S_OK;
@@ -1257,7 +1264,7 @@ int32_t l2s_launch_count(l2s_vocoder* v, int32_t batch, int32_t frames) {
       if (stage_pk_fused(v, i, (int)len, batch, &fg)) n -= c.n_rk - 1;   // one per stage
     }
   }
-  if (c.variant == L2S_VARIANT_MULTI_INPUT && c.multispkr) n += 1;
+  if (c.variant == L2S_VARIANT_MULTI_INPUT && c.multispkr && !(g_knobs.front_fuse && c.spk_dim <= kCondMaxSpk)) n += 1;   // separate speaker projection
   return n;
 }
 
@@ -1371,6 +1378,9 @@ int l2s_debug_set(const char* key, int64_t value) {
   else if (k == "res_quad_pct") g_res_quad_pct = (int)value;
   else if (k == "res_cg2") g_res_cg2 = (int)value;
   else if (k == "res_wide") g_res_wide = (int)value;
+  else if (k == "res_skew") g_res_skew = (int)value;
+  else if (k == "res_ng") g_res_ng = (int)value;
+  else if (k == "res_skew_pct") g_res_skew_pct = (int)value;
   else if (k == "pack") g_pk_on = (int)value;
   else if (k == "pk_mode") g_pk_mode = (int)value;
   else if (k == "pk_cg2") g_pk_cg2 = (int)value;
@@ -1395,6 +1405,7 @@ int l2s_debug_set(const char* key, int64_t value) {
   else if (k == "slab_cap") g_knobs.slab_cap = value;
   else if (k == "max_ctas") g_knobs.max_ctas = value;
   else if (k == "embed_tap") g_knobs.embed_tap = value;
+  else if (k == "front_fuse") g_knobs.front_fuse = value;
   else if (k == "layer_events") g_knobs.layer_events = value;
   else if (k == "branch_par") g_knobs.branch_par = value;
   else if (k == "par_share") g_knobs.par_share = value;

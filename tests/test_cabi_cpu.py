@@ -42,21 +42,21 @@ def test_create_validates_without_cuda(pkg):
     # bf16 mode: 1 speaker projection + 1 conditioning + conv_pre + 5 ups + conv_post + 18 fused ResBlock steps
     # (C = 256, 128: one launch per step) + 6 whole-ResBlock kernels (C = 64, 16) + 1 time-packed stage kernel (C = 32:
     # the three ResBlocks of the stage in one launch)
-    assert lib.l2s_launch_count(hnd, 16, 400) == 34
+    assert lib.l2s_launch_count(hnd, 16, 400) == 33
     assert lib.l2s_debug_set(b"pk_chan", 16 | 32 | 64) == pkg._cabi.OK
-    assert lib.l2s_launch_count(hnd, 16, 400) == 30     # every C <= 64 stage as one time-packed launch
+    assert lib.l2s_launch_count(hnd, 16, 400) == 29     # every C <= 64 stage as one time-packed launch
     assert lib.l2s_debug_set(b"pk_fuse", 0) == pkg._cabi.OK
-    assert lib.l2s_launch_count(hnd, 16, 400) == 36     # one launch per ResBlock on the C <= 64 stages
+    assert lib.l2s_launch_count(hnd, 16, 400) == 35     # one launch per ResBlock on the C <= 64 stages
     assert lib.l2s_debug_set(b"pk_fuse", 1) == pkg._cabi.OK
     assert lib.l2s_debug_set(b"pk_chan", 32) == pkg._cabi.OK
     assert lib.l2s_debug_set(b"fuse_branch", 0) == pkg._cabi.OK
-    assert lib.l2s_launch_count(hnd, 16, 400) == 54     # every ResBlock step its own launch
+    assert lib.l2s_launch_count(hnd, 16, 400) == 53     # every ResBlock step its own launch
     assert lib.l2s_debug_set(b"fuse_branch", 1) == pkg._cabi.OK
     cfg32 = _cfg(pkg)
     cfg32.precision = pkg._cabi.PREC_FP32
     h32 = C.c_void_p()
     assert lib.l2s_create(C.byref(cfg32), C.byref(h32)) == pkg._cabi.OK
-    assert lib.l2s_launch_count(h32, 16, 400) == 99      # fp32 mode: every conv is its own launch
+    assert lib.l2s_launch_count(h32, 16, 400) == 98      # fp32 mode: every conv is its own launch
     lib.l2s_destroy(h32)
     assert lib.l2s_workspace_bytes(hnd, 16, 400) > 0
     assert lib.l2s_workspace_bytes(hnd, 0, 400) < 0
