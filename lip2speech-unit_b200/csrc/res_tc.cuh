@@ -574,6 +574,8 @@ inline int g_res_cg2 = 4;   // whole-ResBlock plans run as CTA pairs issuing cta
 // kind: 0 = one CTA per SM (168 registers, 32-column epilogue chunks), 1 = two (80 registers, <= 112 KB, <= 256 TMEM
 // columns), 2 = four CTAs per SM with four epilogue warps each (<= 55 KB, <= 128 TMEM columns): more independent
 // tiles in flight for the MMA-light ResBlocks, whose epilogue warps otherwise idle while their own tile's MMAs run.
+inline int g_res_tb = 0;         // knob res_tb: cap on the taps per weight stage of the skewed schedule (0: as res_tc_kernel)
+inline int g_res_gmax = 0;       // knob res_gmax: cap on the stages of a head / tail group (0: half the ring)
 inline int g_res_ng = 2;         // knob res_ng: granules per tile of the skewed schedule (each with its own barrier pair)
 inline int g_res_skew = 0;       // knob res_skew: one-CTA-per-SM plans run the skewed schedule of resq_tc.cuh where its two S slabs fit
 
@@ -612,6 +614,7 @@ inline bool res_plan_with(int c, int k, int n_dil, const int* dil, int lin, int 
   int tb = 1;
   while (tb < k && tb < 16 && (tb * 2) * c * g.rb <= 16384) tb *= 2;
   if (tb > k) tb = k;
+  if (skew && g_res_tb > 0 && g_res_tb < tb) tb = g_res_tb;      // finer weight stages: the granule-outer groups hold fewer bytes
   g.tb = tb;
   g.n_tstages = (k + tb - 1) / tb;
   g.m_items = (lin + g.r_out - 1) / g.r_out;
@@ -632,11 +635,11 @@ inline bool res_plan_with(int c, int k, int n_dil, const int* dil, int lin, int 
     g.ng = ngr;
     g.gran = msub / ngr;
   }
-  const int fixed = 1024 + (skew ? 448 : 192) + 2 * kResMaxDil * 64 * 4 + g.ne * g.tile_words * 4 + (skew ? 2 : 1) * g.s_bytes;   // slack, barriers, biases, tiles, S
+  const int fixed = 1024 + (skew ? 576 : 192) + 2 * kResMaxDil * 64 * 4 + g.ne * g.tile_words * 4 + (skew ? 2 : 1) * g.s_bytes;   // slack, barriers, biases, tiles, S
   const int budget = kind == 2 ? 55 * 1024 : (dual ? 112 * 1024 : 220 * 1024);
   int sb = 2;
   if (fixed + sb * g.bstage_bytes > budget) return false;
-  while (sb < kTcMaxStagesB && sb < 2 * g.n_tstages && fixed + (sb + 1) * g.bstage_bytes <= budget &&
+  while (sb < (skew ? 16 : kTcMaxStagesB) && sb < 2 * g.n_tstages && fixed + (sb + 1) * g.bstage_bytes <= budget &&
          (sb + 1) * g.bstage_bytes <= 64 * 1024)
     ++sb;
   g.sb = sb;
@@ -644,7 +647,7 @@ inline bool res_plan_with(int c, int k, int n_dil, const int* dil, int lin, int 
     // head group: the leading stages whose taps all lie at or left of the centre (their MMAs on a granule read no S row of
     // the next granule); tail group: the trailing stages; both at most half the ring (the producer keeps loading ahead)
     int gmax = sb / 2 > 1 ? sb / 2 : 1;
-    if (gmax > 4) gmax = 4;                       // kResqMaxGroup
+    if (g_res_gmax > 0 && gmax > g_res_gmax) gmax = g_res_gmax;
     const int nts = g.n_tstages;
     if (nts == 1) { g.gh = 0; g.gt = 1; }
     else {

@@ -28,6 +28,7 @@
 namespace l2s {
 
 constexpr int kResqMaxGran = 8;
+constexpr int kResqMaxStages = 16;   // weight ring slots (res_tc_kernel: kTcMaxStagesB = 8)
 
 // first unit >= lo owned by this warp (units half, half + ustep, ...)
 __device__ __forceinline__ int resq_first_unit(const ResLane& w, int lo) {
@@ -116,7 +117,6 @@ __device__ __forceinline__ void resq_load_x(const ResParams& P, const ResLane& w
 //   head group  [0, gh)          granule-outer, waits for the granule's e_done (plus the next one's when head_fwd)
 //   middle      [gh, nts - gt)   stage-outer over all accumulators, after every e_done
 //   tail group  [nts - gt, nts)  granule-outer, commits m_done per granule
-constexpr int kResqMaxGroup = 4;
 
 template <int C, bool CG2>
 __device__ __forceinline__ void resq_issue_conv(const ResGeom& g, bool leader, uint32_t w0_lo, uint64_t* b_full, uint64_t* b_empty,
@@ -136,53 +136,49 @@ __device__ __forceinline__ void resq_issue_conv(const ResGeom& g, bool leader, u
     tc_fence_after();
     if (wcyc) wcyc[1] += clock64() - c0;
   };
-  auto run_group = [&](int s0, int s1, int fwd, bool commits) {
-    uint32_t blo[kResqMaxGroup];
-    int tend[kResqMaxGroup];
-    {
+  // ONE loop nest (one inlined copy of the MMA issue code per C: with a copy per group and stage the issuing warp's
+  // instruction footprint grew several-fold and its issue rate fell to ~60 cycles per MMA): segment 0 = head group,
+  // 1 = middle, 2 = tail group; the middle is a single pass over all accumulators.
+  for (int seg = 0; seg < 3; ++seg) {
+    const int s0 = seg == 0 ? 0 : (seg == 1 ? g.gh : nts - g.gt);
+    const int s1 = seg == 0 ? g.gh : (seg == 1 ? nts - g.gt : nts);
+    if (s0 >= s1) continue;
+    const bool outer = seg != 1;
+    const int passes = outer ? ng : 1;
+    const int n_acc = outer ? g.gran : g.msub;
+    const int fwd = seg == 0 ? g.head_fwd : 1;
+    if (outer) {                                                        // the group's stages stay resident over all granules
+      const long long c0 = wcyc ? clock64() : 0;
       int ibw = ib;
       uint32_t pbw = pb;
-      const long long c0 = wcyc ? clock64() : 0;
-#pragma unroll
-      for (int i = 0; i < kResqMaxGroup; ++i) {
-        if (s0 + i < s1) {
-          mbar_wait(&b_full[ibw], pbw);
-          blo[i] = w0_lo + (uint32_t)ibw * stage_step;
-          tend[i] = min(tb, g.k - (s0 + i) * tb);
-          if (++ibw == sbn) { ibw = 0; pbw ^= 1u; }
-        }
+      for (int s = s0; s < s1; ++s) {
+        mbar_wait(&b_full[ibw], pbw);
+        if (++ibw == sbn) { ibw = 0; pbw ^= 1u; }
       }
       tc_fence_after();
       if (wcyc) wcyc[0] += clock64() - c0;
     }
     uint32_t a_g = a_tap0, d_g = d_base;
-    for (int gr = 0; gr < ng; ++gr, a_g += gran_a, d_g += gran_d) {
-      wait_upto(gr + fwd);
-#pragma unroll
-      for (int i = 0; i < kResqMaxGroup; ++i)
-        if (s0 + i < s1) res_issue_stage<C, CG2>(leader, g.gran, desc_hi, a_g, tap_step, blo[i], (s0 + i) * tb, tend[i], d_g);
-      if (commits) commit(&mc[gr]);
+    for (int pass = 0; pass < passes; ++pass, a_g += gran_a, d_g += gran_d) {
+      wait_upto(outer ? pass + fwd : ng - 1);
+      int ibs = ib;
+      uint32_t pbs = pb;
+      for (int s = s0; s < s1; ++s) {
+        if (!outer) {
+          const long long c0 = wcyc ? clock64() : 0;
+          mbar_wait(&b_full[ibs], pbs);
+          tc_fence_after();
+          if (wcyc) wcyc[0] += clock64() - c0;
+        }
+        res_issue_stage<C, CG2>(leader, n_acc, desc_hi, a_g, tap_step, w0_lo + (uint32_t)ibs * stage_step, s * tb, min(tb, g.k - s * tb), d_g);
+        if (pass == passes - 1) commit(&b_empty[ibs]);                  // last user of the stage: hand the slot back right away
+        if (++ibs == sbn) { ibs = 0; pbs ^= 1u; }
+      }
+      if (seg == 2) commit(&mc[pass]);
     }
-    for (int s = s0; s < s1; ++s) {
-      commit(&b_empty[ib]);
+    for (int s = s0; s < s1; ++s)
       if (++ib == sbn) { ib = 0; pb ^= 1u; }
-    }
-  };
-  const int mid0 = g.gh, mid1 = nts - g.gt;
-  if (g.gh > 0) run_group(0, g.gh, g.head_fwd, false);
-  if (mid1 > mid0) {
-    wait_upto(ng - 1);
-    for (int ts = mid0; ts < mid1; ++ts) {                              // middle stages: all accumulators per stage
-      const long long c0 = wcyc ? clock64() : 0;
-      mbar_wait(&b_full[ib], pb);
-      tc_fence_after();
-      if (wcyc) wcyc[0] += clock64() - c0;
-      res_issue_stage<C, CG2>(leader, g.msub, desc_hi, a_tap0, tap_step, w0_lo + (uint32_t)ib * stage_step, ts * tb, min(tb, g.k - ts * tb), d_base);
-      commit(&b_empty[ib]);
-      if (++ib == sbn) { ib = 0; pb ^= 1u; }
-    }
   }
-  run_group(mid1, nts, 1, true);
 }
 
 template <int MODE, bool CG2, bool WIDE>
@@ -199,11 +195,11 @@ resq_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
   uint8_t* stageB = slabB + (size_t)g.s_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(stageB + (size_t)g.sb * g.bstage_bytes);
   uint64_t* b_full = bars;
-  uint64_t* b_empty = b_full + kTcMaxStagesB;
-  uint64_t* m_done = b_empty + kTcMaxStagesB;              // [2][kResqMaxGran]: c1 / c2 commits per granule
+  uint64_t* b_empty = b_full + kResqMaxStages;
+  uint64_t* m_done = b_empty + kResqMaxStages;             // [2][kResqMaxGran]: c1 / c2 commits per granule
   uint64_t* e_done = m_done + 2 * kResqMaxGran;            // [2][kResqMaxGran]: phase A / (phase B or slab-A load) per granule
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(e_done + 2 * kResqMaxGran);
-  float* sbias = reinterpret_cast<float*>(bars + 56);      // [2 n_dil][C]: b1_s, b2_s
+  float* sbias = reinterpret_cast<float*>(bars + 72);      // [2 n_dil][C]: b1_s, b2_s
   float* epi_tiles = sbias + 2 * kResMaxDil * 64;
 
   const int warp = threadIdx.x >> 5;

@@ -1380,6 +1380,8 @@ int l2s_debug_set(const char* key, int64_t value) {
   else if (k == "res_wide") g_res_wide = (int)value;
   else if (k == "res_skew") g_res_skew = (int)value;
   else if (k == "res_ng") g_res_ng = (int)value;
+  else if (k == "res_tb") g_res_tb = (int)value;
+  else if (k == "res_gmax") g_res_gmax = (int)value;
   else if (k == "res_skew_pct") g_res_skew_pct = (int)value;
   else if (k == "pack") g_pk_on = (int)value;
   else if (k == "pk_mode") g_pk_mode = (int)value;

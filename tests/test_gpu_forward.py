@@ -376,6 +376,36 @@ def test_whole_resblock_tilings_agree(pkg, weights, knob, value):
     assert torch.equal(a, b), float((a - b).abs().max())
 
 
+@pytest.mark.parametrize("extra", [{}, {"res_cg2": 0}, {"res_wide": 0}, {"res_ng": 4}, {"res_ng": 1}, {"res_msub": 2}, {"res_tb": 1, "res_gmax": 2}])
+@pytest.mark.parametrize("batch,frames", [(3, 150), (1, 34)])
+def test_skewed_resblock_schedule_is_bit_identical(pkg, weights, extra, batch, frames):
+    """resq_tc.cuh (two S slabs, per-granule barriers, head / tail weight-stage groups walked granule by granule, the next
+    tile's slab loaded under the last conv): a different SCHEDULE of the same MMAs and epilogue arithmetic as res_tc_kernel
+    -- every accumulator still receives its taps in ascending order -- so the waveform must not change by a bit, with CTA
+    pairs or without, 8 or 16 epilogue warps, 1 / 2 / 4 granules, small tiles, one-tap weight stages."""
+    h, sds = weights
+    code, mel, spkr = vo.synthetic_inputs(batch, frames, seed=33)
+    g = make_gen(pkg, h, sds["trained"], "bf16")
+    lib = pkg._cabi.load()
+    defaults = {"pack": 1, "res_mode": 0, "res_skew": 0, "res_cg2": 4, "res_wide": 1, "res_ng": 2, "res_msub": 8, "res_tb": 0, "res_gmax": 0}
+    try:
+        lib.l2s_debug_set(b"pack", 0)             # tap-by-tap whole-ResBlock kernels on every narrow stage
+        lib.l2s_debug_set(b"res_mode", 2)         # one CTA per SM everywhere: the plans the skewed schedule replaces
+        for k, v in extra.items():
+            if k != "res_ng" and k != "res_tb" and k != "res_gmax":
+                lib.l2s_debug_set(k.encode(), v)
+        a = g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV)).clone()
+        lib.l2s_debug_set(b"res_skew", 1)
+        for k, v in extra.items():
+            lib.l2s_debug_set(k.encode(), v)
+        b = g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV)).clone()
+    finally:
+        for k, v in defaults.items():
+            lib.l2s_debug_set(k.encode(), v)
+    assert torch.isfinite(a).all()
+    assert torch.equal(a, b), float((a - b).abs().max())
+
+
 @pytest.mark.parametrize("knob,value", [("pk_mode", 1), ("pk_mode", 2), ("pk_cg2", 0), ("pk_fuse", 0)])
 @pytest.mark.parametrize("batch,frames", [(3, 150), (1, 34)])
 def test_packed_resblock_variants_agree(pkg, weights, knob, value, batch, frames):
