@@ -70,7 +70,8 @@ struct CondParams {
 };
 
 constexpr int kCondFrames = 8;   // frames per pass (even start)
-constexpr int kCondPasses = 2;   // passes per block: the in-block speaker projection (128 KB of weights from L2) is shared by 16 frames
+constexpr int kCondPasses = 3;   // passes per block: the in-block speaker projection (128 KB of weights from L2) is shared by 24 frames
+                                 // (cfg2: 272 blocks = one wave at two 59-register blocks per SM; with 2 passes 400 blocks = two waves)
 constexpr int kCondMaxSpk = 512; // largest spk_dim the in-block projection stages in shared memory
 constexpr int kCondE = 128;      // embedding_dim this kernel is specialised for
 constexpr int kCondSplit = 4;    // K (input channel) split: 4 thread groups of 128 each own a quarter of the reduction
@@ -100,13 +101,20 @@ __global__ void __launch_bounds__(kCondThreads) cond_multi_kernel(const CondPara
       for (int k = threadIdx.x; k < p.spk_dim; k += kCondThreads) s_in[k] = p.spk_raw[(long long)b * p.spk_dim + k];
       __syncthreads();
       const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-      for (int ch = warp; ch < kCondE; ch += kCondThreads / 32) {
-        const float* wr = p.spk_w + (long long)ch * p.spk_dim;
-        float acc = 0.f;
-        for (int k = lane; k < p.spk_dim; k += 32) acc = fmaf(s_in[k], wr[k], acc);
+      constexpr int NW = kCondThreads / 32, CPW = kCondE / NW;   // 16 warps, 8 channels each: all 8 dot products in flight at once
+      float acc[CPW];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) s_sv[ch] = acc + p.spk_b[ch];
+      for (int i = 0; i < CPW; ++i) acc[i] = 0.f;
+      for (int k = lane; k < p.spk_dim; k += 32) {
+        const float x = s_in[k];
+#pragma unroll
+        for (int i = 0; i < CPW; ++i) acc[i] = fmaf(x, p.spk_w[(long long)(warp + i * NW) * p.spk_dim + k], acc[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < CPW; ++i) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+        if (lane == 0) s_sv[warp + i * NW] = acc[i] + p.spk_b[warp + i * NW];
       }
     } else if (threadIdx.x < kCondE) {
       s_sv[threadIdx.x] = p.spk_vec[(long long)b * kCondE + threadIdx.x];
