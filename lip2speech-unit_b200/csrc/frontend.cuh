@@ -330,4 +330,59 @@ __global__ void __launch_bounds__(kPostTile) post_kernel(const PostParams p) {
   }
 }
 
+// Row-per-thread head (C = 16 / 32): every thread reads ITS row once (64 / 128 contiguous bytes straight from global, no
+// staging), forms the row's seven per-tap dot products p_j = sum_c w[j][c] * lrelu(x[l][c]), and an output sample is
+// bias + sum_j p_j[o - 3 + j], collected from the neighbouring rows through 7 KB of shared memory.  post_kernel stages a
+// tile and every output re-reads seven rows of it (7x the tile through the shared-memory pipe: 27-31 us for cfg2, 0.32-0.35
+// of the copy bandwidth); this one is bound by the 65 MB read.  The sum is formed per tap first, then over the taps (the
+// reference's own cuDNN / MKL order is unspecified; post_kernel's single chain differs in the last fp32 bits).
+constexpr int kPostRowsOut = kPostTile - 6;   // output samples per block
+
+template <int CC>
+__global__ void __launch_bounds__(kPostTile) post_rows_kernel(const PostParams p) {
+  __shared__ float sp[7][kPostTile + 8];
+  const int b = blockIdx.y;
+  const int l0 = blockIdx.x * kPostRowsOut;
+  const int r = threadIdx.x;                  // block row r is sample l0 - 3 + r
+  const int l = l0 - 3 + r;
+  float part[7];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) part[j] = 0.f;
+  if (l >= 0 && l < p.len) {                  // rows outside the utterance are conv_post's zero padding
+    const float4* in4 = reinterpret_cast<const float4*>(p.in + ((long long)b * p.len + l) * CC);
+    float4 v[CC / 4];
+#pragma unroll
+    for (int q = 0; q < CC / 4; ++q) v[q] = __ldg(in4 + q);
+#pragma unroll
+    for (int q = 0; q < CC / 4; ++q) {
+      // F.leaky_relu default slope 0.01, models.py:110
+      const float x0 = v[q].x > 0.f ? v[q].x : v[q].x * 0.01f, x1 = v[q].y > 0.f ? v[q].y : v[q].y * 0.01f;
+      const float x2 = v[q].z > 0.f ? v[q].z : v[q].z * 0.01f, x3 = v[q].w > 0.f ? v[q].w : v[q].w * 0.01f;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const float* wr = p.wc + j * CC + 4 * q;
+        part[j] = fmaf(x0, wr[0], part[j]); part[j] = fmaf(x1, wr[1], part[j]);
+        part[j] = fmaf(x2, wr[2], part[j]); part[j] = fmaf(x3, wr[3], part[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 7; ++j) sp[j][r] = part[j];
+  __syncthreads();
+  const int o = l0 + r;
+  if (r >= kPostRowsOut || o >= p.len) return;
+  float acc = p.bias;
+#pragma unroll
+  for (int j = 0; j < 7; ++j) acc += sp[j][r + j];   // tap j reads sample o - 3 + j = block row r + j
+  const float y = tanhf(acc);
+  const long long oo = (long long)b * p.len + o;
+  if (p.out) p.out[oo] = y;
+  if (p.out_i16) {
+    // inference.py:79-81: audio * 32768 -> int16 (astype truncates toward zero); saturate instead of wrapping
+    float s = y * 32768.0f;
+    s = fminf(fmaxf(s, -32768.0f), 32767.0f);
+    p.out_i16[oo] = (int16_t)s;
+  }
+}
+
 }  // namespace l2s

@@ -252,12 +252,16 @@ __device__ __forceinline__ void res_output(const ConvParams& p, float* tile, uin
     return epi_locate<CW>(p, t_base + (uint32_t)(s_ * c + cc_ * CW), b, t_row0 + s_ * 128 + w.quad * 32, cc_ * CW, crow, c4, row_lim,
                           row_lo);
   };
-  const float4 no_res[CW / 4] = {};
+  // MODE & kEpiRes: a SECOND branch output to add (p.res: the ResBlock of another kernel-size branch that ran in parallel with
+  // the one whose running sum is p.acc_in).  epi_finish adds it before the running sum: ((x_0 + x_1) + x_2) / 3, the
+  // association of the reference's `xs += resblock(x)` loop and of the serial branch chain.
   auto finish = [&](const EpiChunk& ch, const float4 (&av)[CW / 4]) {
+    float4 rv[CW / 4] = {};
+    epi_load_res<CW, MODE>(p, ch, rv);       // in flight while the accumulator is staged
     epi_stage<CW>(tile4, ch.taddr, w.lane);
     __syncwarp();
-    if (__all_sync(0xffffffffu, ch.okmask == kAll)) epi_finish<CW, MODE, true>(p, ch, tile4, no_res, av, crow, c4);
-    else epi_finish<CW, MODE, false>(p, ch, tile4, no_res, av, crow, c4);
+    if (__all_sync(0xffffffffu, ch.okmask == kAll)) epi_finish<CW, MODE, true>(p, ch, tile4, rv, av, crow, c4);
+    else epi_finish<CW, MODE, false>(p, ch, tile4, rv, av, crow, c4);
     __syncwarp();   // the tile is rewritten by the next chunk
   };
   int idx = skip(first);
@@ -288,7 +292,10 @@ __device__ __forceinline__ void res_output(const ConvParams& p, float* tile, uin
 #pragma unroll
           for (int i = 0; i < ITERS; ++i) {
             const int q = qa + i * RPI;
-            if (q >= row_lo && q < row_lim) prefetch_l1(p.acc_in + ((long long)b * p.lin + q) * p.ntot + cc_ * CW);
+            if (q >= row_lo && q < row_lim) {
+              prefetch_l1(p.acc_in + ((long long)b * p.lin + q) * p.ntot + cc_ * CW);
+              if constexpr ((MODE & kEpiRes) != 0) prefetch_l1(p.res + ((long long)b * p.lin + q) * p.ntot + cc_ * CW);
+            }
           }
         }
       }
@@ -749,7 +756,7 @@ cudaError_t launch_res_tc(const ResParams& P, const ResMaps& maps, int num_ctas,
     if (pairs < 1) pairs = 1;
     grid = 2 * pairs;
   }
-  const int mode = ((c.acc_in || c.div != 1.0f) ? kEpiAcc : 0) | (c.out_raw ? kEpiRaw : 0) | (c.out_act ? kEpiAct : 0);
+  const int mode = ((c.acc_in || c.div != 1.0f) ? kEpiAcc : 0) | (c.out_raw ? kEpiRaw : 0) | (c.out_act ? kEpiAct : 0) | (c.res ? kEpiRes : 0);
   if (g.skew) return launch_resq_tc(P, maps, grid, mode, stream);
   switch (mode) {
 #define L2S_RMODE(m)                                                                                        \
@@ -758,6 +765,7 @@ cudaError_t launch_res_tc(const ResParams& P, const ResMaps& maps, int num_ctas,
     if (g.cg2) return g.dual ? launch_res_mode<m, true, true>(P, maps, grid, stream) : launch_res_mode<m, false, true>(P, maps, grid, stream); \
     return g.dual ? launch_res_mode<m, true>(P, maps, grid, stream) : launch_res_mode<m, false>(P, maps, grid, stream);
     L2S_RMODE(4) L2S_RMODE(6) L2S_RMODE(8) L2S_RMODE(10) L2S_RMODE(12) L2S_RMODE(14)
+    L2S_RMODE(7) L2S_RMODE(11) L2S_RMODE(15)      // + a second branch output (p.res) next to the running sum
 #undef L2S_RMODE
     default: return cudaErrorInvalidValue;
   }

@@ -64,6 +64,10 @@ struct Knobs {
   long long layer_events = 0;      // record a cudaEvent pair around every launch of the next forwards
   long long par_share = 0;         // experiment: with branch_par, two-CTAs-per-SM step kernels launch ONE CTA per SM each, so CTAs of two
                                    // different branches (k = 3 epilogue-bound, k = 11 MMA-bound) share an SM
+  long long narrow_par = 0;        // C <= 64 stages run as three tap-by-tap whole-ResBlock kernels: branches 2 and 1 concurrently on two streams,
+                                   // branch 0 last adding both (bit-identical; measured neutral: 2514.2 vs 2514.0 us per step in the power-capped
+                                   // steady state, tools/knob_ab.py -- each kernel fills every SM, the second one only gets the first one's tail)
+  long long post_rows = 1;         // head: the row-per-thread kernel (C = 16 / 32), 0: the staged-tile kernel
   long long front_fuse = 1;        // the speaker projection runs inside the conditioning kernel (0: its own launch in front of it)
   long long branch_par = 1;        // C >= 128 stages: the kernel-size branches of a stage run on parallel streams (graph branches); only the
                                    // last step of a branch waits for the previous branch (running sum).  Fills the wave-quantisation tails.
@@ -607,7 +611,7 @@ int run_respk(l2s_vocoder* v, int i, int j0, int n_br, cudaStream_t st, int batc
 
 // One whole ResBlock: x -> x + sum of its steps, then the branch sum / mean epilogue.
 int run_res(l2s_vocoder* v, int i, int j, cudaStream_t st, int batch, int lin, const float* x, float* out_raw, void* out_act,
-            const float* acc_in, float div, float slope) {
+            const float* acc_in, float div, float slope, const float* acc_in2 = nullptr) {
   const l2s_config& c = v->cfg;
   ResParams P{};
   if (!branch_geom(v, i, j, lin, batch, &P.g)) return L2S_ERR_UNSUPPORTED;
@@ -632,6 +636,7 @@ int run_res(l2s_vocoder* v, int i, int j, cudaStream_t st, int batch, int lin, c
   p.out_raw = out_raw;
   p.out_act = out_act;
   p.acc_in = acc_in;
+  p.res = acc_in2;           // the output of a second, parallel branch (added before the running sum)
   p.batch = batch;
   p.lin = lin;
   p.cin_pad = g.c;
@@ -746,6 +751,35 @@ int run_chain(l2s_vocoder* v, cudaStream_t st, const Workspace& ws, int batch, i
                        nullptr, ws.acc, (float)c.n_rk, 0.1f);
         if (rc == L2S_OK) done = true;
         else if (rc != L2S_ERR_UNSUPPORTED) return rc;
+      }
+      // Three tap-by-tap whole-ResBlock branches: the two LARGER kernels (branches 2 and 1) run concurrently on two
+      // streams -- the CTAs of one fill the wave-quantisation tail of the other -- each writing its own buffer, and branch 0
+      // (the smallest kernel) runs last and adds both: ((x_0 + x_1) + x_2) / 3, bit-identical to the serial chain.
+      bool tri = !done && c.n_rk == 3 && g_knobs.narrow_par && !g_res_skew;
+      for (int j = 0; tri && j < c.n_rk; ++j) {
+        PkGeom pg;
+        ResGeom rg;
+        if (branch_pk_geom(v, i, j, 1, (int)len, batch, &pg) || !branch_geom(v, i, j, (int)len, batch, &rg)) tri = false;
+      }
+      if (tri) {
+        const bool fork = !g_knobs.layer_events && !g_knobs.span_ptr && !g_knobs.trace_ptr && v->ev_fork;
+        cudaStream_t s1 = fork ? v->br_stream[1] : st;
+        if (fork) {
+          cudaEventRecord(v->ev_fork, st);
+          cudaStreamWaitEvent(s1, v->ev_fork, 0);
+        }
+        rc = run_res(v, i, 2, st, batch, (int)len, ws.x, ws.acc, nullptr, nullptr, 1.f, 0.1f);
+        if (rc) return rc;
+        rc = run_res(v, i, 1, s1, batch, (int)len, ws.x, ws.y[1], nullptr, nullptr, 1.f, 0.1f);
+        if (rc) return rc;
+        if (fork) {
+          cudaEventRecord(v->ev_join[1], s1);
+          cudaStreamWaitEvent(st, v->ev_join[1], 0);
+        }
+        rc = run_res(v, i, 0, st, batch, (int)len, ws.x, want_raw ? ws.acc : nullptr, last_stage ? nullptr : ws.ma[cur ^ 1], ws.acc,
+                     (float)c.n_rk, 0.1f, ws.y[1]);
+        if (rc) return rc;
+        done = true;
       }
       for (int j = 0; !done && j < c.n_rk; ++j) {
         float* o_raw;
@@ -998,7 +1032,10 @@ int forward_impl(l2s_vocoder* v, void* stream, const int64_t* code, const void* 
   pp.c = v->stage_ch.back();
   dim3 grid((unsigned)((len + kPostTile - 1) / kPostTile), batch);
   timed_begin(v, st, "conv_post", 2.0 * pp.c * 7 * (double)batch * len);
-  if (pp.c == 16) post_kernel<16><<<grid, kPostTile, (kPostTile + 6) * post_pitch(pp.c) * sizeof(float), st>>>(pp);
+  const dim3 grid_rows((unsigned)((len + kPostRowsOut - 1) / kPostRowsOut), batch);
+  if (pp.c == 16 && g_knobs.post_rows) post_rows_kernel<16><<<grid_rows, kPostTile, 0, st>>>(pp);
+  else if (pp.c == 32 && g_knobs.post_rows) post_rows_kernel<32><<<grid_rows, kPostTile, 0, st>>>(pp);
+  else if (pp.c == 16) post_kernel<16><<<grid, kPostTile, (kPostTile + 6) * post_pitch(pp.c) * sizeof(float), st>>>(pp);
   else if (pp.c == 32) post_kernel<32><<<grid, kPostTile, (kPostTile + 6) * post_pitch(pp.c) * sizeof(float), st>>>(pp);
   else post_kernel<0><<<grid, kPostTile, (kPostTile + 6) * post_pitch(pp.c) * sizeof(float), st>>>(pp);
   timed_end(v, st);
@@ -1408,6 +1445,8 @@ int l2s_debug_set(const char* key, int64_t value) {
   else if (k == "max_ctas") g_knobs.max_ctas = value;
   else if (k == "embed_tap") g_knobs.embed_tap = value;
   else if (k == "front_fuse") g_knobs.front_fuse = value;
+  else if (k == "post_rows") g_knobs.post_rows = value;
+  else if (k == "narrow_par") g_knobs.narrow_par = value;
   else if (k == "layer_events") g_knobs.layer_events = value;
   else if (k == "branch_par") g_knobs.branch_par = value;
   else if (k == "par_share") g_knobs.par_share = value;

@@ -352,10 +352,11 @@ def test_whole_resblock_kernels_match_steps(pkg, weights, frames):
 
 
 @pytest.mark.parametrize("knob,value", [("res_mode", 1), ("res_mode", 2), ("res_quad_pct", 200), ("res_quad_pct", 0), ("res_cg2", 0), ("res_cg2", 1), ("res_msub", 2),
-                                        ("res_msub", 4), ("res_wide", 0)])
+                                        ("res_msub", 4), ("res_wide", 0), ("narrow_par", 1)])
 def test_whole_resblock_tilings_agree(pkg, weights, knob, value):
     """Tile size, CTAs per SM (1 / 2 / 4) and epilogue warps per CTA (8 / 4) of the whole-ResBlock kernel change the
-    schedule, not the arithmetic of any output element: the waveform must not change by a bit."""
+    schedule, not the arithmetic of any output element: the waveform must not change by a bit.  narrow_par: branches 2 and 1
+    of a narrow stage on two streams, branch 0 last with a two-input epilogue, ((x_0 + x_1) + x_2) / 3 like the serial chain."""
     h, sds = weights
     code, mel, spkr = vo.synthetic_inputs(3, 150, seed=33)
     g = make_gen(pkg, h, sds["trained"], "bf16")
@@ -372,6 +373,7 @@ def test_whole_resblock_tilings_agree(pkg, weights, knob, value):
         lib.l2s_debug_set(b"res_quad_pct", 115)
         lib.l2s_debug_set(b"res_cg2", 4)
         lib.l2s_debug_set(b"res_wide", 1)
+        lib.l2s_debug_set(b"narrow_par", 0)
     assert torch.isfinite(a).all()
     assert torch.equal(a, b), float((a - b).abs().max())
 
