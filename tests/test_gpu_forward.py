@@ -587,6 +587,14 @@ def test_stage1_outputs_straight_into_the_vocoder(pkg, weights):
     assert len(got) == 5
     for a, b in zip(got, expect):
         assert a.dtype == torch.int16 and torch.equal(a, b)
+    # ... and against the ORACLE: the utterance whose stage-1 mel is three frames longer than 2U (lengths reconciled as the
+    # dataset does) through the CPU restatement of the reference
+    code, mel, spkr = vo.synthetic_inputs(1, 22, seed=84)
+    ref = vo.mel_code_generator_forward(vo.fold_weight_norm(sds["trained"]), h, code, mel, spkr)
+    want = (ref.squeeze().double() * 32768.0).clamp(-32768, 32767).to(torch.int16)
+    lsb = int((got[4].cpu().int() - want.int()).abs().max())
+    print(f"[parity] stage-1 hand-off, 22 frames (+3 surplus mel frames) fp32 vs oracle: max {lsb} int16 LSB")
+    assert got[4].shape == want.shape and lsb <= 1
 
 
 @pytest.mark.parametrize("precision", ["bf16", "tf32", "fp32"])
@@ -711,6 +719,18 @@ def test_serve_vocoder_request_equals_per_utterance_flow(pkg, weights, tmp_path)
         ref_path = os.path.join(str(tmp_path), "ref.wav")
         wavfile.write(ref_path, 16000, expect[:n])
         assert open(pth, "rb").read() == open(ref_path, "rb").read()
+    # ... and against the ORACLE (not only against the CUDA path itself): the two shortest rows through the CPU restatement
+    # of the reference, quantised the way inference.py:79-81 does; the written files may differ by one int16 step at most
+    folded = vo.fold_weight_norm(sds["trained"])
+    for i in sorted(range(len(rows)), key=lambda k: rows[k].n_audio)[:2]:
+        feats, n = ho.load_item(fix, rows[i], code_dict)
+        ref = vo.mel_code_generator_forward(folded, h, *(torch.from_numpy(feats[k]).unsqueeze(0) for k in ("code", "mel", "spkr")))
+        want = (ref.squeeze().double() * 32768.0).clamp(-32768, 32767).numpy().astype("int16")[:n]
+        _, got = wavfile.read(paths[i])
+        assert got.shape == want.shape
+        lsb = int(np.abs(got.astype(np.int32) - want.astype(np.int32)).max())
+        print(f"[parity] /vocoder request, row {rows[i].uid} ({n} samples) fp32 vs oracle: max {lsb} int16 LSB")
+        assert lsb <= 1
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])

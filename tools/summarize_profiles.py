@@ -98,7 +98,7 @@ KEEP = ["sm__issue_active.avg.pct_of_peak_sustained_elapsed", "gpu__time_duratio
 for rep, what in (("prof_pair_stage1", "a fused ResBlock step of stage 1 (C=128)"),
                   ("prof_respk_stage3", "time-packed stage kernel of stage 3 (C=32, three ResBlocks k=3/7/11, dilations 1/3/5)"),
                   ("prof_conv_ups1", "polyphase ConvTranspose1d ups.1 (256 -> 128, k=8, u=4) in conv_tc_kernel"),
-                  ("prof_post", "post_kernel: leaky-ReLU(0.01) -> conv_post -> tanh"),
+                  ("prof_post", "post_rows_kernel: leaky-ReLU(0.01) -> conv_post -> tanh, one row per thread"),
                   ("prof_cond", "cond_multi_kernel: speaker projection + unit gather -> table-folded ConvT -> GELU -> fc -> concat (the whole front end in one launch)"),
                   ("prof_pk16k11", "time-packed kernel, one ResBlock per launch (pk_fuse=0, pk_chan=112): C=16, k=11")):
     path = os.path.join(G, rep + ".ncu-rep")
