@@ -165,6 +165,12 @@ __device__ __forceinline__ void epi_load_res(const ConvParams& p, const EpiChunk
   if constexpr ((MODE & kEpiRes) != 0) {
     const float* rp = p.res + c.e0;
     const int step = RPI * p.ntot;
+    if (p.pf & 4) {     // chained steps: the rows were written by a grid that may still be running -- read them at L2, never from L1
+#pragma unroll
+      for (int i = 0; i < ITERS; ++i, rp += step)
+        rv[i] = ((c.okmask >> i) & 1u) ? __ldcg(reinterpret_cast<const float4*>(rp)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      return;
+    }
 #pragma unroll
     for (int i = 0; i < ITERS; ++i, rp += step)
       rv[i] = ((c.okmask >> i) & 1u) ? *reinterpret_cast<const float4*>(rp) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -195,9 +201,11 @@ __device__ __forceinline__ void epi_prefetch(const ConvParams& p, const EpiChunk
   if (c4 != 0) return;
   const int step = RPI * p.ntot;
   if constexpr ((MODE & kEpiRes) != 0) {
+    if (!(p.pf & 4)) {
 #pragma unroll
-    for (int i = 0; i < ITERS; ++i)
-      if ((c.okmask >> i) & 1u) prefetch_l1(p.res + c.e0 + (long long)i * step);
+      for (int i = 0; i < ITERS; ++i)
+        if ((c.okmask >> i) & 1u) prefetch_l1(p.res + c.e0 + (long long)i * step);
+    }
   }
   if constexpr ((MODE & kEpiAcc) != 0) {
     if (p.acc_in) {

@@ -62,6 +62,12 @@ struct PairParams {
   PairGeom g;
   unsigned long long* span;   // debug: [0] min CTA start, [1] max CTA end (globaltimer), null in production
   long long* trace;      // debug timestamps of CTA 0 (see conv_tc.cuh), null in production
+  // Chained steps of a ResBlock (same k => same item grid): every item of a step counts its finished epilogue warps in
+  // done_flags[item]; the NEXT step is launched programmatically (it may occupy SMs as soon as CTAs of this grid exit),
+  // does not wait for this grid as a whole, and loads an item's input slab once wait_flags[item - 1 .. item + 1] (the
+  // items its halo touches, same utterance) are complete.  Null: plain stream order.
+  int* done_flags;
+  const int* wait_flags;
 };
 
 // swizzled 16-byte slot index inside a T row (matches the TMA / UMMA 128B, 64B, 32B swizzles)
@@ -366,7 +372,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the previous kernel's
   // tail; nothing below may read or write its data before it has completed.
   pdl_launch_dependents();
-  pdl_wait_prior_grid();
+  if (!P.wait_flags) pdl_wait_prior_grid();   // chained step: per-item flags instead (the previous step may still be running)
   const uint32_t tmem_base = *tmem_slot;
   const int acc_cols = g.msub * g.c;          // D1 at [0, acc_cols), D2 at [acc_cols, 2 acc_cols)
   // item walk: a CTA pair advances in lockstep (pair p handles items 2j + rank, j = p, p + pairs, ...)
@@ -389,6 +395,22 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int b = item / g.m_items;
       const int mi = item - b * g.m_items;
       const int row0 = mi * g.r_out - g.h2 - g.h1;          // first xa row of the slab
+      if (P.wait_flags && item < g.total_items) {
+        // the previous step's items this slab reads from (halo h1 + h2 < r_out: the neighbours at most)
+        if (lane == 0) {
+          const int lo = mi > 0 ? mi - 1 : 0, hi = mi + 1 < g.m_items ? mi + 1 : g.m_items - 1;
+          for (int nb = lo; nb <= hi; ++nb) {
+            const int* f = P.wait_flags + b * g.m_items + nb;
+            uint32_t spins = 0;
+            while (ld_acquire_gpu(f) < kTcEpiWarps) {
+              if (++spins > (1u << 24)) __trap();
+              __nanosleep(64);
+            }
+          }
+        }
+        __syncwarp();
+        fence_proxy_async_all();                            // rows written through the generic proxy, read by TMA
+      }
       if (g.alias_at && it_no > 0) {                        // the slabs overwrite the T slab of the previous item
         mbar_wait(t_free, ptf);
         ptf ^= 1u;
@@ -562,6 +584,19 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t pd1 = 0, pd2 = 0;
     uint32_t ph_res[2] = {0u, 0u};
     int it_no = 0;
+    int unpublished = -1;   // chained steps: the item whose stores this warp has issued but not yet counted in done_flags
+    // Counting an item needs a fence that waits for this warp's stores of it; done right after the stores it would expose
+    // their latency once per item, so the count of item i is published after phase 1 of item i + 1 (the stores are long
+    // out by then; the consumer's CTAs only become resident as CTAs of this grid exit) and at the end for the last item.
+    auto publish_item = [&]() {
+      if (unpublished >= 0) {
+        fence_proxy_async_all();
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) red_release_gpu_add(P.done_flags + unpublished, 1);
+        unpublished = -1;
+      }
+    };
     for (int w = walk0; w < walk_n; w += walkers, ++it_no) {
       const int item = g.cluster > 1 ? 2 * w + crank : w;
       const bool dummy = item >= g.total_items;             // odd item count: the pair's last partner stores nothing
@@ -609,6 +644,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) { if constexpr (CG2) mbar_arrive_cluster(t_full, 0u, (uint32_t)crank); else mbar_arrive(t_full); }   // CTA pair: the leader's MMA thread waits
       if (warp == 2) L2S_TRACE(2, it_no, 1);
+      publish_item();                    // the previous item's stores went out a whole phase 1 ago
       // ---- phase 2: D2 -> global (the wait on d2_full happens inside, after the first residual loads are issued)
       {
         const uint32_t t2 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc_cols;
@@ -627,11 +663,13 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         pd2 ^= 1u;
       }
       if (warp == 2) L2S_TRACE(2, it_no, 2);
+      if (P.done_flags && !dummy) unpublished = item;   // this warp's rows of the item are issued: counted later (publish_item)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { if constexpr (CG2) mbar_arrive_cluster(d2_empty, 0u, (uint32_t)crank); else mbar_arrive(d2_empty); }
       if (warp == 2) L2S_TRACE(2, it_no, 3);
     }
+    publish_item();
     if (EPI_TMA && lane == 0) bulk_wait_all();   // every TMA store has landed before the CTA exits
   }
 
@@ -781,7 +819,7 @@ inline cudaError_t launch_pair_mode(const PairParams& P, const CUtensorMap& tmA,
     attr[na].val.clusterDim.z = 1;
     ++na;
   }
-  if (g_tc_pdl) {   // programmatic dependent launch: this grid may start while the previous one drains
+  if (g_tc_pdl || P.wait_flags) {   // programmatic dependent launch: this grid may start while the previous one drains
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
@@ -797,17 +835,20 @@ inline cudaError_t launch_pair_mode(const PairParams& P, const CUtensorMap& tmA,
 #ifndef L2S_TU_PAIR_TC
 cudaError_t launch_pair_tc(const ConvParams& c, const float* bias1, const PairGeom& g, const CUtensorMap& tmA,
                            const CUtensorMap& tmW1, const CUtensorMap& tmW2, const PairEpiMaps& em, int num_ctas,
-                           cudaStream_t stream, long long* trace = nullptr, unsigned long long* span = nullptr);
+                           cudaStream_t stream, long long* trace = nullptr, unsigned long long* span = nullptr,
+                           const int* wait_flags = nullptr, int* done_flags = nullptr);
 #else
 cudaError_t launch_pair_tc(const ConvParams& c, const float* bias1, const PairGeom& g, const CUtensorMap& tmA,
                            const CUtensorMap& tmW1, const CUtensorMap& tmW2, const PairEpiMaps& em, int num_ctas,
-                           cudaStream_t stream, long long* trace, unsigned long long* span) {
+                           cudaStream_t stream, long long* trace, unsigned long long* span, const int* wait_flags, int* done_flags) {
   PairParams P;
   P.c = c;
   P.bias1 = bias1;
   P.g = g;
   P.trace = trace;
   P.span = span;
+  P.wait_flags = wait_flags;
+  P.done_flags = done_flags;
   const int cap = num_ctas * (g.dual ? 2 : 1);
   int grid = g.total_items < cap ? g.total_items : cap;
   if (grid < 1) grid = 1;

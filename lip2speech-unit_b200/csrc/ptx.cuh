@@ -113,6 +113,17 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait_prior_grid() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
 
+// ---- cross-kernel item flags (a dependent grid launched programmatically consumes the items of its predecessor one by one)
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+
 // ------------------------------------------------------------------ cluster
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

@@ -64,6 +64,10 @@ struct Knobs {
   long long layer_events = 0;      // record a cudaEvent pair around every launch of the next forwards
   long long par_share = 0;         // experiment: with branch_par, two-CTAs-per-SM step kernels launch ONE CTA per SM each, so CTAs of two
                                    // different branches (k = 3 epilogue-bound, k = 11 MMA-bound) share an SM
+  long long chain = 0;             // C >= 128 stages: steps 1.. of a ResBlock are launched programmatically and consume the previous step item by
+                                   // item (per-item completion counters) instead of waiting for the whole grid.  Bit-identical; measured with
+                                   // tools/knob_ab.py (BURST=1): 2451 -> 2418 us per step with serial branches, but 2399 -> 2415 us next to the
+                                   // parallel branch streams (branch_par, the default), which already fill the boundaries: off.  2: residual at L2.
   long long narrow_par = 0;        // C <= 64 stages run as three tap-by-tap whole-ResBlock kernels: branches 2 and 1 concurrently on two streams,
                                    // branch 0 last adding both (bit-identical; measured neutral: 2514.2 vs 2514.0 us per step in the power-capped
                                    // steady state, tools/knob_ab.py -- each kernel fills every SM, the second one only gets the first one's tail)
@@ -433,7 +437,8 @@ bool pairs_fused(const l2s_vocoder* v) { return is_bf16(v) && !g_knobs.force_sim
 // One fused ResBlock step  y = x + c2(lrelu(c1(xa)))  (bf16 tensor-core mode).  Returns
 // L2S_ERR_UNSUPPORTED when no fused plan exists (the caller then runs the two convs).
 int run_pair(l2s_vocoder* v, ConvLayer& c1, ConvLayer& c2, cudaStream_t st, int batch, int lin, const void* in_act,
-             const float* res, float* out_raw, void* out_act, const float* acc_in, float div, float slope) {
+             const float* res, float* out_raw, void* out_act, const float* acc_in, float div, float slope,
+             const int* wait_flags = nullptr, int* done_flags = nullptr) {
   if (c1.cin != c1.cout || c2.cin != c2.cout || c1.cin != c2.cin || c1.cin_pad != c1.cin || c1.k != c2.k || c2.dil != 1)
     return L2S_ERR_UNSUPPORTED;
   PairGeom g;
@@ -467,7 +472,10 @@ int run_pair(l2s_vocoder* v, ConvLayer& c1, ConvLayer& c2, cudaStream_t st, int 
   p.out_valid = (long long)lin * c2.cout;
   p.div = div;
   p.slope = slope;
-  p.pf = (int)g_knobs.epi_pf;
+  // chained step: the residual rows come from a grid that may still be running.  Plain (L1) loads are sound: the producer warp's
+  // ld.acquire.gpu of the item's counters precedes them in causality order (TMA -> mbarrier -> MMA -> commit -> epilogue wait);
+  // knob chain = 2 reads them at L2 instead (bit 4 of pf).
+  p.pf = (int)g_knobs.epi_pf | ((wait_flags && g_knobs.chain == 2) ? 4 : 0);
   timed_begin(v, st, c1.name + "+c2", 4.0 * c1.cin * c1.cout * c1.k * (double)batch * lin);
   int ctas = g_knobs.max_ctas > 0 ? (int)g_knobs.max_ctas : v->num_sms;
   if (g_knobs.par_share && g_knobs.branch_par && g.dual) ctas = (ctas + 1) / 2;   // launch_pair_tc doubles it for dual plans
@@ -489,7 +497,8 @@ int run_pair(l2s_vocoder* v, ConvLayer& c1, ConvLayer& c2, cudaStream_t st, int 
   ++v->pair_launches;
   unsigned long long* span = g_knobs.span_ptr ? reinterpret_cast<unsigned long long*>(g_knobs.span_ptr) + 2 * v->tc_launches : nullptr;
   ++v->tc_launches;
-  cudaError_t e = launch_pair_tc(p, c1.bias_dev, g, tmA, c1.tmW, c2.tmW, em, ctas, st, trace, span);
+  if (g.epi_tma) { wait_flags = nullptr; done_flags = nullptr; }   // TMA-store epilogue: its completion is not covered by the flags
+  cudaError_t e = launch_pair_tc(p, c1.bias_dev, g, tmA, c1.tmW, c2.tmW, em, ctas, st, trace, span, wait_flags, done_flags);
   timed_end(v, st);
   if (e != cudaSuccess) return fail(v, L2S_ERR_CUDA, std::string("launch pair ") + c1.name + ": " + cudaGetErrorString(e));
   return L2S_OK;
@@ -670,6 +679,8 @@ struct Workspace {
   void *ya[L2S_MAX_RK], *ta[L2S_MAX_RK];   // per branch: activated copies (ping-pong)
   float* spk_vec;
   float* embed;
+  int* flags;               // per-item completion counters of the chained ResBlock steps (zeroed at the start of every forward)
+  size_t flags_bytes;
   size_t bytes;
 };
 
@@ -708,6 +719,14 @@ Workspace carve(const l2s_vocoder* v, int batch, int frames, uint8_t* base) {
   w.spk_vec = (float*)take((size_t)batch * c.embedding_dim * 4);
   const int units = c.variant == L2S_VARIANT_MULTI_INPUT ? frames / 2 : frames;
   w.embed = (float*)take((size_t)batch * units * c.embedding_dim * 4);
+  // one counter per (stage, branch, step, item); an item has at least 100 output rows (128-row tiles minus the c2 halo)
+  {
+    size_t per_utt = 0;
+    long long l2 = frames;
+    for (int i = 0; i < c.n_ups; ++i) { l2 *= c.up_rates[i]; per_utt += (size_t)(l2 / 100 + 2); }
+    w.flags_bytes = (size_t)batch * per_utt * c.n_rk * c.n_dil * sizeof(int);
+    w.flags = (int*)take(w.flags_bytes);
+  }
   w.bytes = off;
   return w;
 }
@@ -719,6 +738,10 @@ int run_chain(l2s_vocoder* v, cudaStream_t st, const Workspace& ws, int batch, i
   const l2s_config& c = v->cfg;
   ConvLayer& pre = v->convs[v->conv_pre];
   *stopped = true;
+  // chained ResBlock steps (pair_tc.cuh): their per-item counters start at zero in every forward (a memset node in the graph)
+  const bool chain_ok = g_knobs.chain && ws.flags && !g_knobs.layer_events && !g_knobs.span_ptr && !g_knobs.trace_ptr && g_knobs.epi_tma == 0;
+  if (chain_ok) cudaMemsetAsync(ws.flags, 0, ws.flags_bytes, st);
+  size_t flag_off = 0;     // ints handed out so far
   // ---- conv_pre (its consumer applies leaky_relu(0.1): emit the activated copy only)
   int rc = run_conv(v, pre, st, batch, frames, ws.cond, nullptr, ws.ma[0], nullptr, nullptr, 1.f, 0.1f);
   if (rc) return rc;
@@ -820,6 +843,25 @@ int run_chain(l2s_vocoder* v, cudaStream_t st, const Workspace& ws, int batch, i
     for (int j = 0; !whole && j < c.n_rk; ++j) {
       cudaStream_t sj = (par && j > 0) ? v->br_stream[j] : st;
       const int bj = par ? j : 0;                              // serial: every branch reuses buffer set 0
+      // Chain the steps of this branch when they share one item grid (same k: r_out and m_items of every step agree):
+      // step m + 1 is launched programmatically and consumes step m item by item (wait_flags / done_flags).
+      int chain_items = 0;
+      if (chain_ok && stage_fused && c.n_dil > 1) {
+        bool same = true;
+        PairGeom g0{};
+        for (int m = 0; m < c.n_dil && same; ++m) {
+          const ConvLayer& a1 = v->convs[v->rb_c1[i][j][m]];
+          PairGeom pg;
+          if (!pair_plan(a1.cin, a1.k, a1.dil, (int)len, batch, (int)g_knobs.pair_smem, g_knobs.dual != 0, g_knobs.cluster != 0,
+                         g_knobs.alias_at != 0, false, false, &pg) || pg.epi_tma)
+            same = false;
+          else if (m == 0) g0 = pg;
+          else if (pg.r_out != g0.r_out || pg.m_items != g0.m_items || pg.total_items != g0.total_items) same = false;
+        }
+        if (same && (flag_off + (size_t)(c.n_dil - 1) * g0.total_items) * sizeof(int) <= ws.flags_bytes) chain_items = g0.total_items;
+      }
+      int* step_flags[L2S_MAX_DIL] = {nullptr};
+      for (int m = 0; chain_items > 0 && m < c.n_dil - 1; ++m) { step_flags[m] = ws.flags + flag_off; flag_off += (size_t)chain_items; }
       for (int m = 0; m < c.n_dil; ++m) {
         ConvLayer& c1 = v->convs[v->rb_c1[i][j][m]];
         ConvLayer& c2 = v->convs[v->rb_c2[i][j][m]];
@@ -843,7 +885,13 @@ int run_chain(l2s_vocoder* v, cudaStream_t st, const Workspace& ws, int batch, i
         }
         if (par && m == c.n_dil - 1 && j > 0) cudaStreamWaitEvent(sj, v->ev_acc[j - 1], 0);   // the running sum of the previous branch
         if (stage_fused) {
-          rc = run_pair(v, c1, c2, sj, batch, (int)len, in1, res, o_raw, o_act, a_in, dv, 0.1f);
+          // A step that also waits for another stream's event (the running sum of the previous branch) is NOT chained: in a
+          // captured graph every incoming edge of a programmatically launched node becomes programmatic, so it would start
+          // before that branch has finished, and the running sum is not covered by the item counters.
+          const bool ev_dep = par && m == c.n_dil - 1 && j > 0;
+          rc = run_pair(v, c1, c2, sj, batch, (int)len, in1, res, o_raw, o_act, a_in, dv, 0.1f,
+                        (chain_items > 0 && m > 0 && !ev_dep) ? step_flags[m - 1] : nullptr,
+                        (chain_items > 0 && m < c.n_dil - 1) ? step_flags[m] : nullptr);
           if (rc == L2S_ERR_UNSUPPORTED) return fail(v, L2S_ERR_STATE, "fused plan vanished for " + c1.name);
         } else {
           rc = run_conv(v, c1, sj, batch, (int)len, in1, nullptr, ws.ta[bj], nullptr, nullptr, 1.f, 0.1f);
@@ -1447,6 +1495,7 @@ int l2s_debug_set(const char* key, int64_t value) {
   else if (k == "front_fuse") g_knobs.front_fuse = value;
   else if (k == "post_rows") g_knobs.post_rows = value;
   else if (k == "narrow_par") g_knobs.narrow_par = value;
+  else if (k == "chain") g_knobs.chain = value;
   else if (k == "layer_events") g_knobs.layer_events = value;
   else if (k == "branch_par") g_knobs.branch_par = value;
   else if (k == "par_share") g_knobs.par_share = value;

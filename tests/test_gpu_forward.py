@@ -470,10 +470,12 @@ def test_packed_vs_tap_by_tap_whole_resblock(pkg, weights, batch, frames):
     check(ref, outs[1], "bf16", f"time-packed whole-ResBlock {batch}x{frames}")
 
 
-@pytest.mark.parametrize("knob", ["dual", "cluster", "cg2", "alias_at", "epi_tma", "pdl"])
+@pytest.mark.parametrize("knob", ["dual", "cluster", "cg2", "alias_at", "epi_tma", "pdl", "chain"])
 def test_fused_kernel_variants_agree(pkg, weights, knob):
     """Two-CTAs-per-SM plans (dual), CTA pairs (cluster) with plain weight multicast or cta_group::2 MMAs (cg2) and
-    the other fused-step variants change scheduling only: the waveform must not change by a bit."""
+    the other fused-step variants change scheduling only: the waveform must not change by a bit.  chain: steps 1 and 2 of a
+    ResBlock launched programmatically, consuming the previous step item by item through completion counters (three
+    forwards per setting: eager, graph capture, graph replay)."""
     h, sds = weights
     code, mel, spkr = vo.synthetic_inputs(3, 150, seed=33)
     g = make_gen(pkg, h, sds["trained"], "bf16")
@@ -483,8 +485,11 @@ def test_fused_kernel_variants_agree(pkg, weights, knob):
         lib.l2s_debug_set(b"fuse_branch", 0)      # exercise the per-step kernels on every stage
         for v in (0, 1):
             lib.l2s_debug_set(knob.encode(), v)
-            outs.append(g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV)).clone())
+            for _ in range(3 if knob == "chain" else 1):
+                y = g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV)).clone()
+            outs.append(y)
     finally:
+        lib.l2s_debug_set(b"chain", 0)
         lib.l2s_debug_set(b"dual", 1)
         lib.l2s_debug_set(b"cluster", 1)
         lib.l2s_debug_set(b"cg2", 1)

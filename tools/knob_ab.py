@@ -1,10 +1,13 @@
 """Interleaved A/B timing of knob settings on the cfg2 forward (graph replay, 20 forwards per sample, best and median of
 the samples; settings alternate so that the power-capped clock drift hits all of them alike), plus output equality.
+BURST=1 in the environment: one second of idle before every sample (the 20 timed forwards then run at burst clocks like
+bench.py's timed region; back to back the GPU sits at its power cap and any setting that fills idle time just lowers the clock).
 
     python tools/knob_ab.py "narrow_par=0" "narrow_par=1" "post_rows=0" ...      ("-" = defaults)
 """
 import os
 import statistics
+import time
 import sys
 
 import torch
@@ -37,13 +40,16 @@ def restore(s, defaults):
         lib.l2s_debug_set(k.encode(), defaults[k])
 
 
-DEFAULTS = dict(narrow_par=1, post_rows=1, front_fuse=1, res_skew=0, pack=1, branch_par=1, use_graph=1, res_wide=1, res_cg2=4, pk_chan=32)
+DEFAULTS = dict(chain=0, fuse_branch=1, dual=1, cluster=1, narrow_par=0, post_rows=1, front_fuse=1, res_skew=0, pack=1, branch_par=1, use_graph=1, res_wide=1, res_cg2=4, pk_chan=32)
 samples = [[] for _ in settings]
 outs = [None] * len(settings)
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
 for rnd in range(6):
     for i, s in enumerate(settings):
         apply(s)
+        if os.environ.get("BURST"):
+            torch.cuda.synchronize()
+            time.sleep(1.0)
         for _ in range(3):
             o = g(code=code, mel=mel, spkr=spkr)
         torch.cuda.synchronize()
