@@ -8,6 +8,7 @@
  *                         (multi_input_vocoder/dataset_multi_input.py:174, :219-241) followed by the collate into a batch
  *   l2s_io_write_wav_i16  scipy.io.wavfile.write(path, 16000, int16 audio) of inference.py:152-165 and
  *                         inference_server.py:133-146, for every utterance of a batch
+ *   l2s_io_units_to_ids   code_to_sequence (dataset_multi_input.py:128-141) for every row of a batch
  * Both run the files of one call on `threads` host threads and return when all files are done.
  */
 #ifndef L2S_HAND_OFF_H
@@ -46,6 +47,15 @@ int l2s_io_read_npy_f32(const char* const* paths, int32_t n, float* dst, int64_t
  * Directories must exist.  Returns L2S_IO_OK, or the status of the first failing file with its index in *bad. */
 int l2s_io_write_wav_i16(const char* const* paths, int32_t n, const int16_t* samples, int64_t stride, const int32_t* n_samples,
                          int32_t rate, int32_t threads, int32_t* bad);
+
+/* Unit strings -> dictionary indices for n manifest rows: line i (the .unt line of the row, tokens separated by blanks, an
+ * optional "name|" prefix already removed) is split, every token is looked up in dict_tokens (token j of dict.unt.txt maps
+ * to j; tokens absent from the dictionary are DROPPED, the collapse_code = False branch of
+ * multi_input_vocoder/dataset_multi_input.py:128-141), and the first min(count, max_ids[i]) indices land at
+ * out + i * out_stride; n_out[i] receives the number of known tokens of the line (before the cap).  One call per batch
+ * replaces n list comprehensions over a Python dict (5-7 ms of interpreter time per 128-utterance request). */
+int l2s_io_units_to_ids(const char* const* lines, int32_t n, const char* const* dict_tokens, int32_t n_dict, int64_t* out,
+                        int64_t out_stride, const int32_t* max_ids, int32_t* n_out, int32_t threads);
 
 #ifdef __cplusplus
 }

@@ -44,7 +44,7 @@ EXPORTS = [
     "l2s_create", "l2s_destroy", "l2s_set_weight", "l2s_finalize", "l2s_workspace_bytes", "l2s_hop",
     "l2s_forward", "l2s_forward_i16", "l2s_poll_index_error", "l2s_launch_count", "l2s_last_error",
     "l2s_version", "l2s_debug_tap", "l2s_debug_conv", "l2s_debug_set", "l2s_debug_layer_time",
-    "l2s_io_read_npy_f32", "l2s_io_write_wav_i16",            # include/l2s_hand_off.h
+    "l2s_io_read_npy_f32", "l2s_io_write_wav_i16", "l2s_io_units_to_ids",            # include/l2s_hand_off.h
 ]
 IO_OK, IO_ERR_ARG, IO_ERR_OPEN, IO_ERR_FORMAT = range(4)
 IO_REQUIRE_1D, IO_REQUIRE_2D, IO_REQUIRE_F32 = 1, 2, 4
@@ -100,6 +100,8 @@ def load():
     lib.l2s_io_read_npy_f32.restype = C.c_int
     lib.l2s_io_write_wav_i16.argtypes = [pp, i32, vp, i64, ip, i32, i32, ip]
     lib.l2s_io_write_wav_i16.restype = C.c_int
+    lib.l2s_io_units_to_ids.argtypes = [pp, i32, pp, i32, vp, i64, ip, ip, i32]
+    lib.l2s_io_units_to_ids.restype = C.c_int
     _lib = lib
     return lib
 

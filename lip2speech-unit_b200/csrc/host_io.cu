@@ -11,7 +11,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string_view>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/l2s_hand_off.h"
@@ -203,3 +205,35 @@ extern "C" int l2s_io_write_wav_i16(const char* const* paths, int32_t n, const i
     if (!paths[i] || n_samples[i] < 0 || n_samples[i] > stride) return L2S_IO_ERR_ARG;
   return run_jobs(n, threads, bad, [&](int i) { return write_one_wav(paths[i], samples + (int64_t)i * stride, n_samples[i], rate); });
 }
+
+extern "C" int l2s_io_units_to_ids(const char* const* lines, int32_t n, const char* const* dict_tokens, int32_t n_dict, int64_t* out,
+                                   int64_t out_stride, const int32_t* max_ids, int32_t* n_out, int32_t threads) {
+  if (n < 0 || n_dict < 0 || (n > 0 && (!lines || !out || !max_ids || !n_out)) || (n_dict > 0 && !dict_tokens)) return L2S_IO_ERR_ARG;
+  for (int i = 0; i < n; ++i)
+    if (!lines[i] || max_ids[i] < 0 || max_ids[i] > out_stride) return L2S_IO_ERR_ARG;
+  std::unordered_map<std::string_view, int64_t> dict;
+  dict.reserve((size_t)n_dict * 2 + 1);
+  for (int j = 0; j < n_dict; ++j) {
+    if (!dict_tokens[j]) return L2S_IO_ERR_ARG;
+    dict[std::string_view(dict_tokens[j])] = j;            // a repeated token keeps its LAST index, like the dict comprehension
+  }
+  auto is_blank = [](char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\f' || c == '\v'; };   // str.split()
+  return run_jobs(n, threads, nullptr, [&](int i) {
+    const char* p = lines[i];
+    int64_t* dst = out + (int64_t)i * out_stride;
+    int32_t count = 0;
+    while (*p) {
+      while (*p && is_blank(*p)) ++p;
+      const char* b = p;
+      while (*p && !is_blank(*p)) ++p;
+      if (p == b) break;
+      const auto it = dict.find(std::string_view(b, (size_t)(p - b)));
+      if (it == dict.end()) continue;                       // unknown token: dropped
+      if (count < max_ids[i]) dst[count] = it->second;
+      ++count;
+    }
+    n_out[i] = count;
+    return (int)L2S_IO_OK;
+  });
+}
+

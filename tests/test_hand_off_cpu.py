@@ -189,3 +189,35 @@ def test_native_io_argument_checks(pkg):
     cap[0] = 1
     assert lib.l2s_io_read_npy_f32(paths, 1, buf.ctypes.data, 80, cap.ctypes.data_as(ip), 80, 0, rows.ctypes.data_as(ip), 1, C.byref(bad)) == cabi.IO_ERR_OPEN
     assert bad.value == 0
+
+
+def test_native_units_to_ids_matches_code_to_sequence(pkg):
+    """l2s_io_units_to_ids against code_to_sequence (dataset_multi_input.py:128-141, collapse_code = False): the shipped
+    lrs3 rows, unknown tokens dropped, blank runs / tabs / trailing newline, the cap, an empty line."""
+    import ctypes as C
+    ho = pkg.hand_off
+    lib = pkg._cabi.load()
+    fix = FIX
+    _, rows = ho.parse_manifest(os.path.join(fix, "label", "test.tsv"))
+    code_dict = ho.load_code_dict(os.path.join(fix, "label", "dict.unt.txt"))
+    lines = [r.units for r in rows] + ["7  9\t11 nope 3 \n", "", "   ", "x y z", " ".join(str(i % 200) for i in range(1000))]
+    want = [ho.code_to_sequence(ln.split(), code_dict) for ln in lines]
+    n = len(lines)
+    cap = np.asarray([max(len(w), 1) for w in want], dtype=np.int32)
+    cap[-1] = 17                                                    # fewer slots than tokens: the count still reports all of them
+    out = np.full((n, int(cap.max())), -1, dtype=np.int64)
+    n_out = np.zeros(n, dtype=np.int32)
+    ip = C.POINTER(C.c_int32)
+    st = lib.l2s_io_units_to_ids(ho._c_paths(lines), n, ho._dict_tokens(code_dict), len(code_dict), out.ctypes.data, out.strides[0] // 8,
+                                 cap.ctypes.data_as(ip), n_out.ctypes.data_as(ip), 3)
+    assert st == pkg._cabi.IO_OK
+    for k in range(n):
+        assert n_out[k] == len(want[k]), k
+        m = min(len(want[k]), int(cap[k]))
+        assert out[k, :m].tolist() == want[k][:m], k
+        assert (out[k, m:] == -1).all()                             # nothing written past the cap / the count
+    assert n_out[len(rows)] == 4 and n_out[len(rows) + 1] == 0 and n_out[len(rows) + 3] == 0
+    # argument checks
+    assert lib.l2s_io_units_to_ids(None, 1, ho._dict_tokens(code_dict), len(code_dict), out.ctypes.data, 4, cap.ctypes.data_as(ip),
+                                   n_out.ctypes.data_as(ip), 1) == pkg._cabi.IO_ERR_ARG
+
