@@ -54,9 +54,9 @@ def parse_manifest(manifest_path: str, max_keep: Optional[int] = None, min_keep:
             items = line.strip().split("\t")
             code = line_code.strip().split("|")[-1]
             sz = int(items[-2])
-            diff = len(code.split()) - sz * 2
-            if not -2 <= diff <= 2:
-                raise ValueError(f"{items[0]}: code length {len(code.split())} != video length * 2 ({sz * 2})")
+            n_tok = len(code.split())
+            if not -2 <= n_tok - sz * 2 <= 2:
+                raise ValueError(f"{items[0]}: code length {n_tok} != video length * 2 ({sz * 2})")
             if min_keep is not None and sz < min_keep:
                 continue
             if max_keep is not None and sz > max_keep:
@@ -393,10 +393,7 @@ def serve_vocoder_request(generator, dataset_dir: str, out_dir: str, split: str 
     _, rows = parse_manifest(manifest)
     code_dict = load_code_dict(code_dict_path or os.path.join(dataset_dir, "label", "dict.unt.txt"))
     dev = torch.device(device)
-    paths = [os.path.join(out_dir, output_name(r) + ".wav") for r in rows]
-    for d in {os.path.dirname(p) for p in paths}:
-        os.makedirs(d, exist_ok=True)
-
+    paths: List[str] = []                                 # filled below, while the first groups are already loading
     num_mels = int(getattr(getattr(generator, "h", None), "num_mels", 80) or 80)
 
     def load_group(idxs):
@@ -410,6 +407,9 @@ def serve_vocoder_request(generator, dataset_dir: str, out_dir: str, split: str 
     pipe = HostPipeline(generator, dev)
     with ThreadPoolExecutor(max_workers=max(2, io_threads)) as pool:
         loads = [pool.submit(load_group, g_) for g_ in groups]               # later groups load while earlier ones run
+        paths.extend(os.path.join(out_dir, output_name(r) + ".wav") for r in rows)   # off the critical path: the loaders are native
+        for d in {os.path.dirname(p) for p in paths}:
+            os.makedirs(d, exist_ok=True)
         writers = []
         for fut in loads:
             for grp, code, mel, spk, wav in fut.result():
