@@ -50,10 +50,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug traps (the launch fails with an error the host
 // reports) instead of hanging the GPU.
+// L2S_WAIT_BACKOFF_AFTER > 0 (build-time experiment): after that many failed polls the warp sleeps L2S_WAIT_BACKOFF_NS between
+// polls.  The polls of a long wait are real instructions (ncu counts 4.3 M executions of one TRYWAIT in a 250 us whole-ResBlock
+// launch); whether giving them up pays depends on the regime -- see DESIGN.md section 4.
+#ifndef L2S_WAIT_BACKOFF_AFTER
+#define L2S_WAIT_BACKOFF_AFTER 0
+#endif
+#ifndef L2S_WAIT_BACKOFF_NS
+#define L2S_WAIT_BACKOFF_NS 64
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 26)) __trap();
+    if (L2S_WAIT_BACKOFF_AFTER > 0 && spins > (uint32_t)L2S_WAIT_BACKOFF_AFTER) __nanosleep(L2S_WAIT_BACKOFF_NS);
   }
 }
 

@@ -100,7 +100,9 @@ for rep, what in (("prof_pair_stage1", "a fused ResBlock step of stage 1 (C=128)
                   ("prof_conv_ups1", "polyphase ConvTranspose1d ups.1 (256 -> 128, k=8, u=4) in conv_tc_kernel"),
                   ("prof_post", "post_rows_kernel: leaky-ReLU(0.01) -> conv_post -> tanh, one row per thread"),
                   ("prof_cond", "cond_multi_kernel: speaker projection + unit gather -> table-folded ConvT -> GELU -> fc -> concat (the whole front end in one launch)"),
-                  ("prof_pk16k11", "time-packed kernel, one ResBlock per launch (pk_fuse=0, pk_chan=112): C=16, k=11")):
+                  ("prof_pk16k11", "time-packed kernel, one ResBlock per launch (pk_fuse=0, pk_chan=112): C=16, k=11"),
+                  ("prof_res_stage2_k11", "res_tc_kernel: whole ResBlock C=64, k=11 (one CTA per SM, sixteen epilogue warps, CTA pairs), the default plan"),
+                  ("prof_resq_stage2_k11", "resq_tc_kernel: the same ResBlock with the skewed schedule (pack=0 res_mode=2 res_skew=1; off by default)")):
     path = os.path.join(G, rep + ".ncu-rep")
     if not os.path.exists(path):
         continue
