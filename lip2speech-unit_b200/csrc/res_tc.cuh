@@ -47,6 +47,7 @@ struct ResGeom {
   int tb, n_tstages, bstage_bytes, sb;
   int tmem_cols, cw, dual, tile_words;
   int ne;                   // epilogue warps: 8, or 4 in the four-CTAs-per-SM plans (one warp per TMEM lane quadrant)
+  int iss2;                 // 1: a second MMA-issuing warp (index 2 + ne) takes the upper half of the accumulators
   int ctas_per_sm;          // 1, 2 (dual) or 4 (quad)
   int cg2;                  // 1: CTA pairs (cluster of 2) issue cta_group::2 MMAs; a CTA keeps half of every weight stage
   uint32_t idesc;
@@ -375,9 +376,10 @@ res_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 2 * g.n_dil; ++i) tma_prefetch_desc(&maps.w[i]);
-    for (int i = 0; i < g.sb; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    const uint32_t n_iss = g.iss2 ? 2u : 1u;               // every issuing warp commits to b_empty / d_full
+    for (int i = 0; i < g.sb; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], n_iss); }
     mbar_init(s_full, (uint32_t)(CG2 ? 2 * g.ne : g.ne));
-    mbar_init(d_full, 1);
+    mbar_init(d_full, n_iss);
     fence_barrier_init();
   }
   if (warp == 1) { if constexpr (CG2) tmem_alloc_cg2(tmem_slot, (uint32_t)g.tmem_cols); else tmem_alloc_dyn(tmem_slot, (uint32_t)g.tmem_cols); }
@@ -450,17 +452,21 @@ res_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
         }
       }
     }
-  } else if (warp == 1) {
-    // -------------------------------------------------------------- MMA issuer
+  } else if (warp == 1 || (g.iss2 && warp == 2 + g.ne)) {
+    // -------------------------------------------------------------- MMA issuer(s)
+    // iss2: warp 1 issues for accumulators [0, ceil(msub / 2)), warp 2 + ne for the rest; both wait for the same s_full /
+    // b_full completions and both commit to b_empty / d_full (count 2).  Every accumulator still sees its MMAs in the same order.
     const bool leader = elect_one();
     const uint64_t tmpl = umma_desc_template((uint32_t)g.rb);
     const uint32_t desc_hi = (uint32_t)(tmpl >> 32);
     const uint32_t desc_lo_fixed = (uint32_t)tmpl;
     const uint32_t row_step = (uint32_t)g.rb >> 4;
-    const uint32_t s_lo = desc_lo_fixed | ((smem_u32(slab) & 0x3FFFFu) >> 4);
+    const int acc_first = (g.iss2 && warp != 1) ? (g.msub + 1) / 2 : 0;
+    const int acc_count = g.iss2 ? (warp == 1 ? (g.msub + 1) / 2 : g.msub / 2) : g.msub;
+    const uint32_t s_lo = (desc_lo_fixed | ((smem_u32(slab) & 0x3FFFFu) >> 4)) + (uint32_t)acc_first * ((128u * (uint32_t)g.rb) >> 4);
     int ib = 0;
     uint32_t pb = 0, ps = 0;
-    int ntr = 0;
+    int ntr = warp == 1 ? 0 : 128;     // trace stamps: the first issuer only
     auto commit = [&](uint64_t* bar) { if constexpr (CG2) umma_commit_cg2(bar, (uint16_t)3); else umma_commit(bar); };
     for (int wk = (CG2 && crank != 0) ? walk_n : walk0; wk < walk_n; wk += walkers) {   // CTA pair: the leader issues for both
       for (int cv = 0; cv < 2 * g.n_dil; ++cv) {
@@ -474,15 +480,15 @@ res_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
         tc_fence_after();
         L2S_RTRACE(128, ntr);
         const uint32_t a_tap0 = s_lo + (uint32_t)(g.pad - halo) * row_step;
-        const uint32_t d_base = second ? tmem_base : tmem_base + (uint32_t)acc_cols;   // c2 accumulates onto X, c1 onto its bias
+        const uint32_t d_base = (second ? tmem_base : tmem_base + (uint32_t)acc_cols) + (uint32_t)(acc_first * g.c);   // c2 accumulates onto X, c1 onto its bias
         for (int ts = 0; ts < g.n_tstages; ++ts) {
           mbar_wait(&b_full[ib], pb);
           tc_fence_after();
           const uint32_t b_lo = desc_lo_fixed | ((smem_u32(stageB + (size_t)ib * g.bstage_bytes) & 0x3FFFFu) >> 4);
           const int t_end = min(g.tb, g.k - ts * g.tb);
-          if (g.c == 64) res_issue_stage<64, CG2>(leader, g.msub, desc_hi, a_tap0, (uint32_t)dil * row_step, b_lo, ts * g.tb, t_end, d_base);
-          else if (g.c == 32) res_issue_stage<32, CG2>(leader, g.msub, desc_hi, a_tap0, (uint32_t)dil * row_step, b_lo, ts * g.tb, t_end, d_base);
-          else res_issue_stage<16, CG2>(leader, g.msub, desc_hi, a_tap0, (uint32_t)dil * row_step, b_lo, ts * g.tb, t_end, d_base);
+          if (g.c == 64) res_issue_stage<64, CG2>(leader, acc_count, desc_hi, a_tap0, (uint32_t)dil * row_step, b_lo, ts * g.tb, t_end, d_base);
+          else if (g.c == 32) res_issue_stage<32, CG2>(leader, acc_count, desc_hi, a_tap0, (uint32_t)dil * row_step, b_lo, ts * g.tb, t_end, d_base);
+          else res_issue_stage<16, CG2>(leader, acc_count, desc_hi, a_tap0, (uint32_t)dil * row_step, b_lo, ts * g.tb, t_end, d_base);
           if (leader) commit(&b_empty[ib]);
           if (++ib == g.sb) { ib = 0; pb ^= 1u; }
         }
@@ -574,6 +580,9 @@ res_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
 
 // ------------------------------------------------------------------ host side
 
+inline int g_res_iss2 = 0;  // knob res_iss2: the sixteen-warp (WIDE) plans issue their MMAs from TWO warps, each owning half of the tile's
+                            // accumulators.  Bit-identical, measured neutral (C = 64, k = 11: 225.5 vs 225.7 us): in this kernel the issuing
+                            // warp has its scheduler to itself while the MMAs run, and one warp keeps the tensor pipe fed; off.
 inline int g_res_wide = 1;  // knob res_wide: one-CTA-per-SM plans use sixteen epilogue warps (WIDE kernels)
 inline int g_res_cg2 = 4;   // whole-ResBlock plans run as CTA pairs issuing cta_group::2 MMAs (knob res_cg2: 0 off, 1 one-CTA-per-SM
                             // plans only, 2 + dual, 3 + quad, 4 + C = 16)
@@ -617,6 +626,7 @@ inline bool res_plan_with(int c, int k, int n_dil, const int* dil, int lin, int 
   if (cols > (kind == 2 ? 128 : (dual ? 256 : 512))) return false;
   g.tmem_cols = cols;
   g.ne = kind == 2 ? 4 : ((kind == 0 && g_res_wide) ? 16 : kTcEpiWarps);
+  g.iss2 = (g.ne == 16 && g_res_iss2 && !skew && msub >= 2) ? 1 : 0;
   g.ctas_per_sm = kind == 2 ? 4 : (dual ? 2 : 1);
   int tb = 1;
   while (tb < k && tb < 16 && (tb * 2) * c * g.rb <= 16384) tb *= 2;
@@ -725,7 +735,7 @@ inline cudaError_t launch_res_mode(const ResParams& P, const ResMaps& maps, int 
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3((unsigned)(64 + 32 * P.g.ne));
+  cfg.blockDim = dim3((unsigned)(64 + 32 * P.g.ne + (P.g.iss2 ? 32 : 0)));
   cfg.dynamicSmemBytes = (size_t)P.g.smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

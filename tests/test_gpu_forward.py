@@ -352,7 +352,7 @@ def test_whole_resblock_kernels_match_steps(pkg, weights, frames):
 
 
 @pytest.mark.parametrize("knob,value", [("res_mode", 1), ("res_mode", 2), ("res_quad_pct", 200), ("res_quad_pct", 0), ("res_cg2", 0), ("res_cg2", 1), ("res_msub", 2),
-                                        ("res_msub", 4), ("res_wide", 0), ("narrow_par", 1)])
+                                        ("res_msub", 4), ("res_wide", 0), ("narrow_par", 1), ("res_iss2", 1)])
 def test_whole_resblock_tilings_agree(pkg, weights, knob, value):
     """Tile size, CTAs per SM (1 / 2 / 4) and epilogue warps per CTA (8 / 4) of the whole-ResBlock kernel change the
     schedule, not the arithmetic of any output element: the waveform must not change by a bit.  narrow_par: branches 2 and 1
@@ -374,6 +374,7 @@ def test_whole_resblock_tilings_agree(pkg, weights, knob, value):
         lib.l2s_debug_set(b"res_cg2", 4)
         lib.l2s_debug_set(b"res_wide", 1)
         lib.l2s_debug_set(b"narrow_par", 0)
+        lib.l2s_debug_set(b"res_iss2", 0)
     assert torch.isfinite(a).all()
     assert torch.equal(a, b), float((a - b).abs().max())
 

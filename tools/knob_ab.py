@@ -40,7 +40,7 @@ def restore(s, defaults):
         lib.l2s_debug_set(k.encode(), defaults[k])
 
 
-DEFAULTS = dict(chain=0, fuse_branch=1, dual=1, cluster=1, narrow_par=0, post_rows=1, front_fuse=1, res_skew=0, pack=1, branch_par=1, use_graph=1, res_wide=1, res_cg2=4, pk_chan=32)
+DEFAULTS = dict(res_iss2=0, chain=0, fuse_branch=1, dual=1, cluster=1, narrow_par=0, post_rows=1, front_fuse=1, res_skew=0, pack=1, branch_par=1, use_graph=1, res_wide=1, res_cg2=4, pk_chan=32)
 samples = [[] for _ in settings]
 outs = [None] * len(settings)
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
