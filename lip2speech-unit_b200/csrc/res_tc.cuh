@@ -467,6 +467,9 @@ res_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
     int ib = 0;
     uint32_t pb = 0, ps = 0;
     int ntr = warp == 1 ? 0 : 128;     // trace stamps: the first issuer only
+    const bool count_waits = P.trace && blockIdx.x == 0 && warp == 1;   // trace build: cycles spent waiting for weights / for the epilogue
+    long long w_b = 0, w_s = 0;
+    const long long c_start = count_waits ? clock64() : 0;
     auto commit = [&](uint64_t* bar) { if constexpr (CG2) umma_commit_cg2(bar, (uint16_t)3); else umma_commit(bar); };
     for (int wk = (CG2 && crank != 0) ? walk_n : walk0; wk < walk_n; wk += walkers) {   // CTA pair: the leader issues for both
       for (int cv = 0; cv < 2 * g.n_dil; ++cv) {
@@ -475,14 +478,22 @@ res_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
         const int dil = second ? 1 : g.dil[st];
         const int halo = second ? g.h2 : g.h1[st];
         L2S_RTRACE(128, ntr);
-        mbar_wait(s_full, ps);
+        {
+          const long long c0 = count_waits ? clock64() : 0;
+          mbar_wait(s_full, ps);
+          if (count_waits) w_s += clock64() - c0;
+        }
         ps ^= 1u;
         tc_fence_after();
         L2S_RTRACE(128, ntr);
         const uint32_t a_tap0 = s_lo + (uint32_t)(g.pad - halo) * row_step;
         const uint32_t d_base = (second ? tmem_base : tmem_base + (uint32_t)acc_cols) + (uint32_t)(acc_first * g.c);   // c2 accumulates onto X, c1 onto its bias
         for (int ts = 0; ts < g.n_tstages; ++ts) {
-          mbar_wait(&b_full[ib], pb);
+          {
+            const long long c0 = count_waits ? clock64() : 0;
+            mbar_wait(&b_full[ib], pb);
+            if (count_waits) w_b += clock64() - c0;
+          }
           tc_fence_after();
           const uint32_t b_lo = desc_lo_fixed | ((smem_u32(stageB + (size_t)ib * g.bstage_bytes) & 0x3FFFFu) >> 4);
           const int t_end = min(g.tb, g.k - ts * g.tb);
@@ -496,6 +507,7 @@ res_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
         L2S_RTRACE(128, ntr);
       }
     }
+    if (count_waits && lane == 0) { P.trace[500] = w_b; P.trace[501] = w_s; P.trace[502] = clock64() - c_start; }
   } else {
     // ---------------------------------------------------------------- epilogue warps
     constexpr int CW = DUAL ? 16 : 32;
@@ -590,6 +602,7 @@ inline int g_res_cg2 = 4;   // whole-ResBlock plans run as CTA pairs issuing cta
 // kind: 0 = one CTA per SM (168 registers, 32-column epilogue chunks), 1 = two (80 registers, <= 112 KB, <= 256 TMEM
 // columns), 2 = four CTAs per SM with four epilogue warps each (<= 55 KB, <= 128 TMEM columns): more independent
 // tiles in flight for the MMA-light ResBlocks, whose epilogue warps otherwise idle while their own tile's MMAs run.
+inline int g_res_skew_iss2 = 1;  // knob res_skew_iss2: skewed plans with two granules and sixteen epilogue warps issue from one warp per granule
 inline int g_res_tb = 0;         // knob res_tb: cap on the taps per weight stage of the skewed schedule (0: as res_tc_kernel)
 inline int g_res_gmax = 0;       // knob res_gmax: cap on the stages of a head / tail group (0: half the ring)
 inline int g_res_ng = 2;         // knob res_ng: granules per tile of the skewed schedule (each with its own barrier pair)
@@ -626,7 +639,7 @@ inline bool res_plan_with(int c, int k, int n_dil, const int* dil, int lin, int 
   if (cols > (kind == 2 ? 128 : (dual ? 256 : 512))) return false;
   g.tmem_cols = cols;
   g.ne = kind == 2 ? 4 : ((kind == 0 && g_res_wide) ? 16 : kTcEpiWarps);
-  g.iss2 = (g.ne == 16 && g_res_iss2 && !skew && msub >= 2) ? 1 : 0;
+  g.iss2 = (g.ne == 16 && g_res_iss2 && !skew && msub >= 2) ? 1 : 0;   // skewed plans: decided below (an issuer per granule)
   g.ctas_per_sm = kind == 2 ? 4 : (dual ? 2 : 1);
   int tb = 1;
   while (tb < k && tb < 16 && (tb * 2) * c * g.rb <= 16384) tb *= 2;
@@ -651,6 +664,7 @@ inline bool res_plan_with(int c, int k, int n_dil, const int* dil, int lin, int 
     while ((msub / gmin) % ngr != 0) --ngr;
     g.ng = ngr;
     g.gran = msub / ngr;
+    g.iss2 = (g_res_skew_iss2 && ngr == 2 && g.ne == 16) ? 1 : 0;
   }
   const int fixed = 1024 + (skew ? 576 : 192) + 2 * kResMaxDil * 64 * 4 + g.ne * g.tile_words * 4 + (skew ? 2 : 1) * g.s_bytes;   // slack, barriers, biases, tiles, S
   const int budget = kind == 2 ? 55 * 1024 : (dual ? 112 * 1024 : 220 * 1024);

@@ -181,6 +181,52 @@ __device__ __forceinline__ void resq_issue_conv(const ResGeom& g, bool leader, u
   }
 }
 
+// One issuing warp per granule (g.iss2: two granules, warps 1 and 2 + ne).  With the phases overlapped, the epilogue warps of
+// the issuing warp's scheduler compete with it for issue slots and a single issuer fell to 52-54 cycles per N = 64 MMA (43 as a
+// CTA pair at the operand-fetch bound); with an issuer per granule the granule-outer walk disappears as well: each warp runs
+// stage-outer over ITS accumulators, waits for its own granule (and the one before it: taps left of the centre) up front and
+// for the next granule in front of the first stage that holds a tap right of the centre, and commits its granule's m_done.
+template <int C, bool CG2>
+__device__ __forceinline__ void resq_issue_conv_own(const ResGeom& g, int gran_idx, bool leader, uint32_t w0_lo, uint64_t* b_full,
+                                                    uint64_t* b_empty, uint64_t* ew, uint64_t* mc, uint32_t par, uint32_t desc_hi, uint32_t a_tap0,
+                                                    uint32_t tap_step, uint32_t d_base, int& ib, uint32_t& pb, long long* wcyc) {
+  const int ng = g.ng, nts = g.n_tstages, tb = g.tb, sbn = g.sb;
+  const uint32_t stage_step = (uint32_t)g.bstage_bytes >> 4;
+  const uint32_t a_g = a_tap0 + (uint32_t)(gran_idx * g.gran) * (uint32_t)(16 * C);
+  const uint32_t d_g = d_base + (uint32_t)(gran_idx * g.gran * C);
+  auto commit = [&](uint64_t* bar) { if (leader) { if constexpr (CG2) umma_commit_cg2(bar, (uint16_t)3); else umma_commit(bar); } };
+  {
+    const long long c0 = wcyc ? clock64() : 0;
+    mbar_wait(&ew[gran_idx], par);
+    if (gran_idx > 0) mbar_wait(&ew[gran_idx - 1], par);
+    for (int o = 0; o < ng; ++o)                              // every issuer sees every completion of every e_done barrier
+      if (o != gran_idx && o != gran_idx - 1 && o != gran_idx + 1) mbar_wait(&ew[o], par);
+    tc_fence_after();
+    if (wcyc) wcyc[1] += clock64() - c0;
+  }
+  bool next_ready = gran_idx + 1 >= ng;
+  const int first_right = ((g.k - 1) / 2 + 1) / tb;          // first stage with a tap right of the centre
+  for (int ts = 0; ts < nts; ++ts) {
+    {
+      const long long c0 = wcyc ? clock64() : 0;
+      mbar_wait(&b_full[ib], pb);
+      if (wcyc) wcyc[0] += clock64() - c0;
+    }
+    if (!next_ready && ts >= first_right) {
+      const long long c0 = wcyc ? clock64() : 0;
+      mbar_wait(&ew[gran_idx + 1], par);
+      next_ready = true;
+      if (wcyc) wcyc[1] += clock64() - c0;
+    }
+    tc_fence_after();
+    res_issue_stage<C, CG2>(leader, g.gran, desc_hi, a_g, tap_step, w0_lo + (uint32_t)ib * stage_step, ts * tb, min(tb, g.k - ts * tb), d_g);
+    commit(&b_empty[ib]);
+    if (++ib == sbn) { ib = 0; pb ^= 1u; }
+  }
+  if (!next_ready) { mbar_wait(&ew[gran_idx + 1], par); }     // k = 1: no tap right of the centre, the completion is still consumed
+  commit(&mc[gran_idx]);
+}
+
 template <int MODE, bool CG2, bool WIDE>
 __global__ void __maxnreg__(WIDE ? 96 : 168)
 resq_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
@@ -208,7 +254,7 @@ resq_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 2 * g.n_dil; ++i) tma_prefetch_desc(&maps.w[i]);
-    for (int i = 0; i < g.sb; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < g.sb; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], g.iss2 ? 2u : 1u); }
     for (int i = 0; i < 2 * kResqMaxGran; ++i) {
       mbar_init(&m_done[i], 1);
       mbar_init(&e_done[i], (uint32_t)(CG2 ? 2 * g.ne : g.ne));
@@ -285,8 +331,9 @@ resq_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
         }
       }
     }
-  } else if (warp == 1) {
-    // -------------------------------------------------------------- MMA issuer
+  } else if (warp == 1 || (g.iss2 && warp == 2 + g.ne)) {
+    // -------------------------------------------------------------- MMA issuer(s): iss2 = one warp per granule
+    const int my_gran = warp == 1 ? 0 : 1;
     const bool leader = elect_one();
     const uint64_t tmpl = umma_desc_template((uint32_t)g.rb);
     const uint32_t desc_hi = (uint32_t)(tmpl >> 32);
@@ -297,9 +344,9 @@ resq_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
     const uint32_t w0_lo = desc_lo_fixed | ((smem_u32(stageB) & 0x3FFFFu) >> 4);     // weight ring slot i: + i * (bstage_bytes >> 4)
     int ib = 0;
     uint32_t pb = 0, n1 = 0;
-    int ntr = 0;
+    int ntr = warp == 1 ? 0 : 128;
     long long wcyc[2] = {0, 0};
-    long long* wc = (P.trace && blockIdx.x == 0) ? wcyc : nullptr;
+    long long* wc = (P.trace && blockIdx.x == 0 && warp == 1) ? wcyc : nullptr;
     const long long cstart = clock64();
     for (int wk = (CG2 && crank != 0) ? walk_n : walk0; wk < walk_n; wk += walkers) {   // CTA pair: the leader issues for both
       for (int cv = 0; cv < 2 * g.n_dil; ++cv) {
@@ -313,6 +360,11 @@ resq_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
         const uint32_t d_base = second ? tmem_base : tmem_base + (uint32_t)acc_cols;   // c2 accumulates onto X, c1 onto its bias
         const uint32_t tap_step = (uint32_t)dil * row_step;
         L2S_RTRACE(128, ntr);
+        if (g.iss2) {
+          if (g.c == 64) resq_issue_conv_own<64, CG2>(g, my_gran, leader, w0_lo, b_full, b_empty, ew, mc, n1 & 1u, desc_hi, a_tap0, tap_step, d_base, ib, pb, wc);
+          else if (g.c == 32) resq_issue_conv_own<32, CG2>(g, my_gran, leader, w0_lo, b_full, b_empty, ew, mc, n1 & 1u, desc_hi, a_tap0, tap_step, d_base, ib, pb, wc);
+          else resq_issue_conv_own<16, CG2>(g, my_gran, leader, w0_lo, b_full, b_empty, ew, mc, n1 & 1u, desc_hi, a_tap0, tap_step, d_base, ib, pb, wc);
+        } else
         if (g.c == 64) resq_issue_conv<64, CG2>(g, leader, w0_lo, b_full, b_empty, ew, mc, n1 & 1u, desc_hi, a_tap0, tap_step, d_base, ib, pb, wc);
         else if (g.c == 32) resq_issue_conv<32, CG2>(g, leader, w0_lo, b_full, b_empty, ew, mc, n1 & 1u, desc_hi, a_tap0, tap_step, d_base, ib, pb, wc);
         else resq_issue_conv<16, CG2>(g, leader, w0_lo, b_full, b_empty, ew, mc, n1 & 1u, desc_hi, a_tap0, tap_step, d_base, ib, pb, wc);
@@ -458,7 +510,7 @@ inline cudaError_t launch_resq_mode(const ResParams& P, const ResMaps& maps, int
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3((unsigned)(64 + 32 * P.g.ne));
+  cfg.blockDim = dim3((unsigned)(64 + 32 * P.g.ne + (P.g.iss2 ? 32 : 0)));
   cfg.dynamicSmemBytes = (size_t)P.g.smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

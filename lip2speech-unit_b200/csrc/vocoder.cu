@@ -1464,6 +1464,7 @@ int l2s_debug_set(const char* key, int64_t value) {
   else if (k == "res_cg2") g_res_cg2 = (int)value;
   else if (k == "res_wide") g_res_wide = (int)value;
   else if (k == "res_iss2") g_res_iss2 = (int)value;
+  else if (k == "res_skew_iss2") g_res_skew_iss2 = (int)value;
   else if (k == "res_skew") g_res_skew = (int)value;
   else if (k == "res_ng") g_res_ng = (int)value;
   else if (k == "res_tb") g_res_tb = (int)value;

@@ -379,7 +379,8 @@ def test_whole_resblock_tilings_agree(pkg, weights, knob, value):
     assert torch.equal(a, b), float((a - b).abs().max())
 
 
-@pytest.mark.parametrize("extra", [{}, {"res_cg2": 0}, {"res_wide": 0}, {"res_ng": 4}, {"res_ng": 1}, {"res_msub": 2}, {"res_tb": 1, "res_gmax": 2}])
+@pytest.mark.parametrize("extra", [{}, {"res_cg2": 0}, {"res_wide": 0}, {"res_ng": 4}, {"res_ng": 1}, {"res_msub": 2}, {"res_tb": 1, "res_gmax": 2},
+                                   {"res_skew_iss2": 0}])
 @pytest.mark.parametrize("batch,frames", [(3, 150), (1, 34)])
 def test_skewed_resblock_schedule_is_bit_identical(pkg, weights, extra, batch, frames):
     """resq_tc.cuh (two S slabs, per-granule barriers, head / tail weight-stage groups walked granule by granule, the next
@@ -390,12 +391,13 @@ def test_skewed_resblock_schedule_is_bit_identical(pkg, weights, extra, batch, f
     code, mel, spkr = vo.synthetic_inputs(batch, frames, seed=33)
     g = make_gen(pkg, h, sds["trained"], "bf16")
     lib = pkg._cabi.load()
-    defaults = {"pack": 1, "res_mode": 0, "res_skew": 0, "res_cg2": 4, "res_wide": 1, "res_ng": 2, "res_msub": 8, "res_tb": 0, "res_gmax": 0}
+    defaults = {"pack": 1, "res_mode": 0, "res_skew": 0, "res_cg2": 4, "res_wide": 1, "res_ng": 2, "res_msub": 8, "res_tb": 0, "res_gmax": 0,
+                "res_skew_iss2": 1}
     try:
         lib.l2s_debug_set(b"pack", 0)             # tap-by-tap whole-ResBlock kernels on every narrow stage
         lib.l2s_debug_set(b"res_mode", 2)         # one CTA per SM everywhere: the plans the skewed schedule replaces
         for k, v in extra.items():
-            if k != "res_ng" and k != "res_tb" and k != "res_gmax":
+            if k not in ("res_ng", "res_tb", "res_gmax", "res_skew_iss2"):
                 lib.l2s_debug_set(k.encode(), v)
         a = g(code=code.to(DEV), mel=mel.to(DEV), spkr=spkr.to(DEV)).clone()
         lib.l2s_debug_set(b"res_skew", 1)

@@ -46,6 +46,7 @@ for launch in [int(a) for a in sys.argv[1:] if "=" not in a] or [0, 2, 6, 8]:
     if not e:
         print("launch", launch, "no stamps"); continue
     t0 = min(e[0], m[0])
+    print(f"  MMA warp cycles of CTA 0: waiting for weights {int(t[500])}, waiting for the epilogue warps {int(t[501])}, whole loop {int(t[502])}")
     print(f"whole-ResBlock launch {launch} (stage {2 + launch // 3}, branch {launch % 3}); us since first stamp")
     # epilogue stamps per item: start, x loaded, then per step: [wait A.., got d1, phase A done, (got x, phase B done)], final done
     per_item_e = 2 + n_dil * 3 + (n_dil - 1) * 2 + 1

@@ -24,7 +24,7 @@ def knobs(**kw):
         assert lib.l2s_debug_set(k.encode(), int(v)) == 0, k
 
 
-DEFAULT = dict(pack=0, res_mode=0, res_skew=0, res_cg2=4, res_wide=1, res_msub=8, use_graph=0, res_ng=2, res_tb=0, res_gmax=0, res_skew_pct=100)
+DEFAULT = dict(pack=0, res_mode=0, res_skew=0, res_cg2=4, res_wide=1, res_msub=8, use_graph=0, res_ng=2, res_tb=0, res_gmax=0, res_skew_pct=100, res_skew_iss2=1, res_iss2=0, max_nt=256, max_msub=8, tc_cg2=1)
 code, mel, spkr = (t.to(dev) for t in vo.synthetic_inputs(16, 400, seed=52))
 names = [f"C={c} k={k}" for c in (64, 32, 16) for k in (3, 7, 11)]
 ref = None
