@@ -664,7 +664,7 @@ inline bool res_plan_with(int c, int k, int n_dil, const int* dil, int lin, int 
     while ((msub / gmin) % ngr != 0) --ngr;
     g.ng = ngr;
     g.gran = msub / ngr;
-    g.iss2 = (g_res_skew_iss2 && ngr == 2 && g.ne == 16) ? 1 : 0;
+    g.iss2 = (g_res_skew_iss2 && ngr >= 2 && ngr % 2 == 0 && g.ne == 16) ? 1 : 0;
   }
   const int fixed = 1024 + (skew ? 576 : 192) + 2 * kResMaxDil * 64 * 4 + g.ne * g.tile_words * 4 + (skew ? 2 : 1) * g.s_bytes;   // slack, barriers, biases, tiles, S
   const int budget = kind == 2 ? 55 * 1024 : (dual ? 112 * 1024 : 220 * 1024);

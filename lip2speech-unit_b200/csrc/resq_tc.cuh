@@ -197,10 +197,9 @@ __device__ __forceinline__ void resq_issue_conv_own(const ResGeom& g, int gran_i
   auto commit = [&](uint64_t* bar) { if (leader) { if constexpr (CG2) umma_commit_cg2(bar, (uint16_t)3); else umma_commit(bar); } };
   {
     const long long c0 = wcyc ? clock64() : 0;
+    // (over its granules i, i + 2, ... an issuer waits for every e_done barrier at least once per conv: the parity waits stay meaningful)
     mbar_wait(&ew[gran_idx], par);
     if (gran_idx > 0) mbar_wait(&ew[gran_idx - 1], par);
-    for (int o = 0; o < ng; ++o)                              // every issuer sees every completion of every e_done barrier
-      if (o != gran_idx && o != gran_idx - 1 && o != gran_idx + 1) mbar_wait(&ew[o], par);
     tc_fence_after();
     if (wcyc) wcyc[1] += clock64() - c0;
   }
@@ -315,7 +314,9 @@ resq_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
             bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.acc_in + a0) + o, min(16384u, ab - o));
         }
       }
+      const int rounds = g.iss2 ? g.ng / 2 : 1;       // an issuer per granule: the conv's stages once per round of two granules
       for (int cv = 0; cv < 2 * g.n_dil; ++cv) {
+        for (int rd = 0; rd < rounds; ++rd)
         for (int ts = 0; ts < g.n_tstages; ++ts) {
           mbar_wait(&b_empty[ib], pb ^ 1u);
           if (leader) {
@@ -361,9 +362,14 @@ resq_tc_kernel(const __grid_constant__ ResMaps maps, const ResParams P) {
         const uint32_t tap_step = (uint32_t)dil * row_step;
         L2S_RTRACE(128, ntr);
         if (g.iss2) {
-          if (g.c == 64) resq_issue_conv_own<64, CG2>(g, my_gran, leader, w0_lo, b_full, b_empty, ew, mc, n1 & 1u, desc_hi, a_tap0, tap_step, d_base, ib, pb, wc);
-          else if (g.c == 32) resq_issue_conv_own<32, CG2>(g, my_gran, leader, w0_lo, b_full, b_empty, ew, mc, n1 & 1u, desc_hi, a_tap0, tap_step, d_base, ib, pb, wc);
-          else resq_issue_conv_own<16, CG2>(g, my_gran, leader, w0_lo, b_full, b_empty, ew, mc, n1 & 1u, desc_hi, a_tap0, tap_step, d_base, ib, pb, wc);
+          // ng / 2 rounds per conv: in round r this warp works on granule 2 r + my_gran, and the producer streams the conv's
+          // weight stages once per round (a few KB each from L2): granules finish, and are rewritten by the epilogue warps,
+          // round by round while the other round's MMAs run
+          for (int gi = my_gran; gi < g.ng; gi += 2) {
+            if (g.c == 64) resq_issue_conv_own<64, CG2>(g, gi, leader, w0_lo, b_full, b_empty, ew, mc, n1 & 1u, desc_hi, a_tap0, tap_step, d_base, ib, pb, wc);
+            else if (g.c == 32) resq_issue_conv_own<32, CG2>(g, gi, leader, w0_lo, b_full, b_empty, ew, mc, n1 & 1u, desc_hi, a_tap0, tap_step, d_base, ib, pb, wc);
+            else resq_issue_conv_own<16, CG2>(g, gi, leader, w0_lo, b_full, b_empty, ew, mc, n1 & 1u, desc_hi, a_tap0, tap_step, d_base, ib, pb, wc);
+          }
         } else
         if (g.c == 64) resq_issue_conv<64, CG2>(g, leader, w0_lo, b_full, b_empty, ew, mc, n1 & 1u, desc_hi, a_tap0, tap_step, d_base, ib, pb, wc);
         else if (g.c == 32) resq_issue_conv<32, CG2>(g, leader, w0_lo, b_full, b_empty, ew, mc, n1 & 1u, desc_hi, a_tap0, tap_step, d_base, ib, pb, wc);
